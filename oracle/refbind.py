@@ -1,0 +1,313 @@
+"""ctypes binding of the oracles -- TEST INFRASTRUCTURE (the checker), never the product path.
+
+Two shared objects live under oracle/:
+  * oracle/_ref/libref_oracle.so  -- the reference's OWN code (built by oracle/build_ref.sh from
+    /root/reference, git-ignored, travels to the GPU box as a prebuilt file)      kind="reference"
+  * oracle/libert_port.so         -- the C restatement oracle/er_port.c            kind="port"
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import lzma
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+ASSETS = os.path.join(ROOT, "assets", "classifier")
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def svm_model_path():
+    """OCR.model is shipped xz-compressed (16 MB of text); unpack once next to it."""
+    dst = os.path.join(ASSETS, "OCR.model")
+    if not os.path.exists(dst):
+        with lzma.open(dst + ".xz", "rb") as f, open(dst + ".tmp", "wb") as g:
+            g.write(f.read())
+        os.replace(dst + ".tmp", dst)
+    return dst
+
+
+DEFAULTS = dict(thresh_step=8, min_area=120, max_area=900000, stability_t=2, overlap_coef=0.7)
+
+
+class RefOracle:
+    """The reference's own ERFilter / CascadeBoost / libsvm code behind a C wrapper (oracle/ref_capi.cpp)."""
+
+    kind = "reference"
+
+    def __init__(self, with_svm=False, **params):
+        path = os.path.join(HERE, "_ref", "libref_oracle.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run oracle/build_ref.sh where /root/reference exists)")
+        L = self.L = C.CDLL(path)
+        p = dict(DEFAULTS); p.update(params); self.params = p
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int] * 4 + [C.c_double, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.ref_tree_extract.restype = C.c_void_p
+        L.ref_tree_extract.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int]
+        L.ref_tree_size.argtypes = [C.c_void_p]
+        L.ref_tree_dump.argtypes = [C.c_void_p, _i32p]
+        L.ref_nms.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_pool_indices.argtypes = [C.c_void_p, _i32p]
+        L.ref_classify.argtypes = [C.c_void_p, C.c_void_p, _i32p, _f64p, _f64p]
+        L.ref_tree_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_lbp_hist.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _f64p]
+        L.ref_aran.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.ref_resize.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.ref_divide.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
+        L.ref_cascade_predict.argtypes = [C.c_void_p, C.c_int, _f64p, C.c_int, C.c_int, _f64p]
+        L.ref_cascade_num_stumps.argtypes = [C.c_void_p, C.c_int]
+        L.ref_svm_nr_class.argtypes = [C.c_void_p]
+        L.ref_svm_total_sv.argtypes = [C.c_void_p]
+        L.ref_svm_labels.argtypes = [C.c_void_p, _i32p]
+        L.ref_svm_predict_probability.argtypes = [C.c_void_p, _f64p, C.c_int, C.c_int, C.c_int, _f64p, _f64p]
+        L.ref_detect_frames.restype = C.c_double
+        L.ref_detect_frames.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _f64p]
+        L.ref_channels.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        svm = svm_model_path().encode() if with_svm else None
+        self.ctx = L.ref_create(p["thresh_step"], p["min_area"], p["max_area"], p["stability_t"], p["overlap_coef"],
+                                os.path.join(ASSETS, "strong.classifier").encode(),
+                                os.path.join(ASSETS, "weak.classifier").encode(), svm)
+
+    def close(self):
+        if self.ctx:
+            self.L.ref_destroy(self.ctx)
+            self.ctx = None
+
+    # -- stage functions -------------------------------------------------------------------
+    def plane(self, plane, classify=True, scores=False):
+        """er_tree_extract -> nms -> classify on one u8 plane.
+        Returns dict(nodes[n,8]=level,area,x,y,w,h,parent,nchild (DFS preorder, reference child order),
+                     pool[m] node indices, label[m], strong_score, weak_score)."""
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        h, w = plane.shape
+        t = self.L.ref_tree_extract(self.ctx, _p(plane, _u8p), w, h, w)
+        n = self.L.ref_tree_size(t)
+        nodes = np.zeros((n, 8), np.int32)
+        self.L.ref_tree_dump(t, _p(nodes, _i32p))
+        m = self.L.ref_nms(self.ctx, t)
+        pool = np.zeros(m, np.int32)
+        self.L.ref_pool_indices(t, _p(pool, _i32p))
+        out = dict(nodes=nodes, pool=pool)
+        if classify:
+            label = np.zeros(m, np.int32)
+            ss = np.zeros(m, np.float64); ws = np.zeros(m, np.float64)
+            self.L.ref_classify(self.ctx, t, _p(label, _i32p), _p(ss, _f64p) if scores else None,
+                                _p(ws, _f64p) if scores else None)
+            out.update(label=label, strong_score=ss, weak_score=ws)
+        self.L.ref_tree_free(self.ctx, t)
+        return out
+
+    def channels(self, bgr):
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        h, w, _ = bgr.shape
+        out = np.zeros((6, h, w), np.uint8)
+        self.L.ref_channels(_p(bgr, _u8p), w, h, _p(out, _u8p))
+        return out
+
+    def lbp_hist(self, crop):
+        crop = np.ascontiguousarray(crop, dtype=np.uint8)
+        h, w = crop.shape
+        out = np.zeros(1024, np.float64)
+        self.L.ref_lbp_hist(self.ctx, _p(crop, _u8p), w, h, w, _p(out, _f64p))
+        return out
+
+    def aran(self, crop, L=26):
+        crop = np.ascontiguousarray(crop, dtype=np.uint8)
+        h, w = crop.shape
+        out = np.zeros((L, L), np.uint8)
+        self.L.ref_aran(self.ctx, _p(crop, _u8p), w, h, w, L, _p(out, _u8p))
+        return out
+
+    def resize(self, src, dw, dh):
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        h, w = src.shape
+        out = np.zeros((dh, dw), np.uint8)
+        self.L.ref_resize(_p(src, _u8p), w, h, w, dw, dh, _p(out, _u8p))
+        return out
+
+    def divide(self, vals, step):
+        vals = np.ascontiguousarray(vals, dtype=np.uint8)
+        out = np.zeros_like(vals)
+        self.L.ref_divide(_p(vals, _u8p), vals.size, step, _p(out, _u8p))
+        return out
+
+    def cascade_predict(self, which, fv):
+        fv = np.ascontiguousarray(fv, dtype=np.float64)
+        n, d = fv.shape
+        out = np.zeros(n, np.float64)
+        self.L.ref_cascade_predict(self.ctx, which, _p(fv, _f64p), n, d, _p(out, _f64p))
+        return out
+
+    def svm_predict_probability(self, x, nthreads=1):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n, d = x.shape
+        k = self.L.ref_svm_nr_class(self.ctx)
+        label = np.zeros(n, np.float64); prob = np.zeros((n, k), np.float64)
+        self.L.ref_svm_predict_probability(self.ctx, _p(x, _f64p), n, d, nthreads, _p(label, _f64p), _p(prob, _f64p))
+        return label, prob
+
+    def detect_frames(self, bgr, mode=1, nthreads=1):
+        """bgr [F,H,W,3] -> (wall seconds, counts[F,4]=kept,pool,strong,weak, stage seconds[3])."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        f, h, w, _ = bgr.shape
+        counts = np.zeros((f, 4), np.int32); st = np.zeros(3, np.float64)
+        sec = self.L.ref_detect_frames(self.ctx, _p(bgr, _u8p), f, w, h, mode, nthreads, _p(counts, _i32p), _p(st, _f64p))
+        return sec, counts, st
+
+
+class PortOracle:
+    """The C restatement (oracle/er_port.c).  Same call surface as RefOracle."""
+
+    kind = "port"
+
+    def __init__(self, with_svm=False, **params):
+        path = os.path.join(HERE, "libert_port.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle libert_port.so`)")
+        L = self.L = C.CDLL(path)
+        p = dict(DEFAULTS); p.update(params); self.params = p
+        L.port_channels.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
+        L.port_quantize.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
+        L.port_tree_extract.restype = C.c_void_p
+        L.port_tree_extract.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.port_tree_size.argtypes = [C.c_void_p]
+        L.port_tree_dump.argtypes = [C.c_void_p, _i32p]
+        L.port_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.port_pool_indices.argtypes = [C.c_void_p, _i32p]
+        L.port_tree_free.argtypes = [C.c_void_p]
+        L.port_resize.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.port_aran_minor.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.port_aran.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.port_lbp_hist.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _f64p]
+        L.port_cascade_load.restype = C.c_void_p
+        L.port_cascade_load.argtypes = [C.c_char_p]
+        L.port_cascade_info.argtypes = [C.c_void_p, _i32p, _i32p, _i32p]
+        L.port_cascade_predict_batch.argtypes = [C.c_void_p, _f64p, C.c_int, C.c_int, _f64p]
+        L.port_cascade_free.argtypes = [C.c_void_p]
+        L.port_classify.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_void_p, C.c_void_p, _i32p, _f64p, _f64p]
+        L.port_svm_load.restype = C.c_void_p
+        L.port_svm_load.argtypes = [C.c_char_p]
+        L.port_svm_info.argtypes = [C.c_void_p, _i32p, _i32p, _f64p, _i32p]
+        L.port_svm_dense_sv.argtypes = [C.c_void_p, C.c_int, _f64p]
+        L.port_svm_predict_probability.restype = C.c_double
+        L.port_svm_predict_probability.argtypes = [C.c_void_p, _f64p, C.c_int, _f64p, _f64p, _f64p]
+        L.port_svm_free.argtypes = [C.c_void_p]
+        L.port_canonical_nodes.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int]
+        self.casc = [L.port_cascade_load(os.path.join(ASSETS, "strong.classifier").encode()),
+                     L.port_cascade_load(os.path.join(ASSETS, "weak.classifier").encode())]
+        self.svm = L.port_svm_load(svm_model_path().encode()) if with_svm else None
+
+    def close(self):
+        for c in self.casc:
+            self.L.port_cascade_free(c)
+        self.casc = []
+        if self.svm:
+            self.L.port_svm_free(self.svm)
+            self.svm = None
+
+    def plane(self, plane, classify=True, scores=False):
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        h, w = plane.shape
+        p = self.params
+        t = self.L.port_tree_extract(_p(plane, _u8p), w, h, w, p["thresh_step"], p["min_area"])
+        n = self.L.port_tree_size(t)
+        nodes = np.zeros((n, 8), np.int32)
+        self.L.port_tree_dump(t, _p(nodes, _i32p))
+        m = self.L.port_nms(t, p["min_area"], p["max_area"], p["stability_t"], p["overlap_coef"])
+        pool = np.zeros(m, np.int32)
+        self.L.port_pool_indices(t, _p(pool, _i32p))
+        out = dict(nodes=nodes, pool=pool)
+        if classify:
+            label = np.zeros(m, np.int32)
+            ss = np.zeros(m, np.float64); ws = np.zeros(m, np.float64)
+            self.L.port_classify(t, _p(plane, _u8p), w, self.casc[0], self.casc[1], _p(label, _i32p), _p(ss, _f64p), _p(ws, _f64p))
+            out.update(label=label, strong_score=ss, weak_score=ws)
+        self.L.port_tree_free(t)
+        return out
+
+    def canonical_nodes(self, plane, min_area=None):
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        h, w = plane.shape
+        p = self.params
+        ma = p["min_area"] if min_area is None else min_area
+        cap = h * w + 8
+        out = np.zeros((cap, 6), np.int32)
+        n = self.L.port_canonical_nodes(_p(plane, _u8p), w, h, w, p["thresh_step"], ma, _p(out, _i32p), cap)
+        return out[:n].copy()
+
+    def channels(self, bgr):
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        h, w, _ = bgr.shape
+        out = np.zeros((6, h, w), np.uint8)
+        self.L.port_channels(_p(bgr, _u8p), w, h, w * 3, _p(out, _u8p))
+        return out
+
+    def quantize(self, vals, step):
+        vals = np.ascontiguousarray(vals, dtype=np.uint8)
+        out = np.zeros_like(vals)
+        self.L.port_quantize(_p(vals, _u8p), vals.size, step, _p(out, _u8p))
+        return out
+
+    def lbp_hist(self, crop):
+        crop = np.ascontiguousarray(crop, dtype=np.uint8)
+        h, w = crop.shape
+        out = np.zeros(1024, np.float64)
+        self.L.port_lbp_hist(_p(crop, _u8p), w, h, w, _p(out, _f64p))
+        return out
+
+    def aran(self, crop, L=26):
+        crop = np.ascontiguousarray(crop, dtype=np.uint8)
+        h, w = crop.shape
+        out = np.zeros((L, L), np.uint8)
+        self.L.port_aran(_p(crop, _u8p), w, h, w, L, _p(out, _u8p))
+        return out
+
+    def resize(self, src, dw, dh):
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        h, w = src.shape
+        out = np.zeros((dh, dw), np.uint8)
+        self.L.port_resize(_p(src, _u8p), w, h, w, dw, dh, _p(out, _u8p))
+        return out
+
+    def cascade_info(self, which):
+        ns = C.c_int32(0)
+        sl = np.zeros(64, np.int32); st = np.zeros(64, np.int32)
+        n = self.L.port_cascade_info(self.casc[which], C.byref(ns), _p(sl, _i32p), _p(st, _i32p))
+        return n, sl[:ns.value].copy(), st[:ns.value].copy()
+
+    def cascade_predict(self, which, fv):
+        fv = np.ascontiguousarray(fv, dtype=np.float64)
+        n, d = fv.shape
+        out = np.zeros(n, np.float64)
+        self.L.port_cascade_predict_batch(self.casc[which], _p(fv, _f64p), n, d, _p(out, _f64p))
+        return out
+
+    def svm_predict_probability(self, x, nthreads=1, want_kvalue=False):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n, d = x.shape
+        k = C.c_int32(0); l = C.c_int32(0)
+        self.L.port_svm_info(self.svm, C.byref(k), C.byref(l), None, None)
+        k, l = k.value, l.value
+        label = np.zeros(n, np.float64); prob = np.zeros((n, k), np.float64)
+        kv = np.zeros((n, l), np.float64) if want_kvalue else None
+        for i in range(n):
+            label[i] = self.L.port_svm_predict_probability(self.svm, _p(x[i], _f64p), d, _p(prob[i], _f64p),
+                                                           _p(kv[i], _f64p) if want_kvalue else None, None)
+        return (label, prob, kv) if want_kvalue else (label, prob)
+
+
+def best_oracle(**kw):
+    """The reference-backed oracle when its prebuilt .so is present, else the port."""
+    try:
+        return RefOracle(**kw)
+    except (FileNotFoundError, OSError):
+        return PortOracle(**kw)
