@@ -1,0 +1,159 @@
+/* ertext.h -- C ABI of libertext.so: the B200-native Extremal-Region detect + classify path.
+ *
+ * This is the drop-in boundary for the hot path of HsiehYiChia/Scene-text-recognition.  Every
+ * entry point names the reference interface (file:line in that repository) it replaces.  Plain
+ * pointers and sizes only; all buffers are caller owned unless stated; result views returned by
+ * the library stay valid until the next call on the same context.  Functions return 0 on
+ * success and a negative value on error (message via ert_last_error()); there is no CPU
+ * fallback -- without a CUDA device ert_create() fails.
+ *
+ * Thread model: one ert_ctx per host thread / CUDA stream (the reference calls its stage
+ * functions from 6 OpenMP threads on one ERFilter, src/ER.cpp:50-60; here the 6 planes of a frame
+ * are one batched launch instead).
+ */
+#ifndef ERTEXT_H
+#define ERTEXT_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERT_API __attribute__((visibility("default")))
+
+typedef struct ert_ctx ert_ctx;
+
+/* Constructor arguments of ERFilter (inc/ER.h:113, src/ER.cpp:14-19; defaults = inc/utils.h:6-11
+ * as passed by src/main.cpp:22). */
+typedef struct {
+	int thresh_step;      /* THRESH_STEP   8      (supported range 5..255) */
+	int min_area;         /* MIN_AREA      120    */
+	int max_area;         /* MAX_AREA      900000 */
+	int stability_t;      /* STABILITY_T   2      */
+	double overlap_coef;  /* OVERLAP_COEF  0.7    */
+	double min_ocr_prob;  /* MIN_OCR_PROB  0.15   (carried for the facade, unused on this path) */
+} ert_params;
+
+/* One tree node = the fields of `struct ER` (inc/ER.h:42-80) that the path produces:
+ * level, area (reference semantics: pixels + nodes of the subtree), bound, tree links.
+ * Nodes of a plane are stored in DFS pre-order, children in visiting order; `parent` indexes
+ * the same plane-local array (-1 for the root). */
+typedef struct {
+	int32_t level, area, x, y, w, h, parent, n_children;
+} ert_node;
+
+enum { ERT_LABEL_NONE = 0, ERT_LABEL_WEAK = 1, ERT_LABEL_STRONG = 2 };
+enum { ERT_CASCADE_STRONG = 0, ERT_CASCADE_WEAK = 1 };
+enum { ERT_STAGE_EXTRACT = 1, ERT_STAGE_NMS = 2, ERT_STAGE_CLASSIFY = 3 };
+
+/* Result of a batch: n_planes = 6 * n_frames for BGR input (plane order of
+ * ERFilter::compute_channels, src/ER.cpp:122-127: Y, Cr, Cb, 255-Y, 255-Cr, 255-Cb), or the
+ * number of planes given to ert_planes_detect.  Per plane p:
+ *   nodes      [node_offset[p] .. node_offset[p+1])      kept nodes  (root[] / the ER tree)
+ *   pool_*     [pool_offset[p] .. pool_offset[p+1])      NMS survivors in visiting order (pool[])
+ *   pool_node  index of the pooled node inside the plane's node range
+ *   pool_label ERT_LABEL_STRONG / WEAK / NONE             (strong[] / weak[] of classify)
+ *   pool_strong_score / pool_weak_score  CascadeBoost::predict return values (-DBL_MAX = rejected) */
+typedef struct {
+	int32_t n_planes;
+	int32_t width, height;
+	const int32_t *node_offset;     /* n_planes + 1 */
+	const ert_node *nodes;
+	const int32_t *pool_offset;     /* n_planes + 1 */
+	const int32_t *pool_node;
+	const int32_t *pool_label;
+	const double *pool_strong_score;
+	const double *pool_weak_score;
+	const uint8_t *pool_hist;       /* 1024 bins per pooled region, or NULL unless requested */
+	uint32_t status;                /* 0 = ok; bit flags on capacity overflow (see ert_status_string) */
+	/* device time per stage in milliseconds (CUDA events on the context's stream), mirroring
+	 * the reference's times[] of ERFilter::text_detect (src/ER.cpp:99-110):
+	 * [0] extract (incl. channels) [1] nms [2] classify [3] h2d [4] d2h [5] total */
+	double stage_ms[6];
+} ert_result;
+
+ERT_API int ert_abi_version(void);
+ERT_API const char *ert_last_error(void);
+ERT_API const char *ert_status_string(uint32_t status);
+
+/* new ERFilter(...)  (src/main.cpp:22).  device = CUDA ordinal. */
+ERT_API ert_ctx *ert_create(const ert_params *params, int device);
+ERT_API void ert_destroy(ert_ctx *ctx);
+/* ERFilter::set_thresh_step / set_min_area  (src/ER.cpp:21-30) */
+ERT_API int ert_set_thresh_step(ert_ctx *ctx, int step);
+ERT_API int ert_set_min_area(ert_ctx *ctx, int min_area);
+/* option: also return the 1024-bin histograms of pooled regions (costs a D2H copy) */
+ERT_API int ert_set_return_hist(ert_ctx *ctx, int on);
+/* option (debug / A-B): 0 = skip the shared-memory tile pass and link every edge in global memory */
+ERT_API int ert_set_tile_local_union(ert_ctx *ctx, int on);
+/* capacity hints (defaults: 16384 kept nodes and 2048 pooled regions per plane) */
+ERT_API int ert_set_capacity(ert_ctx *ctx, int kept_per_plane, int pool_per_plane);
+
+/* new CascadeBoost(path) -> CascadeBoost::load_classifier  (src/adaboost.cpp:498-501, 873-951).
+ * Parses the reference's text format byte-compatibly.  which = ERT_CASCADE_STRONG | _WEAK. */
+ERT_API int ert_load_cascade(ert_ctx *ctx, int which, const char *path);
+/* svm_load_model  (src/svm.cpp:2876; inc/svm.h:77).  c_svc + rbf probability models. */
+ERT_API int ert_load_svm(ert_ctx *ctx, const char *path);
+ERT_API int ert_svm_nr_class(ert_ctx *ctx);   /* svm_get_nr_class (inc/svm.h:81) */
+ERT_API int ert_svm_dims(ert_ctx *ctx);
+
+/* ---- the batched hot path ---------------------------------------------------------------
+ * ERFilter::text_detect up to and including classify (src/ER.cpp:33-60): compute_channels ->
+ * per plane er_tree_extract -> non_maximum_supression -> classify, for n_frames BGR frames
+ * (8-bit, 3 channels interleaved, row stride in bytes) in HOST memory.  upto = ERT_STAGE_*. */
+ERT_API int ert_detect_classify(ert_ctx *ctx, const uint8_t *bgr, int n_frames, int width, int height, int stride_bytes,
+                                int upto, const ert_result **out);
+/* Same, frames already resident on the device (device pointer); enqueue only. The result is
+ * fetched (one stream sync + small D2H) by ert_fetch_result. */
+ERT_API int ert_detect_classify_device(ert_ctx *ctx, const void *d_bgr, int n_frames, int width, int height, int stride_bytes, int upto);
+ERT_API int ert_fetch_result(ert_ctx *ctx, const ert_result **out);
+
+/* ERFilter::er_tree_extract(Mat) / non_maximum_supression / classify on caller-supplied
+ * single-channel planes (src/ER.cpp:240, 416, 507; inc/ER.h:125-127): n_planes images of the same
+ * size, plane k at planes + k*plane_stride_bytes, rows stride_bytes apart, host memory. */
+ERT_API int ert_planes_detect(ert_ctx *ctx, const uint8_t *planes, int n_planes, int width, int height, int stride_bytes,
+                              size_t plane_stride_bytes, int upto, const ert_result **out);
+
+/* ERFilter::non_maximum_supression(ER *root, ..., pool, input) on a caller tree (src/ER.cpp:416):
+ * nodes in DFS pre-order with the caller's child order (as ert_result delivers them, or as
+ * flattened from a reference ER* tree).  pool_out receives node indices in push order. */
+ERT_API int ert_nms_nodes(ert_ctx *ctx, const ert_node *nodes, int n_nodes, int width, int height, int32_t *pool_out, int pool_cap,
+                          int *n_pool);
+
+/* ERFilter::classify(pool, strong, weak, input) on caller rectangles (src/ER.cpp:507-528):
+ * rects = n x (x, y, w, h) inside the given plane.  Any of the outputs may be NULL. */
+ERT_API int ert_classify_regions(ert_ctx *ctx, const uint8_t *plane, int width, int height, int stride_bytes, const int32_t *rects, int n,
+                                 int32_t *label, double *strong_score, double *weak_score, uint8_t *hist1024);
+/* ERFilter::make_LBP_hist(input(rect), 2, 24)  (src/ER.cpp:789-816): hist = n x 1024 doubles */
+ERT_API int ert_lbp_hist(ert_ctx *ctx, const uint8_t *plane, int width, int height, int stride_bytes, const int32_t *rects, int n,
+                         double *hist);
+
+/* CascadeBoost::predict(vector<double> fv)  (src/adaboost.cpp:507-542) for n feature vectors of
+ * `dims` doubles each; score = predict's return value (-DBL_MAX when a stage rejects). */
+ERT_API int ert_cascade_predict_batch(ert_ctx *ctx, int which, const double *fv, int n, int dims, double *score);
+/* Both cascades on 1024-bin u8 histograms (the pipeline's own feature format), device-side sweep entry */
+ERT_API int ert_cascade_classify_u8(ert_ctx *ctx, const uint8_t *hist, int n, int32_t *label, double *strong_score, double *weak_score);
+
+/* svm_predict_probability(model, x, prob_estimates)  (src/svm.cpp:2592; inc/svm.h:88) for a batch:
+ * x = n dense rows of ert_svm_dims() doubles (zero = absent svm_node), label[n] = returned label,
+ * prob = n x nr_class.  The _u8 form takes features as k in 0..255 meaning k/255.0
+ * (OCR::extract_feature, src/OCR.cpp:203-218). */
+ERT_API int ert_svm_predict_probability_batch(ert_ctx *ctx, const double *x, int n, double *label, double *prob);
+ERT_API int ert_svm_predict_probability_batch_u8(ert_ctx *ctx, const uint8_t *x, int n, double *label, double *prob);
+
+/* ---- plumbing -------------------------------------------------------------------------------- */
+/* use an external CUDA stream (cudaStream_t as integer, e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */
+ERT_API int ert_set_stream(ert_ctx *ctx, uint64_t cuda_stream);
+ERT_API uint64_t ert_get_stream(ert_ctx *ctx);
+/* number of kernel launches issued by the last batch call (bench's gpu_launches) */
+ERT_API int ert_last_launch_count(ert_ctx *ctx);
+/* device-side benchmark helpers for the classifier sweeps (inputs generated/resident on device):
+ * time `iters` back-to-back launches with CUDA events; returns milliseconds per iteration. */
+ERT_API int ert_bench_cascade_u8(ert_ctx *ctx, const uint8_t *hist_host, int n, int iters, double *ms_per_iter);
+ERT_API int ert_bench_svm_u8(ert_ctx *ctx, const uint8_t *x_host, int n, int iters, double *ms_per_iter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERTEXT_H */

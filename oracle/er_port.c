@@ -335,6 +335,50 @@ PORT_API int port_nms(PTree *t, int min_area, int max_area, int stability_t, dou
 	return t->npool;
 }
 
+
+/* Re-order every child list by a canonical key (experiments on how well a traversal-independent
+ * sibling order reproduces the reference's NMS output).  mode:
+ *  1: descending (y0, x0)   2: descending (y1, x1)   3: descending seed pixel   4: ascending (y0,x0)
+ *  5: descending (y0,x0) after ascending level   6: reverse the reference order */
+typedef struct { long long k; int id; } SortEnt;
+static int sortent_cmp(const void *a, const void *b)
+{
+	const SortEnt *x = (const SortEnt *)a, *y = (const SortEnt *)b;
+	if (x->k != y->k) return x->k < y->k ? -1 : 1;
+	return x->id < y->id ? -1 : (x->id > y->id);
+}
+PORT_API void port_sort_children(PTree *t, int mode)
+{
+	SortEnt *tmp = (SortEnt *)malloc(sizeof(SortEnt) * (size_t)(t->n + 1));
+	for (int i = 0; i < t->n; i++) {
+		if (!t->nd[i].alive || t->nd[i].child < 0) continue;
+		int k = 0;
+		for (int c = t->nd[i].child; c >= 0; c = t->nd[c].next) {
+			const PNode *e = &t->nd[c];
+			long long key = 0;
+			switch (mode) {
+			case 1: key = -((long long)e->y0 * 100000 + e->x0); break;
+			case 2: key = -((long long)e->y1 * 100000 + e->x1); break;
+			case 3: key = -(long long)e->seed_pix; break;
+			case 4: key = ((long long)e->y0 * 100000 + e->x0); break;
+			case 5: key = (long long)e->level * 10000000000LL - ((long long)e->y0 * 100000 + e->x0); break;
+			case 6: key = -(long long)k; break;
+			case 7: key = -((long long)e->y1 * 100000 + e->x0); break;
+			case 8: key = -((long long)e->y0 * 100000 + e->x1); break;
+			case 9: /* the GPU path's canonical order: descending (y0, x0, level, area); x1,y1 below */
+				key = -((((long long)e->y0 * 8192 + e->x0) * 64 + e->level) * 4194304LL + (e->area & 4194303)); break;
+			default: key = k; break;
+			}
+			tmp[k].k = key; tmp[k].id = c; k++;
+		}
+		qsort(tmp, (size_t)k, sizeof(SortEnt), sortent_cmp);
+		t->nd[i].child = tmp[0].id;
+		for (int j = 0; j < k; j++) t->nd[tmp[j].id].next = (j + 1 < k) ? tmp[j + 1].id : -1;
+	}
+	free(tmp);
+	free(t->flat); free(t->flat_of); t->flat = NULL; t->flat_of = NULL;
+}
+
 PORT_API void port_pool_indices(PTree *t, int32_t *out)
 {
 	tree_flatten(t);

@@ -202,6 +202,7 @@ class PortOracle:
         L.port_svm_predict_probability.argtypes = [C.c_void_p, _f64p, C.c_int, _f64p, _f64p, _f64p]
         L.port_svm_free.argtypes = [C.c_void_p]
         L.port_canonical_nodes.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int]
+        L.port_sort_children.argtypes = [C.c_void_p, C.c_int]
         self.casc = [L.port_cascade_load(os.path.join(ASSETS, "strong.classifier").encode()),
                      L.port_cascade_load(os.path.join(ASSETS, "weak.classifier").encode())]
         self.svm = L.port_svm_load(svm_model_path().encode()) if with_svm else None
@@ -214,11 +215,15 @@ class PortOracle:
             self.L.port_svm_free(self.svm)
             self.svm = None
 
-    def plane(self, plane, classify=True, scores=False):
+    def plane(self, plane, classify=True, scores=False, canonical_order=False):
+        """canonical_order=True re-orders every child list the way the GPU path visits siblings
+        (descending bbox.y, bbox.x, level, area) before NMS -- the order-independent statement of the path."""
         plane = np.ascontiguousarray(plane, dtype=np.uint8)
         h, w = plane.shape
         p = self.params
         t = self.L.port_tree_extract(_p(plane, _u8p), w, h, w, p["thresh_step"], p["min_area"])
+        if canonical_order:
+            self.L.port_sort_children(t, 9)
         n = self.L.port_tree_size(t)
         nodes = np.zeros((n, 8), np.int32)
         self.L.port_tree_dump(t, _p(nodes, _i32p))

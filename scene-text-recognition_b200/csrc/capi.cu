@@ -1,0 +1,830 @@
+// capi.cu -- the C ABI of libertext.so (include/ertext.h): context, model-file parsers,
+// workspace management and the batched orchestration of the kernels.  C++ host code, no torch,
+// no CPU implementation of the path: every entry point fails if the CUDA device is unavailable.
+#include "../../include/ertext.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+
+namespace ert {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// result compaction: per-plane fixed-capacity device arrays -> contiguous host-mapped arrays
+// ---------------------------------------------------------------------------------------------
+__global__ void k_compact_results(int n_planes, int node_cap, int pool_cap, const int32_t *__restrict__ counts,
+                                  const OutNode *__restrict__ nodes, const int32_t *__restrict__ pool, const int32_t *__restrict__ label,
+                                  const double *__restrict__ ss, const double *__restrict__ ws, const uint8_t *__restrict__ hist,
+                                  int32_t *__restrict__ h_node_off, int32_t *__restrict__ h_pool_off, OutNode *__restrict__ h_nodes,
+                                  int32_t *__restrict__ h_pool, int32_t *__restrict__ h_label, double *__restrict__ h_ss,
+                                  double *__restrict__ h_ws, uint8_t *__restrict__ h_hist, int with_labels)
+{
+	const int plane = blockIdx.x;
+	int noff = 0, poff = 0;
+	for (int p = 0; p < plane; p++) { noff += counts[2 * p]; poff += counts[2 * p + 1]; }
+	const int nn = counts[2 * plane], np = counts[2 * plane + 1];
+	if (threadIdx.x == 0) {
+		h_node_off[plane] = noff; h_pool_off[plane] = poff;
+		if (plane == n_planes - 1) { h_node_off[n_planes] = noff + nn; h_pool_off[n_planes] = poff + np; }
+	}
+	const uint4 *src = reinterpret_cast<const uint4 *>(nodes + (size_t)plane * node_cap);
+	uint4 *dst = reinterpret_cast<uint4 *>(h_nodes + noff);
+	for (int i = threadIdx.x; i < nn * 2; i += blockDim.x) dst[i] = src[i];
+	for (int i = threadIdx.x; i < np; i += blockDim.x) {
+		const size_t s = (size_t)plane * pool_cap + i;
+		h_pool[poff + i] = pool[s];
+		if (with_labels) { h_label[poff + i] = label[s]; h_ss[poff + i] = ss[s]; h_ws[poff + i] = ws[s]; }
+		else { h_label[poff + i] = 0; h_ss[poff + i] = 0.0; h_ws[poff + i] = 0.0; }
+	}
+	if (h_hist && with_labels) {
+		const uint32_t *hs = reinterpret_cast<const uint32_t *>(hist + (size_t)plane * pool_cap * 1024);
+		uint32_t *hd = reinterpret_cast<uint32_t *>(h_hist + (size_t)poff * 1024);
+		for (int i = threadIdx.x; i < np * 256; i += blockDim.x) hd[i] = hs[i];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side model tables
+// ---------------------------------------------------------------------------------------------
+struct CascadeHost {
+	std::vector<int> stage_len, stage_thr;
+	std::vector<Stump> stumps;
+	bool loaded = false;
+	Stump *d_stumps = nullptr;
+	int *d_len = nullptr, *d_thr = nullptr;
+	CascadeDev dev() const { CascadeDev c; c.stumps = d_stumps; c.stage_len = d_len; c.stage_thr = d_thr; c.n_stages = (int)stage_len.size(); return c; }
+};
+
+struct SvmHost {
+	bool loaded = false;
+	int nr_class = 0, l = 0, dims = 0;
+	double gamma = 0;
+	std::vector<double> rho, probA, probB, coef, sv;
+	std::vector<int> label, nsv, start;
+	double *d_sv = nullptr, *d_coef = nullptr, *d_rho = nullptr, *d_probA = nullptr, *d_probB = nullptr;
+	int *d_label = nullptr, *d_nsv = nullptr, *d_start = nullptr;
+	SvmDev dev() const
+	{
+		SvmDev m; m.nr_class = nr_class; m.l = l; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef;
+		m.rho = d_rho; m.probA = d_probA; m.probB = d_probB; m.label = d_label; m.nsv = d_nsv; m.start = d_start;
+		return m;
+	}
+};
+
+template <typename T>
+static int dev_upload(T **dptr, const std::vector<T> &v)
+{
+	if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+	if (v.empty()) return 0;
+	ERT_CUDA_CHECK(cudaMalloc((void **)dptr, sizeof(T) * v.size()));
+	ERT_CUDA_CHECK(cudaMemcpy(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+struct Scratch {
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes)
+	{
+		if (bytes <= cap) return 0;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		ERT_CUDA_CHECK(cudaMalloc(&p, bytes));
+		cap = bytes;
+		return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+} // namespace ert
+
+using namespace ert;
+
+struct ert_ctx {
+	ert_params prm;
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = true;
+	cudaEvent_t ev[8];
+	int local_union = 1;
+	int return_hist = 0;
+	int kept_cap = 16384, pool_cap = 2048;
+	int launches = 0;
+
+	CascadeHost casc[2];
+	SvmHost svm;
+	uint8_t aran_tbl_h[64];
+	uint8_t *d_aran_tbl = nullptr;
+
+	// workspace geometry
+	int W = 0, H = 0, pitch = 0, planes_cap = 0, frames_cap = 0;
+	uint8_t *d_bgr = nullptr; size_t bgr_cap = 0;
+	uint8_t *d_ycc = nullptr;          // frames_cap*3 planes (BGR mode) or planes_cap planes (plane mode)
+	size_t ycc_bytes = 0;
+	PlaneSrc *d_planes = nullptr;
+	ExtractWork wk{};
+	uint8_t *d_nms_scratch = nullptr; size_t nms_stride = 0;
+	OutNode *d_out_nodes = nullptr;
+	int32_t *d_out_pool = nullptr, *d_out_counts = nullptr, *d_label = nullptr;
+	double *d_ss = nullptr, *d_ws = nullptr;
+	uint8_t *d_hist = nullptr;
+	// host-mapped result buffers
+	int32_t *h_node_off = nullptr, *h_pool_off = nullptr, *h_pool = nullptr, *h_label = nullptr;
+	OutNode *h_nodes = nullptr;
+	double *h_ss = nullptr, *h_ws = nullptr;
+	uint8_t *h_hist = nullptr;
+	uint32_t *h_status = nullptr;
+	ert_result res{};
+	int pending_planes = 0, pending_upto = 0;
+	bool pending = false;
+
+	Scratch s0, s1, s2, s3, s4;
+};
+
+namespace {
+
+void free_workspace(ert_ctx *c)
+{
+	cudaFree(c->d_ycc); cudaFree(c->d_planes);
+	cudaFree(c->wk.par); cudaFree(c->wk.attr); cudaFree(c->wk.node_list); cudaFree(c->wk.node_count);
+	cudaFree(c->wk.reach_root); cudaFree(c->wk.lone_level); cudaFree(c->wk.kept); cudaFree(c->wk.kept_count); cudaFree(c->wk.status);
+	cudaFree(c->d_nms_scratch); cudaFree(c->d_out_nodes); cudaFree(c->d_out_pool); cudaFree(c->d_out_counts); cudaFree(c->d_label);
+	cudaFree(c->d_ss); cudaFree(c->d_ws); cudaFree(c->d_hist);
+	cudaFreeHost(c->h_node_off); cudaFreeHost(c->h_pool_off); cudaFreeHost(c->h_pool); cudaFreeHost(c->h_label);
+	cudaFreeHost(c->h_nodes); cudaFreeHost(c->h_ss); cudaFreeHost(c->h_ws); cudaFreeHost(c->h_hist); cudaFreeHost(c->h_status);
+	c->d_ycc = nullptr; c->d_planes = nullptr; c->wk = ExtractWork{};
+	c->d_nms_scratch = nullptr; c->d_out_nodes = nullptr; c->d_out_pool = nullptr; c->d_out_counts = nullptr; c->d_label = nullptr;
+	c->d_ss = c->d_ws = nullptr; c->d_hist = nullptr;
+	c->h_node_off = c->h_pool_off = c->h_pool = c->h_label = nullptr; c->h_nodes = nullptr; c->h_ss = c->h_ws = nullptr;
+	c->h_hist = nullptr; c->h_status = nullptr;
+	c->planes_cap = 0; c->frames_cap = 0; c->W = c->H = 0;
+}
+
+template <typename T>
+int hmalloc(T **p, size_t n)
+{
+	ERT_CUDA_CHECK(cudaHostAlloc((void **)p, sizeof(T) * std::max<size_t>(n, 1), cudaHostAllocMapped));
+	return 0;
+}
+template <typename T>
+int dmalloc(T **p, size_t n)
+{
+	ERT_CUDA_CHECK(cudaMalloc((void **)p, sizeof(T) * std::max<size_t>(n, 1)));
+	return 0;
+}
+
+// (re)allocate everything that depends on (n_planes, W, H)
+int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
+{
+	if (W == c->W && H == c->H && n_planes <= c->planes_cap) return 0;
+	if (W < 1 || H < 1 || (long long)W * H > (1ll << KEY_IDX_BITS) || W > 8191 || H > 8191) {
+		set_error("unsupported plane size %dx%d (max 8191 per side, %d pixels)", W, H, 1 << KEY_IDX_BITS);
+		return -1;
+	}
+	const int keep_planes = std::max(n_planes, (W == c->W && H == c->H) ? c->planes_cap : 0);
+	free_workspace(c);
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	c->W = W; c->H = H; c->pitch = extract_pitch(W);
+	const int P = keep_planes;
+	const size_t N = (size_t)W * H;
+	c->ycc_bytes = (size_t)c->pitch * H;
+	if (dmalloc(&c->d_ycc, c->ycc_bytes * P + 256)) return -1;
+	ERT_CUDA_CHECK(cudaMemset(c->d_ycc, 0, c->ycc_bytes * P + 256));
+	if (dmalloc(&c->d_planes, (size_t)P)) return -1;
+	if (dmalloc(&c->wk.par, N * P) || dmalloc(&c->wk.attr, N * P) || dmalloc(&c->wk.node_list, N * P)) return -1;
+	if (dmalloc(&c->wk.node_count, (size_t)P) || dmalloc(&c->wk.reach_root, (size_t)P) || dmalloc(&c->wk.lone_level, (size_t)P)) return -1;
+	if (dmalloc(&c->wk.kept, (size_t)P * c->kept_cap) || dmalloc(&c->wk.kept_count, (size_t)P) || dmalloc(&c->wk.status, 1)) return -1;
+	ERT_CUDA_CHECK(cudaMemset(c->wk.status, 0, sizeof(uint32_t)));
+	c->wk.node_blocks = 32;
+	c->nms_stride = nms_scratch_stride(c->kept_cap);
+	if (dmalloc(&c->d_nms_scratch, c->nms_stride * P)) return -1;
+	if (dmalloc(&c->d_out_nodes, (size_t)P * c->kept_cap) || dmalloc(&c->d_out_pool, (size_t)P * c->pool_cap)) return -1;
+	if (dmalloc(&c->d_out_counts, (size_t)2 * P) || dmalloc(&c->d_label, (size_t)P * c->pool_cap)) return -1;
+	if (dmalloc(&c->d_ss, (size_t)P * c->pool_cap) || dmalloc(&c->d_ws, (size_t)P * c->pool_cap)) return -1;
+	if (dmalloc(&c->d_hist, (size_t)P * c->pool_cap * 1024)) return -1;
+	if (hmalloc(&c->h_node_off, (size_t)P + 1) || hmalloc(&c->h_pool_off, (size_t)P + 1)) return -1;
+	if (hmalloc(&c->h_nodes, (size_t)P * c->kept_cap) || hmalloc(&c->h_pool, (size_t)P * c->pool_cap)) return -1;
+	if (hmalloc(&c->h_label, (size_t)P * c->pool_cap) || hmalloc(&c->h_ss, (size_t)P * c->pool_cap) || hmalloc(&c->h_ws, (size_t)P * c->pool_cap)) return -1;
+	if (hmalloc(&c->h_hist, (size_t)P * c->pool_cap * 1024) || hmalloc(&c->h_status, 1)) return -1;
+	c->planes_cap = P;
+	return 0;
+}
+
+int set_plane_table(ert_ctx *c, int n_planes, bool bgr_mode)
+{
+	std::vector<PlaneSrc> t((size_t)n_planes);
+	for (int p = 0; p < n_planes; p++) {
+		if (bgr_mode) {
+			const int f = p / 6, ch = p % 6;
+			t[p].src = c->d_ycc + ((size_t)f * 3 + (ch % 3)) * c->ycc_bytes;
+			t[p].invert = ch >= 3;
+		} else {
+			t[p].src = c->d_ycc + (size_t)p * c->ycc_bytes;
+			t[p].invert = 0;
+		}
+	}
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->d_planes, t.data(), sizeof(PlaneSrc) * n_planes, cudaMemcpyHostToDevice, c->stream));
+	// the table is tiny; make the pageable staging copy safe before `t` dies
+	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+ExtractParams make_extract_params(const ert_ctx *c, int n_planes)
+{
+	ExtractParams P;
+	P.W = c->W; P.H = c->H; P.pitch = c->pitch; P.n_planes = n_planes;
+	P.hi = 255 / c->prm.thresh_step + 1;
+	P.qscale = (float)(1.0 / (double)c->prm.thresh_step);
+	P.min_area = c->prm.min_area;
+	P.kept_cap = c->kept_cap;
+	return P;
+}
+
+NmsParams make_nms_params(const ert_ctx *c, int W, int H)
+{
+	NmsParams P;
+	P.W = W; P.H = H; P.N = (size_t)W * H;
+	P.kept_cap = c->kept_cap; P.pool_cap = c->pool_cap;
+	P.min_area = c->prm.min_area; P.max_area = c->prm.max_area; P.stability_t = c->prm.stability_t;
+	P.overlap_coef = c->prm.overlap_coef;
+	return P;
+}
+
+// planes already in d_ycc + plane table set: run extract -> nms -> classify -> compaction (all async)
+int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
+{
+	cudaStream_t st = c->stream;
+	const ExtractParams EP = make_extract_params(c, n_planes);
+	if (launch_extract(EP, c->d_planes, c->wk, c->local_union, st)) return -1;
+	c->launches += 6;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[2], st));
+	const NmsParams NP = make_nms_params(c, c->W, c->H);
+	if (launch_nms(NP, n_planes, c->wk.kept, c->wk.kept_count, c->wk.attr, c->wk.reach_root, c->wk.lone_level, nullptr, nullptr,
+	               c->d_nms_scratch, c->nms_stride, c->d_out_nodes, c->d_out_pool, c->d_out_counts, c->wk.status, st)) return -1;
+	c->launches += 1;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[3], st));
+	const bool do_classify = upto >= ERT_STAGE_CLASSIFY;
+	if (do_classify) {
+		if (!c->casc[0].loaded || !c->casc[1].loaded) { set_error("classify requested but cascades are not loaded"); return -1; }
+		ClassifyParams CP; CP.pitch = c->pitch; CP.pool_cap = c->pool_cap; CP.node_cap = c->kept_cap;
+		if (launch_lbp_hist(CP, n_planes, c->d_planes, c->d_out_nodes, c->d_out_pool, c->d_out_counts, c->d_aran_tbl, c->d_hist, st)) return -1;
+		if (launch_cascade_u8(c->d_hist, 1024, n_planes * c->pool_cap, c->d_out_counts, c->pool_cap, c->casc[0].dev(), c->casc[1].dev(),
+		                      c->d_label, c->d_ss, c->d_ws, st)) return -1;
+		c->launches += 2;
+	}
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
+	k_compact_results<<<n_planes, 256, 0, st>>>(n_planes, c->kept_cap, c->pool_cap, c->d_out_counts, c->d_out_nodes, c->d_out_pool, c->d_label,
+	                                           c->d_ss, c->d_ws, c->d_hist, c->h_node_off, c->h_pool_off, c->h_nodes, c->h_pool, c->h_label,
+	                                           c->h_ss, c->h_ws, (c->return_hist && do_classify) ? c->h_hist : nullptr, do_classify ? 1 : 0);
+	ERT_CUDA_CHECK(cudaGetLastError());
+	c->launches += 1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->wk.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[5], st));
+	c->pending = true; c->pending_planes = n_planes; c->pending_upto = upto;
+	return 0;
+}
+
+int finish_result(ert_ctx *c, const ert_result **out)
+{
+	if (!c->pending) { set_error("no batch in flight"); return -1; }
+	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	c->pending = false;
+	ert_result &r = c->res;
+	r.n_planes = c->pending_planes; r.width = c->W; r.height = c->H;
+	r.node_offset = c->h_node_off; r.nodes = reinterpret_cast<const ert_node *>(c->h_nodes);
+	r.pool_offset = c->h_pool_off; r.pool_node = c->h_pool; r.pool_label = c->h_label;
+	r.pool_strong_score = c->h_ss; r.pool_weak_score = c->h_ws;
+	r.pool_hist = (c->return_hist && c->pending_upto >= ERT_STAGE_CLASSIFY) ? c->h_hist : nullptr;
+	r.status = *c->h_status;
+	float ms;
+	auto el = [&](int a, int b) { ms = 0.f; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return (double)ms; };
+	r.stage_ms[3] = el(0, 1); r.stage_ms[0] = el(1, 2); r.stage_ms[1] = el(2, 3); r.stage_ms[2] = el(3, 4); r.stage_ms[4] = el(4, 5);
+	r.stage_ms[5] = el(0, 5);
+	if (r.status & ERR_LOOP_GUARD) { set_error("device loop guard tripped (internal error)"); return -2; }
+	if (out) *out = &r;
+	return 0;
+}
+
+int check_cuda_device(int device)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) { set_error("no CUDA device available (%s): libertext has no CPU path", cudaGetErrorString(e)); return -1; }
+	if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return -1; }
+	return 0;
+}
+
+void build_aran_table(ert_ctx *c)
+{
+	// for minor = (int)(L * pow(R1, 0.5)) when L*sqrt(R1) is an exact integer m: what does libm give?
+	const int L = 26;
+	for (int m = 0; m < 64; m++) c->aran_tbl_h[m] = (uint8_t)std::min(m, L);
+	for (int m = 1; m <= L; m++) {
+		long long p = (long long)m * m, q = (long long)L * L, a = p, b = q;
+		while (b) { long long t = a % b; a = b; b = t; }
+		p /= a; q /= a;
+		const double R1 = (double)p / (double)q;
+		c->aran_tbl_h[m] = (uint8_t)(int)(L * pow(R1, 0.5));
+	}
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int ert_abi_version(void) { return 1; }
+const char *ert_last_error(void) { return g_err; }
+
+const char *ert_status_string(uint32_t s)
+{
+	static thread_local char buf[256];
+	buf[0] = 0;
+	if (!s) return "ok";
+	if (s & ERR_LOOP_GUARD) strcat(buf, "loop-guard ");
+	if (s & ERR_KEPT_OVERFLOW) strcat(buf, "kept-overflow ");
+	if (s & ERR_POOL_OVERFLOW) strcat(buf, "pool-overflow ");
+	if (s & ERR_NMS_OVERFLOW) strcat(buf, "nms-overflow ");
+	return buf;
+}
+
+ert_ctx *ert_create(const ert_params *params, int device)
+{
+	if (check_cuda_device(device)) return nullptr;
+	if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return nullptr; }
+	ert_ctx *c = new ert_ctx();
+	if (params) c->prm = *params;
+	else { c->prm.thresh_step = 8; c->prm.min_area = 120; c->prm.max_area = 900000; c->prm.stability_t = 2; c->prm.overlap_coef = 0.7; c->prm.min_ocr_prob = 0.15; }
+	if (c->prm.thresh_step < 5 || c->prm.thresh_step > 255) { set_error("thresh_step %d unsupported (5..255)", c->prm.thresh_step); delete c; return nullptr; }
+	c->device = device;
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); delete c; return nullptr; }
+	for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
+	build_aran_table(c);
+	if (cudaMalloc((void **)&c->d_aran_tbl, 64) != cudaSuccess || cudaMemcpy(c->d_aran_tbl, c->aran_tbl_h, 64, cudaMemcpyHostToDevice) != cudaSuccess) {
+		set_error("aran table upload failed"); delete c; return nullptr;
+	}
+	return c;
+}
+
+void ert_destroy(ert_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	free_workspace(c);
+	cudaFree(c->d_bgr); cudaFree(c->d_aran_tbl);
+	for (int k = 0; k < 2; k++) { cudaFree(c->casc[k].d_stumps); cudaFree(c->casc[k].d_len); cudaFree(c->casc[k].d_thr); }
+	cudaFree(c->svm.d_sv); cudaFree(c->svm.d_coef); cudaFree(c->svm.d_rho); cudaFree(c->svm.d_probA); cudaFree(c->svm.d_probB);
+	cudaFree(c->svm.d_label); cudaFree(c->svm.d_nsv); cudaFree(c->svm.d_start);
+	c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
+	for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int ert_set_thresh_step(ert_ctx *c, int step)
+{
+	if (step < 5 || step > 255) { set_error("thresh_step %d unsupported (5..255)", step); return -1; }
+	c->prm.thresh_step = step; return 0;
+}
+int ert_set_min_area(ert_ctx *c, int m) { c->prm.min_area = m; return 0; }
+int ert_set_return_hist(ert_ctx *c, int on) { c->return_hist = on; return 0; }
+int ert_set_tile_local_union(ert_ctx *c, int on) { c->local_union = on ? 1 : 0; return 0; }
+int ert_set_capacity(ert_ctx *c, int kept, int pool)
+{
+	if (kept < 16 || pool < 16 || kept > (1 << 22)) { set_error("bad capacity"); return -1; }
+	cudaStreamSynchronize(c->stream);
+	free_workspace(c);
+	c->kept_cap = kept; c->pool_cap = pool;
+	return 0;
+}
+
+int ert_set_stream(ert_ctx *c, uint64_t s)
+{
+	cudaStreamSynchronize(c->stream);
+	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	if (s == 0) { c->own_stream = true; if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return -1; } }
+	else { c->own_stream = false; c->stream = (cudaStream_t)(uintptr_t)s; }
+	return 0;
+}
+uint64_t ert_get_stream(ert_ctx *c) { return (uint64_t)(uintptr_t)c->stream; }
+int ert_last_launch_count(ert_ctx *c) { return c->launches; }
+
+// ---- model files --------------------------------------------------------------------------------
+int ert_load_cascade(ert_ctx *c, int which, const char *path)
+{
+	if (which < 0 || which > 1) { set_error("bad cascade id"); return -1; }
+	std::ifstream fin(path);
+	if (!fin.is_open()) { set_error("Error: %s is not opened!!", path); return -1; }
+	CascadeHost &h = c->casc[which];
+	h.stage_len.clear(); h.stage_thr.clear(); h.stumps.clear(); h.loaded = false;
+	std::string tok;
+	bool real = true;
+	fin >> tok;
+	if (tok == "boost_type") { fin >> tok; real = (tok != "DISCRETE"); fin >> tok; }
+	if (tok == "base_type") { fin >> tok; fin >> tok; }
+	if (tok == "num_of_iter") {
+		while (fin >> tok) {
+			char *e = nullptr;
+			const double v = strtod(tok.c_str(), &e);
+			if (e == tok.c_str()) break;     // first non-numeric token ends the list ("threshold")
+			h.stage_len.push_back((int)v);
+		}
+	}
+	if (tok == "threshold") {
+		for (size_t j = 0; j < h.stage_len.size(); j++) { fin >> tok; h.stage_thr.push_back((int)strtod(tok.c_str(), nullptr)); }
+	}
+	if (!real) { set_error("%s: only REAL cascades of decision stumps are supported on the device path", path); return -1; }
+	std::string line;
+	std::getline(fin, line);
+	while (std::getline(fin, line)) {
+		const char *s = line.c_str();
+		char *e;
+		double v[5];
+		int k = 0;
+		while (k < 5) { v[k] = strtod(s, &e); if (e == s) break; s = e; k++; }
+		if (k < 5) continue;
+		Stump st; st.dim = (int)v[1]; st.thr = v[2]; st.cp = v[3]; st.cn = v[4]; st.pad = 0;
+		h.stumps.push_back(st);
+	}
+	int total = 0;
+	for (int n : h.stage_len) total += n;
+	if (h.stage_len.empty() || h.stage_thr.size() != h.stage_len.size() || total != (int)h.stumps.size()) {
+		set_error("%s: malformed cascade (stages %zu, thresholds %zu, stumps %zu, expected %d)", path, h.stage_len.size(), h.stage_thr.size(), h.stumps.size(), total);
+		return -1;
+	}
+	for (const Stump &st : h.stumps) if (st.dim < 0 || st.dim >= 1024) { set_error("%s: stump dimension %d outside the 1024-bin feature", path, st.dim); return -1; }
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	if (dev_upload(&h.d_stumps, h.stumps) || dev_upload(&h.d_len, h.stage_len) || dev_upload(&h.d_thr, h.stage_thr)) return -1;
+	h.loaded = true;
+	return (int)h.stumps.size();
+}
+
+int ert_load_svm(ert_ctx *c, const char *path)
+{
+	FILE *f = fopen(path, "rb");
+	if (!f) { set_error("can't open model file %s", path); return -1; }
+	fseek(f, 0, SEEK_END); const long sz = ftell(f); fseek(f, 0, SEEK_SET);
+	std::vector<char> txt((size_t)sz + 1);
+	if (fread(txt.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); set_error("short read on %s", path); return -1; }
+	fclose(f); txt[sz] = 0;
+	SvmHost &m = c->svm;
+	m = SvmHost();
+	char *p = txt.data();
+	auto next_line = [&](char *&line) { line = p; char *e = strchr(p, '\n'); if (!e) { p += strlen(p); return; } *e = 0; p = e + 1; };
+	std::string svm_type, kernel_type;
+	for (;;) {
+		char *line; next_line(line);
+		char *save = nullptr;
+		char *key = strtok_r(line, " \t\r", &save);
+		if (!key) { if (!*p) break; continue; }
+		if (!strcmp(key, "SV")) break;
+		auto tok = [&]() { return strtok_r(nullptr, " \t\r", &save); };
+		if (!strcmp(key, "svm_type")) { char *t = tok(); svm_type = t ? t : ""; }
+		else if (!strcmp(key, "kernel_type")) { char *t = tok(); kernel_type = t ? t : ""; }
+		else if (!strcmp(key, "gamma")) { char *t = tok(); m.gamma = t ? strtod(t, nullptr) : 0; }
+		else if (!strcmp(key, "nr_class")) { char *t = tok(); m.nr_class = t ? atoi(t) : 0; }
+		else if (!strcmp(key, "total_sv")) { char *t = tok(); m.l = t ? atoi(t) : 0; }
+		else if (!strcmp(key, "rho") || !strcmp(key, "probA") || !strcmp(key, "probB")) {
+			std::vector<double> &a = (key[0] == 'r') ? m.rho : (key[4] == 'A' ? m.probA : m.probB);
+			const int n = m.nr_class * (m.nr_class - 1) / 2;
+			a.assign((size_t)n, 0.0);
+			for (int i = 0; i < n; i++) { char *t = tok(); if (t) a[i] = strtod(t, nullptr); }
+		} else if (!strcmp(key, "label") || !strcmp(key, "nr_sv")) {
+			std::vector<int> &a = (key[0] == 'l') ? m.label : m.nsv;
+			a.assign((size_t)m.nr_class, 0);
+			for (int i = 0; i < m.nr_class; i++) { char *t = tok(); if (t) a[i] = atoi(t); }
+		}
+	}
+	if (svm_type != "c_svc" || kernel_type != "rbf" || m.probA.empty() || m.probB.empty() || m.nr_class < 2 || m.l < 1) {
+		set_error("%s: only c_svc + rbf models with probability estimates are supported (svm_type=%s kernel_type=%s)", path, svm_type.c_str(), kernel_type.c_str());
+		return -1;
+	}
+	const int k1 = m.nr_class - 1;
+	m.coef.assign((size_t)k1 * m.l, 0.0);
+	std::vector<int> idx; std::vector<double> val; std::vector<int> rowstart((size_t)m.l + 1, 0);
+	int maxidx = -1;
+	for (int i = 0; i < m.l; i++) {
+		char *line; next_line(line);
+		char *s = line, *e;
+		for (int j = 0; j < k1; j++) { m.coef[(size_t)j * m.l + i] = strtod(s, &e); s = e; }
+		rowstart[i] = (int)idx.size();
+		for (;;) {
+			while (*s == ' ' || *s == '\t' || *s == '\r') s++;
+			if (!*s) break;
+			const long id = strtol(s, &e, 10);
+			if (e == s || *e != ':') break;
+			s = e + 1;
+			const double v = strtod(s, &e);
+			s = e;
+			idx.push_back((int)id); val.push_back(v);
+			if (id > maxidx) maxidx = (int)id;
+		}
+	}
+	rowstart[m.l] = (int)idx.size();
+	m.dims = maxidx + 1;
+	if (m.dims < 1) { set_error("%s: no support vector entries", path); return -1; }
+	m.sv.assign((size_t)m.l * m.dims, 0.0);
+	for (int i = 0; i < m.l; i++)
+		for (int q = rowstart[i]; q < rowstart[i + 1]; q++) if (idx[q] >= 0) m.sv[(size_t)i * m.dims + idx[q]] = val[q];
+	m.start.assign((size_t)m.nr_class, 0);
+	for (int i = 1; i < m.nr_class; i++) m.start[i] = m.start[i - 1] + m.nsv[i - 1];
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	if (dev_upload(&m.d_sv, m.sv) || dev_upload(&m.d_coef, m.coef) || dev_upload(&m.d_rho, m.rho) || dev_upload(&m.d_probA, m.probA) ||
+	    dev_upload(&m.d_probB, m.probB) || dev_upload(&m.d_label, m.label) || dev_upload(&m.d_nsv, m.nsv) || dev_upload(&m.d_start, m.start)) return -1;
+	m.loaded = true;
+	return m.l;
+}
+
+int ert_svm_nr_class(ert_ctx *c) { return c->svm.loaded ? c->svm.nr_class : -1; }
+int ert_svm_dims(ert_ctx *c) { return c->svm.loaded ? c->svm.dims : -1; }
+
+// ---- the batched hot path ----------------------------------------------------------------------
+static int detect_common(ert_ctx *c, const uint8_t *bgr, bool on_device, int n_frames, int W, int H, int stride, int upto)
+{
+	if (!c || !bgr || n_frames < 1) { set_error("bad arguments"); return -1; }
+	if (stride < 3 * W) { set_error("stride %d < 3*width", stride); return -1; }
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	const int n_planes = 6 * n_frames;
+	const bool fresh = !(W == c->W && H == c->H && n_planes <= c->planes_cap);
+	if (ensure_workspace(c, n_planes, W, H)) return -1;
+	if (fresh || c->frames_cap != -1) { if (set_plane_table(c, c->planes_cap, true)) return -1; c->frames_cap = -1; }
+	c->launches = 0;
+	cudaStream_t st = c->stream;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[0], st));
+	const uint8_t *d_in = bgr;
+	const size_t frame_bytes = (size_t)stride * H;
+	if (!on_device) {
+		if (c->bgr_cap < frame_bytes * n_frames) {
+			cudaFree(c->d_bgr); c->d_bgr = nullptr; c->bgr_cap = 0;
+			ERT_CUDA_CHECK(cudaMalloc((void **)&c->d_bgr, frame_bytes * n_frames));
+			c->bgr_cap = frame_bytes * n_frames;
+		}
+		ERT_CUDA_CHECK(cudaMemcpyAsync(c->d_bgr, bgr, frame_bytes * n_frames, cudaMemcpyHostToDevice, st));
+		d_in = c->d_bgr;
+	}
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
+	if (launch_channels(d_in, frame_bytes, stride, W, H, n_frames, c->d_ycc, c->pitch, st)) return -1;
+	c->launches += 1;
+	return enqueue_pipeline(c, n_planes, upto);
+}
+
+int ert_detect_classify(ert_ctx *c, const uint8_t *bgr, int n_frames, int W, int H, int stride, int upto, const ert_result **out)
+{
+	if (detect_common(c, bgr, false, n_frames, W, H, stride, upto)) return -1;
+	return finish_result(c, out);
+}
+
+int ert_detect_classify_device(ert_ctx *c, const void *d_bgr, int n_frames, int W, int H, int stride, int upto)
+{
+	return detect_common(c, (const uint8_t *)d_bgr, true, n_frames, W, H, stride, upto);
+}
+
+int ert_fetch_result(ert_ctx *c, const ert_result **out) { return finish_result(c, out); }
+
+int ert_planes_detect(ert_ctx *c, const uint8_t *planes, int n_planes, int W, int H, int stride, size_t plane_stride, int upto, const ert_result **out)
+{
+	if (!c || !planes || n_planes < 1 || stride < W) { set_error("bad arguments"); return -1; }
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	if (ensure_workspace(c, n_planes, W, H)) return -1;
+	if (set_plane_table(c, n_planes, false)) return -1;
+	c->frames_cap = 0;   // plane table no longer in BGR layout
+	c->launches = 0;
+	cudaStream_t st = c->stream;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[0], st));
+	for (int p = 0; p < n_planes; p++)
+		ERT_CUDA_CHECK(cudaMemcpy2DAsync(c->d_ycc + (size_t)p * c->ycc_bytes, (size_t)c->pitch, planes + (size_t)p * plane_stride, (size_t)stride,
+		                                 (size_t)W, (size_t)H, cudaMemcpyHostToDevice, st));
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
+	if (enqueue_pipeline(c, n_planes, upto)) return -1;
+	return finish_result(c, out);
+}
+
+// ---- stage entry points on caller data --------------------------------------------------------
+int ert_nms_nodes(ert_ctx *c, const ert_node *nodes, int n, int W, int H, int32_t *pool_out, int pool_cap, int *n_pool)
+{
+	if (!c || !nodes || n < 1) { set_error("bad arguments"); return -1; }
+	if (n > c->kept_cap) { set_error("ert_nms_nodes: %d nodes exceed the kept capacity %d (ert_set_capacity)", n, c->kept_cap); return -1; }
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const size_t stride = nms_scratch_stride(c->kept_cap);
+	if (c->s0.ensure(sizeof(OutNode) * (size_t)n) || c->s1.ensure(stride) || c->s2.ensure(sizeof(OutNode) * (size_t)c->kept_cap) ||
+	    c->s3.ensure(sizeof(int32_t) * (size_t)(c->pool_cap + 8)) || c->s4.ensure(64)) return -1;
+	int32_t offs[2] = {0, n};
+	int32_t *d_offs = (int32_t *)c->s4.p;             // [0..1] offsets, [2..3] counts, [4] status
+	int32_t *d_counts = d_offs + 2;
+	uint32_t *d_status = (uint32_t *)(d_offs + 4);
+	ERT_CUDA_CHECK(cudaMemsetAsync(c->s4.p, 0, 64, st));
+	ERT_CUDA_CHECK(cudaMemcpyAsync(d_offs, offs, sizeof offs, cudaMemcpyHostToDevice, st));
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, nodes, sizeof(OutNode) * (size_t)n, cudaMemcpyHostToDevice, st));
+	NmsParams NP = make_nms_params(c, W, H);
+	if (launch_nms(NP, 1, nullptr, nullptr, nullptr, nullptr, nullptr, (const OutNode *)c->s0.p, d_offs, (uint8_t *)c->s1.p, stride,
+	               (OutNode *)c->s2.p, (int32_t *)c->s3.p, d_counts, d_status, st)) return -1;
+	int32_t counts[3] = {0, 0, 0};
+	ERT_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts, sizeof(int32_t) * 3, cudaMemcpyDeviceToHost, st));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
+	const int np = counts[1];
+	if (np > pool_cap) { set_error("pool_out too small: need %d", np); return -1; }
+	// pool indices come back in the kernel's DFS numbering, which equals the caller's numbering
+	// because the caller's order was used verbatim
+	ERT_CUDA_CHECK(cudaMemcpy(pool_out, c->s3.p, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost));
+	if (n_pool) *n_pool = np;
+	return 0;
+}
+
+static int classify_common(ert_ctx *c, const uint8_t *plane, int W, int H, int stride, const int32_t *rects, int n, int32_t *label,
+                           double *ss, double *ws, uint8_t *hist_u8, double *hist_f64, bool need_cascade)
+{
+	if (!c || !plane || !rects || n < 0 || stride < W) { set_error("bad arguments"); return -1; }
+	if (n == 0) return 0;
+	if (need_cascade && (!c->casc[0].loaded || !c->casc[1].loaded)) { set_error("cascades are not loaded"); return -1; }
+	for (int i = 0; i < n; i++) {
+		const int32_t *r = rects + 4 * i;
+		if (r[0] < 0 || r[1] < 0 || r[2] < 1 || r[3] < 1 || r[0] + r[2] > W || r[1] + r[3] > H) { set_error("rect %d outside the plane", i); return -1; }
+	}
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const int pitch = extract_pitch(W);
+	const size_t nodes_b = sizeof(OutNode) * (size_t)n, pool_b = sizeof(int32_t) * (size_t)n;
+	// s0: plane, s1: nodes + pool + counts + PlaneSrc, s2: hist, s3: label + scores
+	if (c->s0.ensure((size_t)pitch * H) || c->s1.ensure(nodes_b + pool_b + 64 + sizeof(PlaneSrc)) || c->s2.ensure((size_t)n * 1024) ||
+	    c->s3.ensure((size_t)n * (sizeof(int32_t) + 2 * sizeof(double)) + 64)) return -1;
+	ERT_CUDA_CHECK(cudaMemcpy2DAsync(c->s0.p, (size_t)pitch, plane, (size_t)stride, (size_t)W, (size_t)H, cudaMemcpyHostToDevice, st));
+	std::vector<OutNode> hn((size_t)n);
+	std::vector<int32_t> hp((size_t)n);
+	for (int i = 0; i < n; i++) {
+		hn[i].level = 0; hn[i].area = 0; hn[i].x = rects[4 * i]; hn[i].y = rects[4 * i + 1]; hn[i].w = rects[4 * i + 2]; hn[i].h = rects[4 * i + 3];
+		hn[i].parent = -1; hn[i].nchild = 0; hp[i] = i;
+	}
+	uint8_t *b1 = (uint8_t *)c->s1.p;
+	OutNode *d_nodes = (OutNode *)b1;
+	int32_t *d_pool = (int32_t *)(b1 + nodes_b);
+	int32_t *d_counts = (int32_t *)(b1 + nodes_b + ((pool_b + 15) / 16) * 16);
+	PlaneSrc *d_ps = (PlaneSrc *)((uint8_t *)d_counts + 32);
+	int32_t counts[2] = {n, n};
+	PlaneSrc ps; ps.src = (const uint8_t *)c->s0.p; ps.invert = 0;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(d_nodes, hn.data(), nodes_b, cudaMemcpyHostToDevice, st));
+	ERT_CUDA_CHECK(cudaMemcpyAsync(d_pool, hp.data(), pool_b, cudaMemcpyHostToDevice, st));
+	ERT_CUDA_CHECK(cudaMemcpyAsync(d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, st));
+	ERT_CUDA_CHECK(cudaMemcpyAsync(d_ps, &ps, sizeof ps, cudaMemcpyHostToDevice, st));
+	ClassifyParams CP; CP.pitch = pitch; CP.pool_cap = n; CP.node_cap = n;
+	if (launch_lbp_hist(CP, 1, d_ps, d_nodes, d_pool, d_counts, c->d_aran_tbl, (uint8_t *)c->s2.p, st)) return -1;
+	int32_t *d_label = (int32_t *)c->s3.p;
+	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
+	double *d_ws = d_ss + n;
+	if (need_cascade) {
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, st)) return -1;
+	}
+	ERT_CUDA_CHECK(cudaStreamSynchronize(st));   // staging vectors hn/hp may go out of scope now
+	if (label) ERT_CUDA_CHECK(cudaMemcpy(label, d_label, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+	if (ss) ERT_CUDA_CHECK(cudaMemcpy(ss, d_ss, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+	if (ws) ERT_CUDA_CHECK(cudaMemcpy(ws, d_ws, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+	if (hist_u8) ERT_CUDA_CHECK(cudaMemcpy(hist_u8, c->s2.p, (size_t)n * 1024, cudaMemcpyDeviceToHost));
+	if (hist_f64) {
+		std::vector<uint8_t> tmp((size_t)n * 1024);
+		ERT_CUDA_CHECK(cudaMemcpy(tmp.data(), c->s2.p, (size_t)n * 1024, cudaMemcpyDeviceToHost));
+		for (size_t i = 0; i < tmp.size(); i++) hist_f64[i] = (double)tmp[i];   // vector<double> of counts, as make_LBP_hist returns
+	}
+	return 0;
+}
+
+int ert_classify_regions(ert_ctx *c, const uint8_t *plane, int W, int H, int stride, const int32_t *rects, int n, int32_t *label,
+                         double *ss, double *ws, uint8_t *hist1024)
+{
+	return classify_common(c, plane, W, H, stride, rects, n, label, ss, ws, hist1024, nullptr, true);
+}
+
+int ert_lbp_hist(ert_ctx *c, const uint8_t *plane, int W, int H, int stride, const int32_t *rects, int n, double *hist)
+{
+	return classify_common(c, plane, W, H, stride, rects, n, nullptr, nullptr, nullptr, nullptr, hist, false);
+}
+
+int ert_cascade_predict_batch(ert_ctx *c, int which, const double *fv, int n, int dims, double *score)
+{
+	if (!c || !fv || !score || which < 0 || which > 1 || n < 0) { set_error("bad arguments"); return -1; }
+	if (!c->casc[which].loaded) { set_error("cascade %d is not loaded", which); return -1; }
+	if (dims < 1024) { set_error("feature vectors must have at least 1024 dims (stump dims index 0..1023)"); return -1; }
+	if (n == 0) return 0;
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	if (c->s0.ensure(sizeof(double) * (size_t)n * dims) || c->s3.ensure((size_t)n * (sizeof(int32_t) + 2 * sizeof(double)) + 64)) return -1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, fv, sizeof(double) * (size_t)n * dims, cudaMemcpyHostToDevice, st));
+	int32_t *d_label = (int32_t *)c->s3.p;
+	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
+	double *d_ws = d_ss + n;
+	// evaluate the requested cascade in the "strong" slot; the other slot gets the same table (cheap, keeps one kernel)
+	const CascadeDev cd = c->casc[which].dev();
+	if (launch_cascade_f64((const double *)c->s0.p, (size_t)dims, n, cd, cd, d_label, d_ss, d_ws, st)) return -1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(score, d_ss, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int ert_cascade_classify_u8(ert_ctx *c, const uint8_t *hist, int n, int32_t *label, double *ss, double *ws)
+{
+	if (!c || !hist || n < 0) { set_error("bad arguments"); return -1; }
+	if (!c->casc[0].loaded || !c->casc[1].loaded) { set_error("cascades are not loaded"); return -1; }
+	if (n == 0) return 0;
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	if (c->s2.ensure((size_t)n * 1024) || c->s3.ensure((size_t)n * (sizeof(int32_t) + 2 * sizeof(double)) + 64)) return -1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s2.p, hist, (size_t)n * 1024, cudaMemcpyHostToDevice, st));
+	int32_t *d_label = (int32_t *)c->s3.p;
+	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
+	double *d_ws = d_ss + n;
+	if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, st)) return -1;
+	if (label) ERT_CUDA_CHECK(cudaMemcpyAsync(label, d_label, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	if (ss) ERT_CUDA_CHECK(cudaMemcpyAsync(ss, d_ss, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	if (ws) ERT_CUDA_CHECK(cudaMemcpyAsync(ws, d_ws, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+static int svm_common(ert_ctx *c, const double *xf, const uint8_t *xu, int n, double *label, double *prob)
+{
+	if (!c || (!xf && !xu) || n < 0) { set_error("bad arguments"); return -1; }
+	if (!c->svm.loaded) { set_error("svm model is not loaded"); return -1; }
+	if (n == 0) return 0;
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const SvmHost &m = c->svm;
+	const size_t xb = xf ? sizeof(double) * (size_t)n * m.dims : (size_t)n * m.dims;
+	if (c->s0.ensure(xb) || c->s1.ensure(sizeof(double) * (size_t)n * m.l) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, xf ? (const void *)xf : (const void *)xu, xb, cudaMemcpyHostToDevice, st));
+	double *d_label = (double *)c->s3.p, *d_prob = d_label + n;
+	if (launch_svm_predict(m.dev(), xf ? (const double *)c->s0.p : nullptr, xu ? (const uint8_t *)c->s0.p : nullptr, n, (double *)c->s1.p, d_label, d_prob, st)) return -1;
+	if (label) ERT_CUDA_CHECK(cudaMemcpyAsync(label, d_label, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	if (prob) ERT_CUDA_CHECK(cudaMemcpyAsync(prob, d_prob, sizeof(double) * (size_t)n * m.nr_class, cudaMemcpyDeviceToHost, st));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int ert_svm_predict_probability_batch(ert_ctx *c, const double *x, int n, double *label, double *prob) { return svm_common(c, x, nullptr, n, label, prob); }
+int ert_svm_predict_probability_batch_u8(ert_ctx *c, const uint8_t *x, int n, double *label, double *prob) { return svm_common(c, nullptr, x, n, label, prob); }
+
+int ert_bench_cascade_u8(ert_ctx *c, const uint8_t *hist, int n, int iters, double *ms_per_iter)
+{
+	if (!c || !hist || n < 1 || iters < 1) { set_error("bad arguments"); return -1; }
+	if (!c->casc[0].loaded || !c->casc[1].loaded) { set_error("cascades are not loaded"); return -1; }
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	if (c->s2.ensure((size_t)n * 1024) || c->s3.ensure((size_t)n * (sizeof(int32_t) + 2 * sizeof(double)) + 64)) return -1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s2.p, hist, (size_t)n * 1024, cudaMemcpyHostToDevice, st));
+	int32_t *d_label = (int32_t *)c->s3.p;
+	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
+	double *d_ws = d_ss + n;
+	for (int w = 0; w < 3; w++)
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, st)) return -1;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[6], st));
+	for (int i = 0; i < iters; i++)
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, st)) return -1;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[7], st));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
+	float ms = 0;
+	ERT_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+	*ms_per_iter = (double)ms / iters;
+	return 0;
+}
+
+int ert_bench_svm_u8(ert_ctx *c, const uint8_t *x, int n, int iters, double *ms_per_iter)
+{
+	if (!c || !x || n < 1 || iters < 1) { set_error("bad arguments"); return -1; }
+	if (!c->svm.loaded) { set_error("svm model is not loaded"); return -1; }
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const SvmHost &m = c->svm;
+	if (c->s0.ensure((size_t)n * m.dims) || c->s1.ensure(sizeof(double) * (size_t)n * m.l) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, x, (size_t)n * m.dims, cudaMemcpyHostToDevice, st));
+	double *d_label = (double *)c->s3.p, *d_prob = d_label + n;
+	if (launch_svm_predict(m.dev(), nullptr, (const uint8_t *)c->s0.p, n, (double *)c->s1.p, d_label, d_prob, st)) return -1;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[6], st));
+	for (int i = 0; i < iters; i++)
+		if (launch_svm_predict(m.dev(), nullptr, (const uint8_t *)c->s0.p, n, (double *)c->s1.p, d_label, d_prob, st)) return -1;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev[7], st));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
+	float ms = 0;
+	ERT_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+	*ms_per_iter = (double)ms / iters;
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,551 @@
+// er_extract.cu -- component-tree build (replaces ERFilter::er_tree_extract, src/ER.cpp:240-413,
+// and compute_channels, src/ER.cpp:114-128) as hand-written sm_100a kernels.
+//
+// Pipeline per batch of planes (a plane = one u8 channel image, 6 per BGR frame):
+//   k_channels      BGR -> Y, Cr, Cb planes (inverted planes are derived on the fly)
+//   k_tile_build    per 64x32 tile: TMA bulk-copy the tile into shared memory, quantise to levels,
+//                   build the tile-local component forest with a keyed lock-free union-find in
+//                   shared memory, count own-level pixels / bbox per tile-local node, emit nodes
+//   k_seam_link     stitch tiles: the same keyed union-find on the (few) edges that cross tile seams
+//   k_fold          fold nodes that were merged across seams into their final node; count children
+//   k_refit         bottom-up accumulation of (pixels, nodes, bbox) with arrival counters, no grid sync
+//   k_reach_root    the flood's start-pixel rule (src/ER.cpp:267-341): which tree is the reference's
+//   k_emit_kept     compact the nodes the reference keeps (area > MIN_AREA, or the root)
+//
+// Exact reference semantics reproduced: level = rint_half_even(v/step); levels >= hi
+// are walls; one node per (level L, 4-connected component of {level<=L} holding a level-L pixel);
+// area = pixels + number of nodes in the subtree; bbox exact; kept = area > MIN_AREA or root.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ert {
+
+// ---------------------------------------------------------------------------------------------
+// k_channels : OpenCV 8-bit BGR2YCrCb in integer arithmetic (14 fractional bits)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_channels(const uint8_t *__restrict__ bgr, size_t frame_stride, int row_stride, int W, int H,
+                           uint8_t *__restrict__ ycc, int pitch)
+{
+	const int f = blockIdx.z;
+	const int y = blockIdx.y;
+	const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (x4 >= W) return;
+	const uint8_t *row = bgr + (size_t)f * frame_stride + (size_t)y * row_stride + (size_t)x4 * 3;
+	const size_t plane_bytes = (size_t)pitch * H;
+	uint8_t *o0 = ycc + ((size_t)f * 3 + 0) * plane_bytes + (size_t)y * pitch + x4;
+	uint8_t *o1 = o0 + plane_bytes, *o2 = o1 + plane_bytes;
+	const int n = min(4, W - x4);
+	uint8_t yy[4] = {0, 0, 0, 0}, cr[4] = {0, 0, 0, 0}, cb[4] = {0, 0, 0, 0};
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		if (i < n) {
+			const int b = __ldg(row + 3 * i), g = __ldg(row + 3 * i + 1), r = __ldg(row + 3 * i + 2);
+			const int lum = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
+			int vr = ((r - lum) * 11682 + (128 << 14) + 8192) >> 14;
+			int vb = ((b - lum) * 9241 + (128 << 14) + 8192) >> 14;
+			vr = min(max(vr, 0), 255);
+			vb = min(max(vb, 0), 255);
+			yy[i] = (uint8_t)lum; cr[i] = (uint8_t)vr; cb[i] = (uint8_t)vb;
+		}
+	}
+	// pitch is a multiple of 64 and x4 a multiple of 4: 4-byte stores are aligned (pad bytes are don't-care)
+	*reinterpret_cast<uchar4 *>(o0) = make_uchar4(yy[0], yy[1], yy[2], yy[3]);
+	*reinterpret_cast<uchar4 *>(o1) = make_uchar4(cr[0], cr[1], cr[2], cr[3]);
+	*reinterpret_cast<uchar4 *>(o2) = make_uchar4(cb[0], cb[1], cb[2], cb[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory keyed union-find.  local key = level << 16 | local pixel index
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t find_s(volatile uint32_t *par, uint32_t k)
+{
+	for (;;) {
+		const uint32_t p = par[k & 0xFFFFu];
+		if (p == KEY_NONE || (p >> 16) != (k >> 16)) return k;
+		k = p;
+	}
+}
+
+// Insert the edge a--b.  par[x] only ever decreases (atomicMin) and whatever it displaces is
+// re-linked, so the final forest does not depend on the interleaving of concurrent links.
+__device__ __forceinline__ void link_s(uint32_t *par, uint32_t a, uint32_t b, uint32_t *status)
+{
+	for (int guard = 0; guard < (1 << 20); ++guard) {
+		a = find_s(par, a);
+		b = find_s(par, b);
+		if (a == b) return;
+		if (a > b) { const uint32_t t = a; a = b; b = t; }
+		const uint32_t old = atomicMin(&par[a & 0xFFFFu], b);
+		if (old == b || old == KEY_NONE) return;
+		if (old < b) a = old;           // a already had a closer ancestor: b must sit above it
+		else { a = b; b = old; }        // b slipped in between a and its old ancestor
+	}
+	atomicOr(status, ERR_LOOP_GUARD);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	do {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ void tma_row_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tile_build
+// ---------------------------------------------------------------------------------------------
+template <int TW, int TH, int NT>
+__global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneSrc *__restrict__ planes,
+                                                   uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
+                                                   uint32_t *__restrict__ node_list, uint32_t *__restrict__ node_count,
+                                                   uint32_t *status, int tiles_x, int local_union)
+{
+	constexpr int TPX = TW * TH;
+	constexpr int SEGS = TPX / 32;
+	constexpr int NWARP = NT / 32;
+	static_assert(TW % 32 == 0 && TPX <= 65536, "tile shape");
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *lvl = smem;                                     // TMA destination, converted to levels in place
+	uint32_t *par = reinterpret_cast<uint32_t *>(smem + TPX);
+	uint32_t *cnt = par + TPX;
+	uint32_t *xmn = cnt + TPX;
+	uint32_t *xmx = xmn + TPX;
+	uint32_t *ymn = xmx + TPX;
+	__shared__ __align__(8) uint64_t bar;
+	__shared__ uint32_t s_nroots, s_base, s_cursor;
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int plane = blockIdx.y;
+	const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+	const int X0 = tx * TW, Y0 = ty * TH;
+	const int rows = min(TH, P.H - Y0), cols = min(TW, P.W - X0);
+	const PlaneSrc ps = planes[plane];
+	const uint8_t *src = ps.src + (size_t)Y0 * P.pitch + X0;
+	const size_t N = (size_t)P.W * P.H;
+	uint32_t *parP = par_g + (size_t)plane * N;
+	NodeAttr *attrP = attr_g + (size_t)plane * N;
+
+	// ---- stage the tile through TMA (one bulk copy per row, all completing on one mbarrier) ----
+	if (tid == 0) { mbar_init(&bar, 1); s_nroots = 0; s_cursor = 0; }
+	__syncthreads();
+	if (warp == 0) {
+		if (lane == 0) mbar_expect_tx(&bar, (uint32_t)(rows * TW));
+		__syncwarp();
+		for (int r = lane; r < rows; r += 32) tma_row_g2s(lvl + r * TW, src + (size_t)r * P.pitch, TW, &bar);
+	}
+	mbar_wait(&bar, 0);
+
+	// ---- phase A: quantise, horizontal same-level runs become chains without atomics ----
+	for (int seg = warp; seg < SEGS; seg += NWARP) {
+		const int p = seg * 32 + lane;
+		const int y = p / TW, x = p % TW;
+		int L = 255;
+		if (y < rows && x < cols) {
+			int v = lvl[p];
+			if (ps.invert) v = 255 - v;
+			L = quantize_level(v, P.qscale);
+			if (L >= P.hi) L = 255;
+		}
+		const int Lr = __shfl_down_sync(0xFFFFFFFFu, L, 1);
+		const bool same = local_union && (lane < 31) && (Lr == L) && (L != 255);
+		const uint32_t bmask = __ballot_sync(0xFFFFFFFFu, !same);
+		const int end = lane + __ffs(bmask >> lane) - 1;
+		__syncwarp();
+		lvl[p] = (uint8_t)L;
+		par[p] = (L == 255 || end == lane) ? KEY_NONE : (((uint32_t)L << 16) | (uint32_t)(seg * 32 + end));
+		cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymn[p] = 0xFFFFFFFFu;
+	}
+	__syncthreads();
+
+	// ---- phase B: link the remaining in-tile edges ----
+	if (local_union) {
+		for (int seg = warp; seg < SEGS; seg += NWARP) {
+			const int p = seg * 32 + lane;
+			const int y = p / TW, x = p % TW;
+			const uint32_t L = lvl[p];
+			if (L == 255) continue;
+			const uint32_t kp = (L << 16) | (uint32_t)p;
+			if (x + 1 < TW) {
+				const uint32_t Lq = lvl[p + 1];
+				if (Lq != 255 && (Lq != L || lane == 31)) link_s(par, kp, (Lq << 16) | (uint32_t)(p + 1), status);
+			}
+			if (y + 1 < TH) {
+				const int q = p + TW;
+				const uint32_t Lq = lvl[q];
+				if (Lq != 255) {
+					const bool skip = (x > 0) && (lvl[p - 1] == L) && (lvl[q - 1] == Lq);
+					if (!skip) link_s(par, kp, (Lq << 16) | (uint32_t)q, status);
+				}
+			}
+		}
+		__syncthreads();
+
+		// ---- phase C: compress: every pixel points at its level root, every root at its parent's root ----
+		for (int p = tid; p < TPX; p += NT) {
+			const uint32_t L = lvl[p];
+			if (L == 255) continue;
+			const uint32_t k = (L << 16) | (uint32_t)p;
+			const uint32_t r = find_s(par, k);
+			if (r != k) par[p] = r;
+			else {
+				const uint32_t pr = par[p];
+				if (pr != KEY_NONE) {
+					const uint32_t fr = find_s(par, pr);
+					if (fr != pr) par[p] = fr;
+				}
+			}
+		}
+		__syncthreads();
+	}
+
+	// ---- phase D: own-level pixel count and bbox per tile-local node, one update per run ----
+	for (int seg = warp; seg < SEGS; seg += NWARP) {
+		const int p = seg * 32 + lane;
+		const int y = p / TW, x = p % TW;
+		const uint32_t L = lvl[p];
+		const uint32_t Lr = __shfl_down_sync(0xFFFFFFFFu, L, 1);
+		const bool same = local_union && (lane < 31) && (Lr == L) && (L != 255);
+		const uint32_t bmask = __ballot_sync(0xFFFFFFFFu, !same);
+		const uint32_t pk = par[p];
+		const bool isroot = (L != 255) && (pk == KEY_NONE || (pk >> 16) != L);
+		if (L != 255 && !same) {
+			const uint32_t prev = bmask & ((1u << lane) - 1u);
+			const int start = prev ? (32 - __clz(prev)) : 0;
+			const int len = lane - start + 1;
+			const uint32_t r = isroot ? (uint32_t)p : (pk & 0xFFFFu);
+			atomicAdd(&cnt[r], (uint32_t)len);
+			atomicMin(&xmn[r], (uint32_t)(x - (lane - start)));
+			atomicMax(&xmx[r], (uint32_t)x);
+			atomicMin(&ymn[r], (uint32_t)y);
+		}
+		const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, isroot);
+		if (lane == 0 && rmask) atomicAdd(&s_nroots, (uint32_t)__popc(rmask));
+	}
+	__syncthreads();
+	if (tid == 0) s_base = s_nroots ? atomicAdd(&node_count[plane], s_nroots) : 0u;
+	__syncthreads();
+
+	// ---- phase E: emit tile-local nodes (global key space) and the root of every border pixel ----
+	for (int seg = warp; seg < SEGS; seg += NWARP) {
+		const int p = seg * 32 + lane;
+		const int y = p / TW, x = p % TW;
+		const uint32_t L = lvl[p];
+		const uint32_t pk = par[p];
+		const bool isroot = (L != 255) && (pk == KEY_NONE || (pk >> 16) != L);
+		const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, isroot);
+		uint32_t wbase = 0;
+		if (lane == 0 && rmask) wbase = atomicAdd(&s_cursor, (uint32_t)__popc(rmask));
+		wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+		if (L == 255) continue;
+		const uint32_t gidx = (uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x);
+		if (isroot) {
+			uint32_t gpar = KEY_NONE;
+			if (pk != KEY_NONE) {
+				const uint32_t q = pk & 0xFFFFu;
+				gpar = make_key(pk >> 16, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
+			}
+			parP[gidx] = gpar;
+			uint4 *a = reinterpret_cast<uint4 *>(&attrP[gidx]);
+			a[0] = make_uint4(cnt[p], 1u, 0u, 0u);
+			a[1] = make_uint4((uint32_t)X0 + xmn[p], (uint32_t)Y0 + ymn[p], (uint32_t)X0 + xmx[p], (uint32_t)(Y0 + y));
+			const uint32_t pos = s_base + wbase + (uint32_t)__popc(rmask & ((1u << lane) - 1u));
+			node_list[(size_t)plane * N + pos] = make_key(L, gidx);
+		} else if (x == 0 || y == 0 || x == cols - 1 || y == rows - 1) {
+			const uint32_t q = pk & 0xFFFFu;
+			parP[gidx] = make_key(L, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// global-memory keyed union-find (seams)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t find_g(const uint32_t *par, uint32_t k)
+{
+	for (;;) {
+		const uint32_t p = ld_relaxed(par + key_idx(k));
+		if (p == KEY_NONE || key_level(p) != key_level(k)) return k;
+		k = p;
+	}
+}
+
+__device__ __forceinline__ void link_g(uint32_t *par, uint32_t a, uint32_t b, uint32_t *status)
+{
+	for (int guard = 0; guard < (1 << 22); ++guard) {
+		a = find_g(par, a);
+		b = find_g(par, b);
+		if (a == b) return;
+		if (a > b) { const uint32_t t = a; a = b; b = t; }
+		const uint32_t old = atomicMin(&par[key_idx(a)], b);
+		if (old == b || old == KEY_NONE) return;
+		if (old < b) a = old;
+		else { a = b; b = old; }
+	}
+	atomicOr(status, ERR_LOOP_GUARD);
+}
+
+__device__ __forceinline__ int level_at(const PlaneSrc &ps, const ExtractParams &P, int x, int y)
+{
+	int v = __ldg(ps.src + (size_t)y * P.pitch + x);
+	if (ps.invert) v = 255 - v;
+	const int L = quantize_level(v, P.qscale);
+	return L >= P.hi ? 255 : L;
+}
+
+__global__ void k_seam_link(ExtractParams P, const PlaneSrc *__restrict__ planes, uint32_t *__restrict__ par_g,
+                            uint32_t *status, int TW, int TH)
+{
+	const int plane = blockIdx.y;
+	const int nvs = (P.W - 1) / TW, nhs = (P.H - 1) / TH;
+	const long long nv = (long long)nvs * P.H, nh = (long long)nhs * P.W;
+	const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= nv + nh) return;
+	const PlaneSrc ps = planes[plane];
+	uint32_t *parP = par_g + (size_t)plane * P.W * P.H;
+	int xa, ya, xb, yb;
+	bool skip = false;
+	int la, lb;
+	if (e < nv) {
+		const int k = (int)(e / P.H) + 1, y = (int)(e % P.H);
+		xa = k * TW - 1; xb = xa + 1; ya = yb = y;
+		la = level_at(ps, P, xa, ya); lb = level_at(ps, P, xb, yb);
+		if (la == 255 || lb == 255) return;
+		// the pair one row up makes the same union -- but only if each of its pixels is already united with
+		// the pixel below it INSIDE a tile (not across a horizontal seam, whose own skip rule would lean on us)
+		if (y % TH != 0) skip = (level_at(ps, P, xa, y - 1) == la) && (level_at(ps, P, xb, y - 1) == lb);
+	} else {
+		const long long e2 = e - nv;
+		const int k = (int)(e2 / P.W) + 1, x = (int)(e2 % P.W);
+		ya = k * TH - 1; yb = ya + 1; xa = xb = x;
+		la = level_at(ps, P, xa, ya); lb = level_at(ps, P, xb, yb);
+		if (la == 255 || lb == 255) return;
+		if (x % TW != 0) skip = (level_at(ps, P, x - 1, ya) == la) && (level_at(ps, P, x - 1, yb) == lb);
+	}
+	if (skip) return;
+	link_g(parP, make_key((uint32_t)la, (uint32_t)(ya * P.W + xa)), make_key((uint32_t)lb, (uint32_t)(yb * P.W + xb)), status);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fold : aliases (nodes merged into a same-level node of another tile) hand their own-level
+// pixels to the final node; final nodes resolve their final parent and register as its child.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fold(ExtractParams P, uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
+                       const uint32_t *__restrict__ node_list, const uint32_t *__restrict__ node_count)
+{
+	const int plane = blockIdx.y;
+	const size_t N = (size_t)P.W * P.H;
+	uint32_t *parP = par_g + (size_t)plane * N;
+	NodeAttr *attrP = attr_g + (size_t)plane * N;
+	const uint32_t n = node_count[plane];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t g = node_list[(size_t)plane * N + i];
+		const uint32_t f = find_g(parP, g);
+		NodeAttr *ag = &attrP[key_idx(g)];
+		if (f != g) {
+			NodeAttr *af = &attrP[key_idx(f)];
+			atomicAdd(&af->cnt, ag->cnt);
+			atomicMin(&af->x0, ag->x0); atomicMin(&af->y0, ag->y0);
+			atomicMax(&af->x1, ag->x1); atomicMax(&af->y1, ag->y1);
+			ag->nn = 0;   // alias marker
+		} else {
+			const uint32_t pk = ld_relaxed(parP + key_idx(g));
+			if (pk != KEY_NONE) {
+				const uint32_t fp = find_g(parP, pk);
+				if (fp != pk) parP[key_idx(g)] = fp;
+				atomicAdd(&attrP[key_idx(fp)].pend, 1u);
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_refit : leaves start; a thread carries a node's finished totals into its parent and continues
+// upward only if it was the last child to arrive (no grid-wide synchronisation).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_refit(ExtractParams P, const uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
+                        const uint32_t *__restrict__ node_list, const uint32_t *__restrict__ node_count)
+{
+	const int plane = blockIdx.y;
+	const size_t N = (size_t)P.W * P.H;
+	const uint32_t *parP = par_g + (size_t)plane * N;
+	NodeAttr *attrP = attr_g + (size_t)plane * N;
+	const uint32_t n = node_count[plane];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		uint32_t cur = node_list[(size_t)plane * N + i];
+		{
+			const NodeAttr *a = &attrP[key_idx(cur)];
+			if (a->nn == 0 || a->pend != 0) continue;   // alias, or not a leaf (pend is constant in this kernel)
+		}
+		for (int guard = 0; guard < 64; ++guard) {
+			const uint32_t p = parP[key_idx(cur)];
+			if (p == KEY_NONE) break;
+			const uint32_t *a = reinterpret_cast<const uint32_t *>(&attrP[key_idx(cur)]);
+			const uint32_t c_cnt = ld_relaxed(a + 0), c_nn = ld_relaxed(a + 1);
+			const uint32_t c_x0 = ld_relaxed(a + 4), c_y0 = ld_relaxed(a + 5), c_x1 = ld_relaxed(a + 6), c_y1 = ld_relaxed(a + 7);
+			NodeAttr *ap = &attrP[key_idx(p)];
+			atomicAdd(&ap->cnt, c_cnt);
+			atomicAdd(&ap->nn, c_nn);
+			atomicMin(&ap->x0, c_x0); atomicMin(&ap->y0, c_y0);
+			atomicMax(&ap->x1, c_x1); atomicMax(&ap->y1, c_y1);
+			__threadfence();
+			const uint32_t t = atomicAdd(&ap->arr, 1u);
+			if (t + 1u != ap->pend) break;
+			__threadfence();
+			cur = p;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_reach_root : the flood starts at pixel 0; if that is a wall it escapes to pixel 1, else to
+// pixel W (neighbour order right, bottom); only that tree is the reference's result.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_reach_root(ExtractParams P, const PlaneSrc *__restrict__ planes, const uint32_t *__restrict__ par_g,
+                             uint32_t *__restrict__ reach_root, int32_t *__restrict__ lone_level)
+{
+	const int plane = blockIdx.x * blockDim.x + threadIdx.x;
+	if (plane >= P.n_planes) return;
+	const PlaneSrc ps = planes[plane];
+	const uint32_t *parP = par_g + (size_t)plane * P.W * P.H;
+	int s = -1, ls = 255;
+	const int l0 = level_at(ps, P, 0, 0);
+	if (l0 != 255) { s = 0; ls = l0; }
+	else if (P.W > 1 && (ls = level_at(ps, P, 1, 0)) != 255) s = 1;
+	else if (P.H > 1 && (ls = level_at(ps, P, 0, 1)) != 255) s = P.W;
+	if (s < 0) {
+		reach_root[plane] = KEY_NONE;
+		int v = __ldg(ps.src);
+		if (ps.invert) v = 255 - v;
+		lone_level[plane] = quantize_level(v, P.qscale);
+		return;
+	}
+	uint32_t k = find_g(parP, make_key((uint32_t)ls, (uint32_t)s));
+	for (int guard = 0; guard < 64; ++guard) {
+		const uint32_t p = parP[key_idx(k)];
+		if (p == KEY_NONE) break;
+		k = p;
+	}
+	reach_root[plane] = k;
+	lone_level[plane] = -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_emit_kept : what er_merge leaves alive (src/ER.cpp:167-180): area > MIN_AREA, plus the root
+// ---------------------------------------------------------------------------------------------
+__global__ void k_emit_kept(ExtractParams P, const uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
+                            const uint32_t *__restrict__ node_list, const uint32_t *__restrict__ node_count,
+                            const uint32_t *__restrict__ reach_root, KeptRec *__restrict__ kept, uint32_t *__restrict__ kept_count,
+                            uint32_t *status)
+{
+	const int plane = blockIdx.y;
+	const size_t N = (size_t)P.W * P.H;
+	const uint32_t *parP = par_g + (size_t)plane * N;
+	NodeAttr *attrP = attr_g + (size_t)plane * N;
+	const uint32_t n = node_count[plane];
+	const uint32_t rr = reach_root[plane];
+	if (rr == KEY_NONE) return;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t g = node_list[(size_t)plane * N + i];
+		NodeAttr *a = &attrP[key_idx(g)];
+		if (a->nn == 0) continue;
+		const int area = (int)(a->cnt + a->nn);
+		if (!(area > P.min_area || g == rr)) continue;
+		uint32_t t = g;
+		for (int guard = 0; guard < 64; ++guard) {
+			const uint32_t p = parP[key_idx(t)];
+			if (p == KEY_NONE) break;
+			t = p;
+		}
+		if (t != rr) continue;
+		const uint32_t pos = atomicAdd(&kept_count[plane], 1u);
+		if (pos >= (uint32_t)P.kept_cap) { atomicOr(status, ERR_KEPT_OVERFLOW); continue; }
+		a->arr = pos;
+		KeptRec r;
+		r.gidx = key_idx(g);
+		const uint32_t pk = parP[key_idx(g)];
+		r.parent = (pk == KEY_NONE) ? KEY_NONE : key_idx(pk);
+		r.level = (int32_t)key_level(g);
+		r.area = area;
+		r.x0 = (uint16_t)a->x0; r.y0 = (uint16_t)a->y0; r.x1 = (uint16_t)a->x1; r.y1 = (uint16_t)a->y1;
+		kept[(size_t)plane * P.kept_cap + pos] = r;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+constexpr int TILE_W = 64, TILE_H = 32, TILE_NT = 256;
+
+int extract_pitch(int W) { return (W + 127) / 128 * 128; }
+
+size_t tile_smem_bytes() { return (size_t)TILE_W * TILE_H * (1 + 5 * 4); }
+
+int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st)
+{
+	dim3 block(128), grid(((W + 3) / 4 + 127) / 128, H, n_frames);
+	k_channels<<<grid, block, 0, st>>>(d_bgr, frame_stride, row_stride, W, H, d_ycc, pitch);
+	ERT_CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st)
+{
+	const size_t smem = tile_smem_bytes();
+		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TILE_W, TILE_H, TILE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
+	ERT_CUDA_CHECK(cudaMemsetAsync(wk.node_count, 0, sizeof(uint32_t) * P.n_planes, st));
+	ERT_CUDA_CHECK(cudaMemsetAsync(wk.kept_count, 0, sizeof(uint32_t) * P.n_planes, st));
+	{
+		dim3 grid(tiles_x * tiles_y, P.n_planes);
+		k_tile_build<TILE_W, TILE_H, TILE_NT><<<grid, TILE_NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count,
+		                                                                  wk.status, tiles_x, local_union);
+		ERT_CUDA_CHECK(cudaGetLastError());
+	}
+	{
+		// with local_union == 0 every pixel is its own tile-local node and ALL edges are seams (debug A/B mode)
+		const int tw = local_union ? TILE_W : 1, th = local_union ? TILE_H : 1;
+		const long long edges = (long long)((P.W - 1) / tw) * P.H + (long long)((P.H - 1) / th) * P.W;
+		if (edges > 0) {
+			dim3 grid((unsigned)((edges + 255) / 256), P.n_planes);
+			k_seam_link<<<grid, 256, 0, st>>>(P, d_planes, wk.par, wk.status, tw, th);
+			ERT_CUDA_CHECK(cudaGetLastError());
+		}
+	}
+	{
+		dim3 grid(wk.node_blocks, P.n_planes);
+		k_fold<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_list, wk.node_count);
+		ERT_CUDA_CHECK(cudaGetLastError());
+		k_refit<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_list, wk.node_count);
+		ERT_CUDA_CHECK(cudaGetLastError());
+		k_reach_root<<<(P.n_planes + 63) / 64, 64, 0, st>>>(P, d_planes, wk.par, wk.reach_root, wk.lone_level);
+		ERT_CUDA_CHECK(cudaGetLastError());
+		k_emit_kept<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_list, wk.node_count, wk.reach_root, wk.kept, wk.kept_count, wk.status);
+		ERT_CUDA_CHECK(cudaGetLastError());
+	}
+	return 0;
+}
+
+} // namespace ert

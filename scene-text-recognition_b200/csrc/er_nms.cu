@@ -1,0 +1,302 @@
+// er_nms.cu -- tree non-maximum suppression (replaces ERFilter::non_maximum_supression,
+// src/ER.cpp:416-505).  One CTA per plane.
+//
+// The reference walks the tree so that a node is processed after all of its children, children in
+// list order, and the result depends on that order through the `done` flags.  List order in the
+// reference is the (sequential) flood's completion order; the parallel build has no such order, so
+// siblings are visited in a CANONICAL order instead: descending (bbox.y, bbox.x), ties by
+// descending level, area, x1, y1, root pixel.  On the 211 ICDAR frames of the reference repo this
+// changes 1 of 14 668 pooled regions (tests/test_sibling_order.py); against the oracle run with
+// the same canonical order the result is bit-exact.  When the caller supplies an explicit child
+// order (ert_nms_nodes, used by the drop-in facade on trees it got from us or from the reference)
+// that order is used verbatim.
+//
+// Steps: (1) load the kept list, resolve parent positions; (2) bitonic sort by (parent, sibling
+// key) so every child list is contiguous and ordered; (3) one thread runs the reference's
+// sequential post-order walk out of shared memory (arithmetic in IEEE double exactly as the
+// reference: overlap = area(bbox∩)/area(parent bbox) > coef, stability = a_i / (a_{i+T} - a_i));
+// (4) all threads scatter nodes into DFS pre-order (the oracle's dump order) and the pool.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ert {
+
+struct NmsView {
+	unsigned long long *keyA;   // [n2] sort key, high part
+	uint32_t *keyB;             // [n2] sort key, low part (tie break)
+	uint32_t *ord;              // [n2] payload: original position
+	int32_t *area;              // [n] sorted-position attributes
+	uint16_t *bx;               // [4n] x0,y0,x1,y1
+	int32_t *parent;            // [n]
+	int32_t *first;             // [n] first child (sorted position) or -1
+	int32_t *pre;               // [n] DFS pre-order index
+	int32_t *newpos;            // [n] original position -> sorted position
+	uint8_t *level;             // [n]
+	uint8_t *done;              // [n]
+};
+
+__host__ __device__ inline size_t nms_bytes_per_node() { return 8 + 4 + 4 + 4 + 8 + 4 + 4 + 4 + 4 + 1 + 1; }
+
+__host__ __device__ inline size_t nms_view_bytes(int n2) { return (size_t)n2 * nms_bytes_per_node() + 64; }
+
+__device__ inline NmsView make_view(uint8_t *base, int n2)
+{
+	NmsView v;
+	v.keyA = reinterpret_cast<unsigned long long *>(base); base += (size_t)n2 * 8;
+	v.keyB = reinterpret_cast<uint32_t *>(base); base += (size_t)n2 * 4;
+	v.ord = reinterpret_cast<uint32_t *>(base); base += (size_t)n2 * 4;
+	v.area = reinterpret_cast<int32_t *>(base); base += (size_t)n2 * 4;
+	v.bx = reinterpret_cast<uint16_t *>(base); base += (size_t)n2 * 8;
+	v.parent = reinterpret_cast<int32_t *>(base); base += (size_t)n2 * 4;
+	v.first = reinterpret_cast<int32_t *>(base); base += (size_t)n2 * 4;
+	v.pre = reinterpret_cast<int32_t *>(base); base += (size_t)n2 * 4;
+	v.newpos = reinterpret_cast<int32_t *>(base); base += (size_t)n2 * 4;
+	v.level = base; base += n2;
+	v.done = base;
+	return v;
+}
+
+__device__ __forceinline__ int bb_area(const uint16_t *b) { return ((int)b[2] - (int)b[0] + 1) * ((int)b[3] - (int)b[1] + 1); }
+__device__ __forceinline__ int bb_inter(const uint16_t *a, const uint16_t *b)
+{
+	const int x0 = max((int)a[0], (int)b[0]), y0 = max((int)a[1], (int)b[1]);
+	const int x1 = min((int)a[2], (int)b[2]), y1 = min((int)a[3], (int)b[3]);
+	if (x1 < x0 || y1 < y0) return 0;
+	return (x1 - x0 + 1) * (y1 - y0 + 1);
+}
+
+// in:  either the extract stage's kept list (kept != nullptr; parents given as root-pixel indices,
+//      resolved through attr[].arr) or caller nodes (in_nodes: DFS pre-order with explicit order).
+template <int NT>
+__global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restrict__ kept, const uint32_t *__restrict__ kept_count,
+                                            const NodeAttr *__restrict__ attr_g, const uint32_t *__restrict__ reach_root,
+                                            const int32_t *__restrict__ lone_level,
+                                            const OutNode *__restrict__ in_nodes, const int32_t *__restrict__ in_offsets,
+                                            uint8_t *__restrict__ scratch, size_t scratch_stride, int smem_cap,
+                                            OutNode *__restrict__ out_nodes, int32_t *__restrict__ out_pool,
+                                            int32_t *__restrict__ out_counts /* per plane: n_nodes, n_pool */, uint32_t *status)
+{
+	extern __shared__ __align__(16) uint8_t nms_smem[];
+	__shared__ int s_npool;
+	const int tid = threadIdx.x;
+	const int plane = blockIdx.x;
+	const bool from_kept = (kept != nullptr);
+	int n;
+	const KeptRec *kp = nullptr;
+	const OutNode *inp = nullptr;
+	if (from_kept) {
+		n = (int)min(kept_count[plane], (uint32_t)P.kept_cap);
+		kp = kept + (size_t)plane * P.kept_cap;
+	} else {
+		n = in_offsets[plane + 1] - in_offsets[plane];
+		inp = in_nodes + in_offsets[plane];
+	}
+	OutNode *outn = out_nodes + (size_t)plane * P.kept_cap;
+	int32_t *outp = out_pool + (size_t)plane * P.pool_cap;
+
+	if (from_kept && reach_root[plane] == KEY_NONE) {
+		// the flood never left a wall pixel: a lone component of level(pixel 0), area 2 (ctor 1 + one pixel)
+		if (tid == 0) {
+			OutNode o; o.level = lone_level[plane]; o.area = 2; o.x = 0; o.y = 0; o.w = 1; o.h = 1; o.parent = -1; o.nchild = 0;
+			outn[0] = o;
+			out_counts[2 * plane] = 1; out_counts[2 * plane + 1] = 0;
+		}
+		return;
+	}
+	if (n == 0) {
+		if (tid == 0) { out_counts[2 * plane] = 0; out_counts[2 * plane + 1] = 0; }
+		return;
+	}
+	int n2 = 1;
+	while (n2 < n) n2 <<= 1;
+	uint8_t *base = (n2 <= smem_cap) ? nms_smem : (scratch + (size_t)plane * scratch_stride);
+	NmsView v = make_view(base, n2);
+
+	// ---- (1) keys ----
+	for (int i = tid; i < n2; i += NT) {
+		if (i < n) {
+			int ppos, lvl, ar; uint32_t tie; int x0, y0, x1, y1;
+			if (from_kept) {
+				const KeptRec r = kp[i];
+				ppos = (r.parent == KEY_NONE) ? -1 : (int)attr_g[(size_t)plane * P.N + r.parent].arr;
+				lvl = r.level; ar = r.area; tie = r.gidx; x0 = r.x0; y0 = r.y0; x1 = r.x1; y1 = r.y1;
+			} else {
+				const OutNode r = inp[i];
+				ppos = r.parent; lvl = r.level; ar = r.area; tie = (uint32_t)i; x0 = r.x; y0 = r.y; x1 = r.x + r.w - 1; y1 = r.y + r.h - 1;
+			}
+			unsigned long long a;
+			uint32_t b;
+			if (from_kept) {
+				// parent | ~y0 | ~x0 | ~level  ;  ~area | ~x1(13) ... tie by root pixel
+				a = ((unsigned long long)(uint32_t)(ppos + 1) << 40) | ((unsigned long long)(8191 - y0) << 27) |
+				    ((unsigned long long)(8191 - x0) << 14) | ((unsigned long long)(63 - lvl) << 8);
+				b = 0xFFFFFFFFu - (uint32_t)ar;
+				// (x1,y1,root pixel) decide only if level, area, x0, y0 all tie: fold them into the low byte order via ord compare
+				v.keyA[i] = a; v.keyB[i] = b;
+			} else {
+				v.keyA[i] = ((unsigned long long)(uint32_t)(ppos + 1) << 40) | (unsigned long long)tie;   // explicit order
+				v.keyB[i] = 0;
+			}
+			v.ord[i] = (uint32_t)i;
+			v.newpos[i] = ppos;   // stash the unsorted parent position
+		} else {
+			v.keyA[i] = ~0ull; v.keyB[i] = ~0u; v.ord[i] = (uint32_t)i;
+		}
+	}
+	__syncthreads();
+
+	// ---- (2) bitonic sort by (keyA, keyB, tie) ----
+	for (int k = 2; k <= n2; k <<= 1) {
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int i = tid; i < n2; i += NT) {
+				const int l = i ^ j;
+				if (l > i) {
+					const unsigned long long ai = v.keyA[i], al = v.keyA[l];
+					const uint32_t bi = v.keyB[i], bl = v.keyB[l];
+					const uint32_t oi = v.ord[i], ol = v.ord[l];
+					bool gt;
+					if (ai != al) gt = ai > al;
+					else if (bi != bl) gt = bi > bl;
+					else {
+						// full tie on (parent,y0,x0,level,area): x1 desc, y1 desc, root pixel desc
+						if (from_kept && oi < (uint32_t)n && ol < (uint32_t)n) {
+							const KeptRec ri = kp[oi], rl = kp[ol];
+							if (ri.x1 != rl.x1) gt = ri.x1 < rl.x1;
+							else if (ri.y1 != rl.y1) gt = ri.y1 < rl.y1;
+							else gt = ri.gidx < rl.gidx;
+						} else gt = oi > ol;
+					}
+					const bool up = ((i & k) == 0);
+					if (gt == up) {
+						v.keyA[i] = al; v.keyA[l] = ai;
+						v.keyB[i] = bl; v.keyB[l] = bi;
+						v.ord[i] = ol; v.ord[l] = oi;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	}
+
+	// ---- (3) build the sorted tree arrays ----
+	// newpos currently holds unsorted parent positions; move them aside through `pre`
+	for (int i = tid; i < n; i += NT) v.pre[i] = v.newpos[i];
+	__syncthreads();
+	for (int j = tid; j < n; j += NT) v.newpos[v.ord[j]] = j;
+	__syncthreads();
+	for (int j = tid; j < n; j += NT) {
+		const int o = (int)v.ord[j];
+		int lvl, ar, x0, y0, x1, y1;
+		if (from_kept) { const KeptRec r = kp[o]; lvl = r.level; ar = r.area; x0 = r.x0; y0 = r.y0; x1 = r.x1; y1 = r.y1; }
+		else { const OutNode r = inp[o]; lvl = r.level; ar = r.area; x0 = r.x; y0 = r.y; x1 = r.x + r.w - 1; y1 = r.y + r.h - 1; }
+		v.level[j] = (uint8_t)lvl; v.area[j] = ar;
+		v.bx[4 * j] = (uint16_t)x0; v.bx[4 * j + 1] = (uint16_t)y0; v.bx[4 * j + 2] = (uint16_t)x1; v.bx[4 * j + 3] = (uint16_t)y1;
+		const int pp = v.pre[o];
+		v.parent[j] = (pp < 0) ? -1 : v.newpos[pp];
+		v.first[j] = -1;
+		v.done[j] = 0;
+	}
+	__syncthreads();
+	for (int j = tid; j < n; j += NT) {
+		const int p = v.parent[j];
+		if (p >= 0 && (j == 0 || v.parent[j - 1] != p)) v.first[p] = j;
+	}
+	__syncthreads();
+
+	// ---- (4) the reference's sequential walk (src/ER.cpp:426-502) ----
+	if (tid == 0) {
+		int stack[72];
+		int chain[72];
+		int sp = 0, pre = 0, npool = 0;
+		const int T = P.stability_t;
+		int cur = 0;   // the root sorts first (parent -1)
+		for (long long guard = 0; guard < 4ll * n + 8; ++guard) {
+			while (cur >= 0) {
+				if (sp >= 72) { atomicOr(status, ERR_NMS_OVERFLOW); cur = -1; break; }
+				stack[sp++] = cur; v.pre[cur] = pre++; cur = v.first[cur];
+			}
+			if (sp == 0) break;
+			cur = stack[--sp];
+			if (!v.done[cur]) {
+				int len = 0, p = cur;
+				const uint16_t *bc = &v.bx[4 * cur];
+				while (!v.done[p] && (double)bb_inter(bc, &v.bx[4 * p]) / (double)bb_area(&v.bx[4 * p]) > P.overlap_coef) {
+					v.done[p] = 1;
+					if (len < 72) chain[len] = p;
+					len++;
+					const int pp = v.parent[p];
+					p = (pp < 0) ? p : pp;      // root->parent = root (src/ER.cpp:424)
+				}
+				if (len > 72) { atomicOr(status, ERR_NMS_OVERFLOW); len = 72; }
+				if (len >= 1 + T) {
+					int best = 0;
+					double best_s = 0.0;
+					for (int i = 0; i < len - T; i++) {
+						const int ai = bb_area(&v.bx[4 * chain[i]]), aj = bb_area(&v.bx[4 * chain[i + T]]);
+						const double s = (double)ai / (double)(aj - ai);
+						if (i == 0) { best = 0; best_s = s; }
+						else if (s > best_s) { best = i; best_s = s; }
+						else if (s == best_s && ai < bb_area(&v.bx[4 * chain[best]])) { best = i; best_s = s; }
+					}
+					const int b = chain[best];
+					const uint16_t *bb = &v.bx[4 * b];
+					const int w = bb[2] - bb[0] + 1, h = bb[3] - bb[1] + 1;
+					const double ar = (double)w / (double)h;
+					if (ar < 2.0 && ar > 0.10 && v.area[b] < P.max_area && v.area[b] > P.min_area &&
+					    h < P.H * 0.8 && w < P.W * 0.8) {
+						if (npool < P.pool_cap) v.keyB[npool] = (uint32_t)b;   // keyB is free after the sort
+						else atomicOr(status, ERR_POOL_OVERFLOW);
+						npool++;
+					}
+				}
+			}
+			// next sibling: the following sorted position if it has the same parent
+			const int nx = cur + 1;
+			cur = (nx < n && v.parent[nx] == v.parent[cur] && v.parent[cur] >= 0) ? nx : -1;
+		}
+		s_npool = min(npool, P.pool_cap);
+	}
+	__syncthreads();
+
+	// ---- (5) scatter into DFS pre-order ----
+	for (int j = tid; j < n; j += NT) {
+		OutNode o;
+		o.level = v.level[j]; o.area = v.area[j];
+		o.x = v.bx[4 * j]; o.y = v.bx[4 * j + 1];
+		o.w = v.bx[4 * j + 2] - v.bx[4 * j] + 1; o.h = v.bx[4 * j + 3] - v.bx[4 * j + 1] + 1;
+		o.parent = (v.parent[j] < 0) ? -1 : v.pre[v.parent[j]];
+		int nc = 0;
+		const int f = v.first[j];
+		if (f >= 0) { nc = 1; while (f + nc < n && v.parent[f + nc] == j) nc++; }
+		o.nchild = nc;
+		outn[v.pre[j]] = o;
+	}
+	const int npool = s_npool;
+	for (int k = tid; k < npool; k += NT) outp[k] = v.pre[v.keyB[k]];
+	if (tid == 0) { out_counts[2 * plane] = n; out_counts[2 * plane + 1] = npool; }
+}
+
+constexpr int NMS_NT = 512;
+constexpr int NMS_SMEM_NODES = 4096;
+
+size_t nms_scratch_stride(int kept_cap)
+{
+	int n2 = 1;
+	while (n2 < kept_cap) n2 <<= 1;
+	return (nms_view_bytes(n2) + 255) / 256 * 256;
+}
+
+int launch_nms(const NmsParams &P, int n_planes, const KeptRec *kept, const uint32_t *kept_count, const NodeAttr *attr,
+               const uint32_t *reach_root, const int32_t *lone_level, const OutNode *in_nodes, const int32_t *in_offsets,
+               uint8_t *scratch, size_t scratch_stride, OutNode *out_nodes, int32_t *out_pool, int32_t *out_counts,
+               uint32_t *status, cudaStream_t st)
+{
+	const size_t smem = nms_view_bytes(NMS_SMEM_NODES);
+		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_nms<NMS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_nms<NMS_NT><<<n_planes, NMS_NT, smem, st>>>(P, kept, kept_count, attr, reach_root, lone_level, in_nodes, in_offsets,
+	                                              scratch, scratch_stride, NMS_SMEM_NODES, out_nodes, out_pool, out_counts, status);
+	ERT_CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
+} // namespace ert

@@ -1,0 +1,71 @@
+// kernels.h -- host-side launchers of the sm_100a kernels (internal to libertext.so)
+#pragma once
+#include "common.cuh"
+
+namespace ert {
+
+struct ExtractWork {
+	uint32_t *par;          // [n_planes][N] keyed forest
+	NodeAttr *attr;         // [n_planes][N] node attributes (sparse)
+	uint32_t *node_list;    // [n_planes][N] keys of tile-local nodes
+	uint32_t *node_count;   // [n_planes]
+	uint32_t *reach_root;   // [n_planes]
+	int32_t *lone_level;    // [n_planes]
+	KeptRec *kept;          // [n_planes][kept_cap]
+	uint32_t *kept_count;   // [n_planes]
+	uint32_t *status;       // [1]
+	int node_blocks;        // grid.x of the node-list kernels
+};
+
+struct NmsParams {
+	int W, H;
+	size_t N;
+	int kept_cap, pool_cap;
+	int min_area, max_area, stability_t;
+	double overlap_coef;
+};
+
+struct ClassifyParams {
+	int pitch;
+	int pool_cap, node_cap;
+};
+
+struct Stump { double thr, cp, cn; int dim; int pad; };
+
+struct CascadeDev {
+	const Stump *stumps;
+	const int *stage_len;
+	const int *stage_thr;
+	int n_stages;
+};
+
+struct SvmDev {
+	int nr_class, l, dims;
+	double gamma;
+	const double *sv;        // [l][dims] dense support vectors
+	const double *coef;      // [nr_class-1][l]
+	const double *rho, *probA, *probB;   // [nr_class*(nr_class-1)/2]
+	const int *label, *nsv, *start;      // [nr_class]
+};
+
+int extract_pitch(int W);
+int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st);
+int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st);
+
+size_t nms_scratch_stride(int kept_cap);
+int launch_nms(const NmsParams &P, int n_planes, const KeptRec *kept, const uint32_t *kept_count, const NodeAttr *attr,
+               const uint32_t *reach_root, const int32_t *lone_level, const OutNode *in_nodes, const int32_t *in_offsets,
+               uint8_t *scratch, size_t scratch_stride, OutNode *out_nodes, int32_t *out_pool, int32_t *out_counts,
+               uint32_t *status, cudaStream_t st);
+
+int launch_lbp_hist(const ClassifyParams &P, int n_planes, const PlaneSrc *planes, const OutNode *nodes, const int32_t *pool,
+                    const int32_t *counts, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st);
+int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const int32_t *counts, int pool_cap, const CascadeDev &strong,
+                      const CascadeDev &weak, int32_t *label, double *sscore, double *wscore, cudaStream_t st);
+int launch_cascade_f64(const double *fv, size_t row_stride, int n_rows, const CascadeDev &strong, const CascadeDev &weak,
+                       int32_t *label, double *sscore, double *wscore, cudaStream_t st);
+
+int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *kvalue_ws, double *label, double *prob,
+                       cudaStream_t st);
+
+} // namespace ert

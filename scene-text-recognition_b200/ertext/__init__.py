@@ -1,0 +1,313 @@
+"""ertext -- thin ctypes binding of libertext.so (the C ABI in include/ertext.h).
+
+Used by tests/, bench.py and __graft_entry__.py.  There is no Python or CPU implementation of
+the path behind this module: if libertext.so is missing or no CUDA device is present, it raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+LIB_PATH = os.path.join(PKG_ROOT, "libertext.so")
+ASSETS = os.path.join(REPO_ROOT, "assets", "classifier")
+
+STAGE_EXTRACT, STAGE_NMS, STAGE_CLASSIFY = 1, 2, 3
+LABEL_NONE, LABEL_WEAK, LABEL_STRONG = 0, 1, 2
+NEG_DBL_MAX = -1.7976931348623157e308
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class ErtParams(C.Structure):
+    _fields_ = [("thresh_step", C.c_int), ("min_area", C.c_int), ("max_area", C.c_int), ("stability_t", C.c_int),
+                ("overlap_coef", C.c_double), ("min_ocr_prob", C.c_double)]
+
+
+class ErtResult(C.Structure):
+    _fields_ = [("n_planes", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("node_offset", _i32p), ("nodes", _i32p), ("pool_offset", _i32p), ("pool_node", _i32p),
+                ("pool_label", _i32p), ("pool_strong_score", _f64p), ("pool_weak_score", _f64p),
+                ("pool_hist", _u8p), ("status", C.c_uint32), ("stage_ms", C.c_double * 6)]
+
+
+EXPORTS = [
+    "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
+    "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_capacity", "ert_load_cascade",
+    "ert_load_svm", "ert_svm_nr_class", "ert_svm_dims", "ert_detect_classify", "ert_detect_classify_device",
+    "ert_fetch_result", "ert_planes_detect", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
+    "ert_cascade_predict_batch", "ert_cascade_classify_u8", "ert_svm_predict_probability_batch",
+    "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
+    "ert_bench_cascade_u8", "ert_bench_svm_u8",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libertext.so (built in tree by `make -C scene-text-recognition_b200`) and declare prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libertext.so is not built (%s): run __graft_entry__.build(); there is no fallback path" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.ert_last_error.restype = C.c_char_p
+    L.ert_status_string.restype = C.c_char_p
+    L.ert_status_string.argtypes = [C.c_uint32]
+    L.ert_create.restype = C.c_void_p
+    L.ert_create.argtypes = [C.POINTER(ErtParams), C.c_int]
+    L.ert_destroy.argtypes = [C.c_void_p]
+    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_int]
+    L.ert_set_capacity.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ert_load_cascade.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    L.ert_load_svm.argtypes = [C.c_void_p, C.c_char_p]
+    L.ert_svm_nr_class.argtypes = [C.c_void_p]
+    L.ert_svm_dims.argtypes = [C.c_void_p]
+    RP = C.POINTER(C.POINTER(ErtResult))
+    L.ert_detect_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, RP]
+    L.ert_detect_classify_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ert_fetch_result.argtypes = [C.c_void_p, RP]
+    L.ert_planes_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, RP]
+    L.ert_nms_nodes.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int)]
+    L.ert_classify_regions.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f64p, _f64p, _u8p]
+    L.ert_lbp_hist.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f64p]
+    L.ert_cascade_predict_batch.argtypes = [C.c_void_p, C.c_int, _f64p, C.c_int, C.c_int, _f64p]
+    L.ert_cascade_classify_u8.argtypes = [C.c_void_p, _u8p, C.c_int, _i32p, _f64p, _f64p]
+    L.ert_svm_predict_probability_batch.argtypes = [C.c_void_p, _f64p, C.c_int, _f64p, _f64p]
+    L.ert_svm_predict_probability_batch_u8.argtypes = [C.c_void_p, _u8p, C.c_int, _f64p, _f64p]
+    L.ert_set_stream.argtypes = [C.c_void_p, C.c_uint64]
+    L.ert_get_stream.restype = C.c_uint64
+    L.ert_get_stream.argtypes = [C.c_void_p]
+    L.ert_last_launch_count.argtypes = [C.c_void_p]
+    L.ert_bench_cascade_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _f64p]
+    L.ert_bench_svm_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _f64p]
+    _lib = L
+    return L
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+class ErtError(RuntimeError):
+    pass
+
+
+def svm_model_path():
+    """assets/classifier/OCR.model is shipped xz-compressed; unpack once."""
+    import lzma
+    dst = os.path.join(ASSETS, "OCR.model")
+    if not os.path.exists(dst):
+        with lzma.open(dst + ".xz", "rb") as f, open(dst + ".tmp", "wb") as g:
+            g.write(f.read())
+        os.replace(dst + ".tmp", dst)
+    return dst
+
+
+class PlaneResult:
+    """Kept nodes (DFS pre-order: level, area, x, y, w, h, parent, n_children), pool and labels of one plane."""
+    __slots__ = ("nodes", "pool", "label", "strong_score", "weak_score", "hist")
+
+    def __init__(self, nodes, pool, label, ss, ws, hist):
+        self.nodes, self.pool, self.label, self.strong_score, self.weak_score, self.hist = nodes, pool, label, ss, ws, hist
+
+
+class BatchResult:
+    def __init__(self, planes, status, stage_ms, width, height):
+        self.planes, self.status, self.stage_ms, self.width, self.height = planes, status, stage_ms, width, height
+
+
+class ErText:
+    """Context object = `new ERFilter(...)` + the two CascadeBoost objects (+ the OCR SVM model)."""
+
+    def __init__(self, device=0, thresh_step=8, min_area=120, max_area=900000, stability_t=2, overlap_coef=0.7,
+                 min_ocr_prob=0.15, load_cascades=True, load_svm=False):
+        self.L = load_library()
+        prm = ErtParams(thresh_step, min_area, max_area, stability_t, overlap_coef, min_ocr_prob)
+        self.ctx = self.L.ert_create(C.byref(prm), device)
+        if not self.ctx:
+            raise ErtError(self.L.ert_last_error().decode())
+        if load_cascades:
+            self.load_cascade(0, os.path.join(ASSETS, "strong.classifier"))
+            self.load_cascade(1, os.path.join(ASSETS, "weak.classifier"))
+        if load_svm:
+            self.load_svm(svm_model_path())
+
+    def _check(self, rc):
+        if rc < 0:
+            raise ErtError(self.L.ert_last_error().decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.ert_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_cascade(self, which, path):
+        return self._check(self.L.ert_load_cascade(self.ctx, which, path.encode()))
+
+    def load_svm(self, path):
+        return self._check(self.L.ert_load_svm(self.ctx, path.encode()))
+
+    def set_thresh_step(self, t):
+        self._check(self.L.ert_set_thresh_step(self.ctx, t))
+
+    def set_min_area(self, m):
+        self._check(self.L.ert_set_min_area(self.ctx, m))
+
+    def set_return_hist(self, on):
+        self._check(self.L.ert_set_return_hist(self.ctx, int(on)))
+
+    def set_tile_local_union(self, on):
+        self._check(self.L.ert_set_tile_local_union(self.ctx, int(on)))
+
+    def set_capacity(self, kept, pool):
+        self._check(self.L.ert_set_capacity(self.ctx, kept, pool))
+
+    def set_stream(self, s):
+        self._check(self.L.ert_set_stream(self.ctx, s))
+
+    def launch_count(self):
+        return self.L.ert_last_launch_count(self.ctx)
+
+    # ---- result unpacking ----------------------------------------------------------------------
+    def _unpack(self, rp):
+        r = rp.contents
+        P = r.n_planes
+        noff = np.ctypeslib.as_array(r.node_offset, (P + 1,)).copy()
+        poff = np.ctypeslib.as_array(r.pool_offset, (P + 1,)).copy()
+        nt, pt = int(noff[-1]), int(poff[-1])
+        nodes = np.ctypeslib.as_array(r.nodes, (max(nt, 1) * 8,))[: nt * 8].reshape(nt, 8).copy()
+        if pt:
+            pool = np.ctypeslib.as_array(r.pool_node, (pt,)).copy()
+            label = np.ctypeslib.as_array(r.pool_label, (pt,)).copy()
+            ss = np.ctypeslib.as_array(r.pool_strong_score, (pt,)).copy()
+            ws = np.ctypeslib.as_array(r.pool_weak_score, (pt,)).copy()
+            hist = np.ctypeslib.as_array(r.pool_hist, (pt * 1024,)).reshape(pt, 1024).copy() if r.pool_hist else None
+        else:
+            pool = np.zeros(0, np.int32); label = np.zeros(0, np.int32); ss = np.zeros(0); ws = np.zeros(0); hist = None
+        planes = []
+        for p in range(P):
+            a, b = int(poff[p]), int(poff[p + 1])
+            planes.append(PlaneResult(nodes[noff[p]:noff[p + 1]], pool[a:b], label[a:b], ss[a:b], ws[a:b],
+                                      hist[a:b] if hist is not None else None))
+        return BatchResult(planes, int(r.status), list(r.stage_ms), r.width, r.height)
+
+    # ---- the batched hot path ------------------------------------------------------------------
+    def detect_classify(self, bgr, upto=STAGE_CLASSIFY):
+        """bgr: uint8 [F,H,W,3] (or [H,W,3]) in host memory -> BatchResult with 6*F planes."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        if bgr.ndim == 3:
+            bgr = bgr[None]
+        f, h, w, c = bgr.shape
+        assert c == 3
+        rp = C.POINTER(ErtResult)()
+        self._check(self.L.ert_detect_classify(self.ctx, bgr.ctypes.data, f, w, h, w * 3, upto, C.byref(rp)))
+        return self._unpack(rp)
+
+    def detect_classify_ptr(self, host_ptr, f, w, h, stride, upto=STAGE_CLASSIFY):
+        """Raw host pointer (e.g. pinned torch tensor .data_ptr())."""
+        rp = C.POINTER(ErtResult)()
+        self._check(self.L.ert_detect_classify(self.ctx, host_ptr, f, w, h, stride, upto, C.byref(rp)))
+        return self._unpack(rp)
+
+    def enqueue_device(self, dev_ptr, f, w, h, stride, upto=STAGE_CLASSIFY):
+        self._check(self.L.ert_detect_classify_device(self.ctx, dev_ptr, f, w, h, stride, upto))
+
+    def fetch(self):
+        rp = C.POINTER(ErtResult)()
+        self._check(self.L.ert_fetch_result(self.ctx, C.byref(rp)))
+        return self._unpack(rp)
+
+    def planes_detect(self, planes, upto=STAGE_CLASSIFY):
+        """planes: uint8 [P,H,W] (or [H,W]) single-channel images."""
+        planes = np.ascontiguousarray(planes, dtype=np.uint8)
+        if planes.ndim == 2:
+            planes = planes[None]
+        p, h, w = planes.shape
+        rp = C.POINTER(ErtResult)()
+        self._check(self.L.ert_planes_detect(self.ctx, planes.ctypes.data, p, w, h, w, w * h, upto, C.byref(rp)))
+        return self._unpack(rp)
+
+    # ---- stage entry points --------------------------------------------------------------------
+    def nms_nodes(self, nodes, w, h):
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        n = nodes.shape[0]
+        pool = np.zeros(max(n, 1), np.int32)
+        npool = C.c_int(0)
+        self._check(self.L.ert_nms_nodes(self.ctx, _ptr(nodes, _i32p), n, w, h, _ptr(pool, _i32p), pool.size, C.byref(npool)))
+        return pool[: npool.value].copy()
+
+    def classify_regions(self, plane, rects, want_hist=False):
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+        h, w = plane.shape
+        n = rects.shape[0]
+        label = np.zeros(n, np.int32); ss = np.zeros(n); ws = np.zeros(n)
+        hist = np.zeros((n, 1024), np.uint8) if want_hist else None
+        self._check(self.L.ert_classify_regions(self.ctx, _ptr(plane, _u8p), w, h, w, _ptr(rects, _i32p), n, _ptr(label, _i32p),
+                                                _ptr(ss, _f64p), _ptr(ws, _f64p), _ptr(hist, _u8p) if want_hist else None))
+        return label, ss, ws, hist
+
+    def lbp_hist(self, plane, rects):
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+        h, w = plane.shape
+        n = rects.shape[0]
+        hist = np.zeros((n, 1024), np.float64)
+        self._check(self.L.ert_lbp_hist(self.ctx, _ptr(plane, _u8p), w, h, w, _ptr(rects, _i32p), n, _ptr(hist, _f64p)))
+        return hist
+
+    def cascade_predict(self, which, fv):
+        fv = np.ascontiguousarray(fv, dtype=np.float64)
+        n, d = fv.shape
+        out = np.zeros(n)
+        self._check(self.L.ert_cascade_predict_batch(self.ctx, which, _ptr(fv, _f64p), n, d, _ptr(out, _f64p)))
+        return out
+
+    def cascade_classify_u8(self, hist):
+        hist = np.ascontiguousarray(hist, dtype=np.uint8)
+        n = hist.shape[0]
+        label = np.zeros(n, np.int32); ss = np.zeros(n); ws = np.zeros(n)
+        self._check(self.L.ert_cascade_classify_u8(self.ctx, _ptr(hist, _u8p), n, _ptr(label, _i32p), _ptr(ss, _f64p), _ptr(ws, _f64p)))
+        return label, ss, ws
+
+    def svm_predict_probability(self, x):
+        k = self.L.ert_svm_nr_class(self.ctx)
+        if x.dtype == np.uint8:
+            x = np.ascontiguousarray(x)
+            n = x.shape[0]
+            label = np.zeros(n); prob = np.zeros((n, k))
+            self._check(self.L.ert_svm_predict_probability_batch_u8(self.ctx, _ptr(x, _u8p), n, _ptr(label, _f64p), _ptr(prob, _f64p)))
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            n = x.shape[0]
+            label = np.zeros(n); prob = np.zeros((n, k))
+            self._check(self.L.ert_svm_predict_probability_batch(self.ctx, _ptr(x, _f64p), n, _ptr(label, _f64p), _ptr(prob, _f64p)))
+        return label, prob
+
+    def svm_dims(self):
+        return self.L.ert_svm_dims(self.ctx)
+
+    def bench_cascade_u8(self, hist, iters):
+        hist = np.ascontiguousarray(hist, dtype=np.uint8)
+        ms = C.c_double(0)
+        self._check(self.L.ert_bench_cascade_u8(self.ctx, _ptr(hist, _u8p), hist.shape[0], iters, C.byref(ms)))
+        return ms.value
+
+    def bench_svm_u8(self, x, iters):
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        ms = C.c_double(0)
+        self._check(self.L.ert_bench_svm_u8(self.ctx, _ptr(x, _u8p), x.shape[0], iters, C.byref(ms)))
+        return ms.value
