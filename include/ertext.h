@@ -69,8 +69,9 @@ typedef struct {
 	uint32_t status;                /* 0 = ok; bit flags on capacity overflow (see ert_status_string) */
 	/* device time per stage in milliseconds (CUDA events on the context's stream), mirroring
 	 * the reference's times[] of ERFilter::text_detect (src/ER.cpp:99-110):
-	 * [0] extract (incl. channels) [1] nms [2] classify [3] h2d [4] d2h [5] total */
-	double stage_ms[6];
+	 * [0] extract (incl. channels) [1] nms [2] classify [3] h2d [4] d2h [5] total
+	 * [6] the tile-build kernel alone (the dominant kernel; roofline numerator) [7] rest of extract */
+	double stage_ms[8];
 } ert_result;
 
 ERT_API int ert_abi_version(void);
@@ -104,6 +105,10 @@ ERT_API int ert_svm_dims(ert_ctx *ctx);
  * (8-bit, 3 channels interleaved, row stride in bytes) in HOST memory.  upto = ERT_STAGE_*. */
 ERT_API int ert_detect_classify(ert_ctx *ctx, const uint8_t *bgr, int n_frames, int width, int height, int stride_bytes,
                                 int upto, const ert_result **out);
+/* Asynchronous form of the above: enqueue the H2D copy (host memory should be pinned for a truly
+ * asynchronous copy) and all kernels on the context's stream, return immediately; the result is
+ * collected by ert_fetch_result.  Two contexts used alternately overlap copy and compute. */
+ERT_API int ert_enqueue_host(ert_ctx *ctx, const uint8_t *bgr, int n_frames, int width, int height, int stride_bytes, int upto);
 /* Same, frames already resident on the device (device pointer); enqueue only. The result is
  * fetched (one stream sync + small D2H) by ert_fetch_result. */
 ERT_API int ert_detect_classify_device(ert_ctx *ctx, const void *d_bgr, int n_frames, int width, int height, int stride_bytes, int upto);

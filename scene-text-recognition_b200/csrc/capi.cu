@@ -122,7 +122,7 @@ struct ert_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool own_stream = true;
-	cudaEvent_t ev[8];
+	cudaEvent_t ev[12];
 	int local_union = 1;
 	int return_hist = 0;
 	int kept_cap = 16384, pool_cap = 2048;
@@ -272,7 +272,7 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 {
 	cudaStream_t st = c->stream;
 	const ExtractParams EP = make_extract_params(c, n_planes);
-	if (launch_extract(EP, c->d_planes, c->wk, c->local_union, st)) return -1;
+	if (launch_extract(EP, c->d_planes, c->wk, c->local_union, st, c->ev[8], c->ev[9])) return -1;
 	c->launches += 6;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[2], st));
 	const NmsParams NP = make_nms_params(c, c->W, c->H);
@@ -317,6 +317,7 @@ int finish_result(ert_ctx *c, const ert_result **out)
 	auto el = [&](int a, int b) { ms = 0.f; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return (double)ms; };
 	r.stage_ms[3] = el(0, 1); r.stage_ms[0] = el(1, 2); r.stage_ms[1] = el(2, 3); r.stage_ms[2] = el(3, 4); r.stage_ms[4] = el(4, 5);
 	r.stage_ms[5] = el(0, 5);
+	r.stage_ms[6] = el(8, 9); r.stage_ms[7] = r.stage_ms[0] - r.stage_ms[6];
 	if (r.status & ERR_LOOP_GUARD) { set_error("device loop guard tripped (internal error)"); return -2; }
 	if (out) *out = &r;
 	return 0;
@@ -377,7 +378,7 @@ ert_ctx *ert_create(const ert_params *params, int device)
 	if (c->prm.thresh_step < 5 || c->prm.thresh_step > 255) { set_error("thresh_step %d unsupported (5..255)", c->prm.thresh_step); delete c; return nullptr; }
 	c->device = device;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); delete c; return nullptr; }
-	for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
+	for (int i = 0; i < 12; i++) cudaEventCreate(&c->ev[i]);
 	build_aran_table(c);
 	if (cudaMalloc((void **)&c->d_aran_tbl, 64) != cudaSuccess || cudaMemcpy(c->d_aran_tbl, c->aran_tbl_h, 64, cudaMemcpyHostToDevice) != cudaSuccess) {
 		set_error("aran table upload failed"); delete c; return nullptr;
@@ -396,7 +397,7 @@ void ert_destroy(ert_ctx *c)
 	cudaFree(c->svm.d_sv); cudaFree(c->svm.d_coef); cudaFree(c->svm.d_rho); cudaFree(c->svm.d_probA); cudaFree(c->svm.d_probB);
 	cudaFree(c->svm.d_label); cudaFree(c->svm.d_nsv); cudaFree(c->svm.d_start);
 	c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
-	for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+	for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -592,6 +593,11 @@ int ert_detect_classify(ert_ctx *c, const uint8_t *bgr, int n_frames, int W, int
 {
 	if (detect_common(c, bgr, false, n_frames, W, H, stride, upto)) return -1;
 	return finish_result(c, out);
+}
+
+int ert_enqueue_host(ert_ctx *c, const uint8_t *bgr, int n_frames, int W, int H, int stride, int upto)
+{
+	return detect_common(c, bgr, false, n_frames, W, H, stride, upto);
 }
 
 int ert_detect_classify_device(ert_ctx *c, const void *d_bgr, int n_frames, int W, int H, int stride, int upto)

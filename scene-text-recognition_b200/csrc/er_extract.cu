@@ -83,6 +83,21 @@ __device__ __forceinline__ void link_s(uint32_t *par, uint32_t a, uint32_t b, ui
 	atomicOr(status, ERR_LOOP_GUARD);
 }
 
+// One step of a walk towards the level root with path halving.  Returns true when k is a level root.
+// Halving rewrites par[k] from its same-level parent to its same-level grandparent with a plain
+// store: all three are pixels of the same node, so connectivity per level is unchanged, and a
+// concurrent atomicMin that the store might overwrite has already queued the re-link of what it
+// displaced ("why compression is safe").
+__device__ __forceinline__ bool climb_s(volatile uint32_t *par, uint32_t &k)
+{
+	const uint32_t p = par[k & 0xFFFFu];
+	if (p == KEY_NONE || (p >> 16) != (k >> 16)) return true;
+	const uint32_t g = par[p & 0xFFFFu];
+	if (g != KEY_NONE && (g >> 16) == (k >> 16)) { par[k & 0xFFFFu] = g; k = g; }
+	else k = p;
+	return false;
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA (bulk async copy) + mbarrier helpers
 // ---------------------------------------------------------------------------------------------
@@ -135,7 +150,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	uint32_t *xmx = xmn + TPX;
 	uint32_t *ymn = xmx + TPX;
 	__shared__ __align__(8) uint64_t bar;
-	__shared__ uint32_t s_nroots, s_base, s_cursor;
+	__shared__ uint32_t s_nroots, s_base, s_cursor, s_nlinks;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int plane = blockIdx.y;
@@ -149,7 +164,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	NodeAttr *attrP = attr_g + (size_t)plane * N;
 
 	// ---- stage the tile through TMA (one bulk copy per row, all completing on one mbarrier) ----
-	if (tid == 0) { mbar_init(&bar, 1); s_nroots = 0; s_cursor = 0; }
+	if (tid == 0) { mbar_init(&bar, 1); s_nroots = 0; s_cursor = 0; s_nlinks = 0; }
 	__syncthreads();
 	if (warp == 0) {
 		if (lane == 0) mbar_expect_tx(&bar, (uint32_t)(rows * TW));
@@ -176,50 +191,112 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		__syncwarp();
 		lvl[p] = (uint8_t)L;
 		par[p] = (L == 255 || end == lane) ? KEY_NONE : (((uint32_t)L << 16) | (uint32_t)(seg * 32 + end));
-		cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymn[p] = 0xFFFFFFFFu;
 	}
 	__syncthreads();
 
-	// ---- phase B: link the remaining in-tile edges ----
+	// ---- phase B: the remaining in-tile edges.  B1 compacts them into a work list in shared memory
+	// (aliasing cnt/xmn, which are not live yet); B2 drains the list with warp-converged state machines:
+	// every lane owns one edge at a time, all lanes advance one hop per iteration (no divergent inner
+	// loops), idle lanes refill from the list -- so a long chain stalls one lane, not the CTA. ----
+	uint32_t *links = cnt;   // up to 2*TPX packed (p << 16 | q)
 	if (local_union) {
 		for (int seg = warp; seg < SEGS; seg += NWARP) {
 			const int p = seg * 32 + lane;
 			const int y = p / TW, x = p % TW;
 			const uint32_t L = lvl[p];
-			if (L == 255) continue;
-			const uint32_t kp = (L << 16) | (uint32_t)p;
-			if (x + 1 < TW) {
-				const uint32_t Lq = lvl[p + 1];
-				if (Lq != 255 && (Lq != L || lane == 31)) link_s(par, kp, (Lq << 16) | (uint32_t)(p + 1), status);
+			bool eh = false, ev = false;
+			if (L != 255) {
+				if (x + 1 < TW) { const uint32_t Lq = lvl[p + 1]; eh = (Lq != 255) && (Lq != L || lane == 31); }
+				if (y + 1 < TH) {
+					const uint32_t Lq = lvl[p + TW];
+					if (Lq != 255) ev = !((x > 0) && (lvl[p - 1] == L) && (lvl[p + TW - 1] == Lq));
+				}
 			}
-			if (y + 1 < TH) {
-				const int q = p + TW;
-				const uint32_t Lq = lvl[q];
-				if (Lq != 255) {
-					const bool skip = (x > 0) && (lvl[p - 1] == L) && (lvl[q - 1] == Lq);
-					if (!skip) link_s(par, kp, (Lq << 16) | (uint32_t)q, status);
+			const uint32_t mh = __ballot_sync(0xFFFFFFFFu, eh), mv = __ballot_sync(0xFFFFFFFFu, ev);
+			uint32_t base = 0;
+			if (lane == 0 && (mh | mv)) base = atomicAdd(&s_nlinks, (uint32_t)(__popc(mh) + __popc(mv)));
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			const uint32_t lt = (1u << lane) - 1u;
+			if (eh) links[base + __popc(mh & lt)] = ((uint32_t)p << 16) | (uint32_t)(p + 1);
+			if (ev) links[base + __popc(mh) + __popc(mv & lt)] = ((uint32_t)p << 16) | (uint32_t)(p + TW);
+		}
+		__syncthreads();
+		{
+			const uint32_t nl = s_nlinks;
+			uint32_t a = 0, b = 0;
+			bool act = false, more = true;
+			for (int guard = 0; guard < (1 << 22); ++guard) {
+				const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !act);
+				if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= 12)) {
+					uint32_t base = 0;
+					if (lane == 0) base = atomicAdd(&s_cursor, (uint32_t)__popc(idle));
+					base = __shfl_sync(0xFFFFFFFFu, base, 0);
+					if (!act) {
+						const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+						if (i < nl) {
+							const uint32_t e = links[i];
+							const uint32_t p = e >> 16, q = e & 0xFFFFu;
+							a = ((uint32_t)lvl[p] << 16) | p;
+							b = ((uint32_t)lvl[q] << 16) | q;
+							act = true;
+						}
+					}
+					if (base + (uint32_t)__popc(idle) >= nl) more = false;
+				}
+				if (!__any_sync(0xFFFFFFFFu, act)) { if (!more) break; else continue; }
+				if (act) {
+					const bool ra = climb_s(par, a);
+					const bool rb = climb_s(par, b);
+					if (ra && rb) {
+						if (a == b) act = false;
+						else {
+							if (a > b) { const uint32_t t = a; a = b; b = t; }
+							const uint32_t old = atomicMin(&par[a & 0xFFFFu], b);
+							if (old == b || old == KEY_NONE) act = false;
+							else if (old < b) a = old;
+							else { a = b; b = old; }
+						}
+					}
 				}
 			}
 		}
 		__syncthreads();
 
-		// ---- phase C: compress: every pixel points at its level root, every root at its parent's root ----
-		for (int p = tid; p < TPX; p += NT) {
+		// ---- phase C: every pixel points at its level root, every root at its parent's level root;
+		// also (re)initialise the accumulators that aliased the work list ----
+		for (int p0 = warp * 32; p0 < TPX; p0 += NT) {
+			const int p = p0 + lane;
 			const uint32_t L = lvl[p];
-			if (L == 255) continue;
-			const uint32_t k = (L << 16) | (uint32_t)p;
-			const uint32_t r = find_s(par, k);
-			if (r != k) par[p] = r;
-			else {
-				const uint32_t pr = par[p];
-				if (pr != KEY_NONE) {
-					const uint32_t fr = find_s(par, pr);
-					if (fr != pr) par[p] = fr;
+			uint32_t k = (L << 16) | (uint32_t)p;
+			bool act = (L != 255);
+			while (__any_sync(0xFFFFFFFFu, act)) {
+				if (act) {
+					const uint32_t q = par[k & 0xFFFFu];
+					if (q == KEY_NONE || (q >> 16) != (k >> 16)) act = false;
+					else k = q;
 				}
 			}
+			uint32_t pr = KEY_NONE;
+			if (L != 255) {
+				if (k != ((L << 16) | (uint32_t)p)) par[p] = k;
+				else pr = par[p];
+			}
+			// roots: resolve the parent's level root
+			uint32_t k2 = pr;
+			bool act2 = (pr != KEY_NONE);
+			while (__any_sync(0xFFFFFFFFu, act2)) {
+				if (act2) {
+					const uint32_t q = par[k2 & 0xFFFFu];
+					if (q == KEY_NONE || (q >> 16) != (k2 >> 16)) act2 = false;
+					else k2 = q;
+				}
+			}
+			if (pr != KEY_NONE && k2 != pr) par[p] = k2;
 		}
 		__syncthreads();
 	}
+	for (int p = tid; p < TPX; p += NT) { cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymn[p] = 0xFFFFFFFFu; }
+	__syncthreads();
 
 	// ---- phase D: own-level pixel count and bbox per tile-local node, one update per run ----
 	for (int seg = warp; seg < SEGS; seg += NWARP) {
@@ -245,7 +322,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		if (lane == 0 && rmask) atomicAdd(&s_nroots, (uint32_t)__popc(rmask));
 	}
 	__syncthreads();
-	if (tid == 0) s_base = s_nroots ? atomicAdd(&node_count[plane], s_nroots) : 0u;
+	if (tid == 0) { s_base = s_nroots ? atomicAdd(&node_count[plane], s_nroots) : 0u; s_cursor = 0; }
 	__syncthreads();
 
 	// ---- phase E: emit tile-local nodes (global key space) and the root of every border pixel ----
@@ -511,7 +588,8 @@ int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, i
 	return 0;
 }
 
-int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st)
+int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
+                   cudaEvent_t ev_tile_begin, cudaEvent_t ev_tile_end)
 {
 	const size_t smem = tile_smem_bytes();
 		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TILE_W, TILE_H, TILE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -520,9 +598,11 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	ERT_CUDA_CHECK(cudaMemsetAsync(wk.kept_count, 0, sizeof(uint32_t) * P.n_planes, st));
 	{
 		dim3 grid(tiles_x * tiles_y, P.n_planes);
+		if (ev_tile_begin) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_begin, st));
 		k_tile_build<TILE_W, TILE_H, TILE_NT><<<grid, TILE_NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count,
 		                                                                  wk.status, tiles_x, local_union);
 		ERT_CUDA_CHECK(cudaGetLastError());
+		if (ev_tile_end) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_end, st));
 	}
 	{
 		// with local_union == 0 every pixel is its own tile-local node and ALL edges are seams (debug A/B mode)

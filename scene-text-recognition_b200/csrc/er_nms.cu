@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 			if (from_kept) {
 				const KeptRec r = kp[i];
 				ppos = (r.parent == KEY_NONE) ? -1 : (int)attr_g[(size_t)plane * P.N + r.parent].arr;
+				if (ppos >= n) ppos = -1;   // parent fell off an overflowing kept list (status already flags the batch)
 				lvl = r.level; ar = r.area; tie = r.gidx; x0 = r.x0; y0 = r.y0; x1 = r.x1; y1 = r.y1;
 			} else {
 				const OutNode r = inp[i];

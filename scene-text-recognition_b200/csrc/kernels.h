@@ -50,7 +50,8 @@ struct SvmDev {
 
 int extract_pitch(int W);
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st);
-int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st);
+int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
+                   cudaEvent_t ev_tile_begin = nullptr, cudaEvent_t ev_tile_end = nullptr);
 
 size_t nms_scratch_stride(int kept_cap);
 int launch_nms(const NmsParams &P, int n_planes, const KeptRec *kept, const uint32_t *kept_count, const NodeAttr *attr,

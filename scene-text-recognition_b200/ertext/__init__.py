@@ -31,13 +31,13 @@ class ErtResult(C.Structure):
     _fields_ = [("n_planes", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("node_offset", _i32p), ("nodes", _i32p), ("pool_offset", _i32p), ("pool_node", _i32p),
                 ("pool_label", _i32p), ("pool_strong_score", _f64p), ("pool_weak_score", _f64p),
-                ("pool_hist", _u8p), ("status", C.c_uint32), ("stage_ms", C.c_double * 6)]
+                ("pool_hist", _u8p), ("status", C.c_uint32), ("stage_ms", C.c_double * 8)]
 
 
 EXPORTS = [
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
     "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_capacity", "ert_load_cascade",
-    "ert_load_svm", "ert_svm_nr_class", "ert_svm_dims", "ert_detect_classify", "ert_detect_classify_device",
+    "ert_load_svm", "ert_svm_nr_class", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
     "ert_fetch_result", "ert_planes_detect", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
     "ert_cascade_predict_batch", "ert_cascade_classify_u8", "ert_svm_predict_probability_batch",
     "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
@@ -71,6 +71,7 @@ def load_library():
     RP = C.POINTER(C.POINTER(ErtResult))
     L.ert_detect_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, RP]
     L.ert_detect_classify_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ert_enqueue_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ert_fetch_result.argtypes = [C.c_void_p, RP]
     L.ert_planes_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, RP]
     L.ert_nms_nodes.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int)]
@@ -222,6 +223,9 @@ class ErText:
         self._check(self.L.ert_detect_classify(self.ctx, host_ptr, f, w, h, stride, upto, C.byref(rp)))
         return self._unpack(rp)
 
+    def enqueue_host(self, host_ptr, f, w, h, stride, upto=STAGE_CLASSIFY):
+        self._check(self.L.ert_enqueue_host(self.ctx, host_ptr, f, w, h, stride, upto))
+
     def enqueue_device(self, dev_ptr, f, w, h, stride, upto=STAGE_CLASSIFY):
         self._check(self.L.ert_detect_classify_device(self.ctx, dev_ptr, f, w, h, stride, upto))
 
@@ -285,6 +289,8 @@ class ErText:
 
     def svm_predict_probability(self, x):
         k = self.L.ert_svm_nr_class(self.ctx)
+        if k < 0:
+            raise ErtError("svm model is not loaded")
         if x.dtype == np.uint8:
             x = np.ascontiguousarray(x)
             n = x.shape[0]

@@ -1,0 +1,87 @@
+"""GPU: er_tree_extract + NMS + classify through the C ABI against the oracle -- bit-exact.
+
+The oracle is run with the canonical sibling order (see test_sibling_order.py); with that, node
+arrays (DFS order, parents, child counts), pool order, labels and scores must be IDENTICAL."""
+import numpy as np
+import pytest
+from conftest import make_plane
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(got, exp, tag):
+    assert got.nodes.shape == exp["nodes"].shape and (got.nodes == exp["nodes"]).all(), ("nodes", tag)
+    assert got.pool.shape == exp["pool"].shape and (got.pool == exp["pool"]).all(), ("pool", tag)
+    assert (got.label == exp["label"]).all(), ("label", tag)
+    assert (got.strong_score == exp["strong_score"]).all() and (got.weak_score == exp["weak_score"]).all(), ("score", tag)
+
+
+KINDS = ["noise", "smooth", "blobs", "walls", "wall0", "wall01", "allwall", "flat", "checker", "ramp"]
+SIZES = [(1, 1), (1, 9), (7, 1), (31, 33), (32, 64), (33, 65), (64, 128), (100, 130), (257, 191)]
+
+
+@pytest.mark.parametrize("local_union", [1, 0])
+@pytest.mark.parametrize("kind", KINDS)
+def test_planes_match_oracle(ert, port, kind, local_union):
+    ert.set_tile_local_union(local_union)
+    try:
+        for si, (h, w) in enumerate(SIZES):
+            img = make_plane(si, h, w, kind)
+            for ma in (3, 120):
+                ert.set_min_area(ma); port.params["min_area"] = ma
+                exp = port.plane(img, scores=True, canonical_order=True)
+                got = ert.planes_detect(img)
+                assert got.status == 0
+                _check(got.planes[0], exp, (kind, h, w, ma, local_union))
+    finally:
+        ert.set_tile_local_union(1); ert.set_min_area(120); port.params["min_area"] = 120
+
+
+@pytest.mark.parametrize("step", [5, 8, 13, 16, 32])
+def test_other_threshold_steps(ert, port, step):
+    img = make_plane(5, 120, 160, "smooth")
+    port.params["thresh_step"] = step
+    ert.set_thresh_step(step)
+    try:
+        _check(ert.planes_detect(img).planes[0], port.plane(img, scores=True, canonical_order=True), step)
+    finally:
+        port.params["thresh_step"] = 8; ert.set_thresh_step(8)
+
+
+def test_batch_of_planes_is_independent_of_position(ert, port):
+    planes = np.stack([make_plane(s, 96, 200, k) for s, k in enumerate(["noise", "smooth", "walls", "blobs", "flat", "checker", "allwall"])])
+    res = ert.planes_detect(planes)
+    for i in range(planes.shape[0]):
+        _check(res.planes[i], port.plane(planes[i], scores=True, canonical_order=True), i)
+    res2 = ert.planes_detect(planes[::-1].copy())
+    for i in range(planes.shape[0]):
+        assert (res2.planes[planes.shape[0] - 1 - i].nodes == res.planes[i].nodes).all()
+
+
+def test_full_hd_plane_and_mode_equivalence(ert, port):
+    """1080p: oracle parity on one natural-like and one noise plane; shared-memory tile pass == all-global pass."""
+    for kind in ("blobs", "noise"):
+        img = make_plane(42, 1080, 1920, kind)
+        exp = port.plane(img, scores=True, canonical_order=True)
+        got = ert.planes_detect(img)
+        assert got.status == 0
+        _check(got.planes[0], exp, kind)
+        ert.set_tile_local_union(0)
+        try:
+            got0 = ert.planes_detect(img)
+        finally:
+            ert.set_tile_local_union(1)
+        assert (got0.planes[0].nodes == got.planes[0].nodes).all() and (got0.planes[0].pool == got.planes[0].pool).all()
+        root = got.planes[0].nodes[0]
+        assert root[6] == -1 and root[1] > 1080 * 1920 - (img >= 252).sum()   # area = pixels + nodes (Q2)
+
+
+def test_kept_capacity_overflow_is_reported(ert):
+    img = make_plane(1, 300, 300, "noise")
+    ert.set_capacity(64, 64)
+    ert.set_min_area(3)
+    try:
+        res = ert.planes_detect(img)
+        assert res.status & 2
+    finally:
+        ert.set_capacity(16384, 2048); ert.set_min_area(120)

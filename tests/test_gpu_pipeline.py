@@ -1,0 +1,140 @@
+"""GPU: the batched BGR entry point and the stage-level entry points against the golden vectors that
+the reference's own code produced (tests/golden/*.npz) and against the live oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NEG = -1.7976931348623157e308
+
+
+def test_bgr_frames_vs_reference_golden(ert, port, golden_frames, golden_planes):
+    """Reference outputs (its own sibling order): node SETS identical; pool / labels identical up to the
+    documented sibling-order effect (<= 2 entries over the 18 planes, measured 0)."""
+    res = ert.detect_classify(golden_frames)
+    assert res.status == 0 and len(res.planes) == 18
+    diff = 0
+    for f in range(3):
+        for k in range(6):
+            got = res.planes[f * 6 + k]
+            rn = golden_planes["f%d_p%d_nodes" % (f, k)]
+            assert sorted(map(tuple, got.nodes[:, :6])) == sorted(map(tuple, rn[:, :6])), (f, k)
+            gp = {tuple(got.nodes[i][:6]): (int(got.label[j]), got.strong_score[j], got.weak_score[j]) for j, i in enumerate(got.pool)}
+            rp_idx = golden_planes["f%d_p%d_pool" % (f, k)]
+            rp = {tuple(rn[i][:6]): (int(golden_planes["f%d_p%d_label" % (f, k)][j]), golden_planes["f%d_p%d_strong_score" % (f, k)][j],
+                                     golden_planes["f%d_p%d_weak_score" % (f, k)][j]) for j, i in enumerate(rp_idx)}
+            diff += len(set(gp) ^ set(rp))
+            for key in set(gp) & set(rp):
+                assert gp[key] == rp[key], (f, k, key)       # label and both scores bit-identical
+    assert diff <= 2
+
+
+def test_bgr_frames_vs_oracle_canonical_exact(ert, port, golden_frames):
+    res = ert.detect_classify(golden_frames[:2])
+    for f in range(2):
+        ch = port.channels(golden_frames[f])
+        for k in range(6):
+            exp = port.plane(ch[k], scores=True, canonical_order=True)
+            got = res.planes[f * 6 + k]
+            assert (got.nodes == exp["nodes"]).all() and (got.pool == exp["pool"]).all()
+            assert (got.label == exp["label"]).all() and (got.strong_score == exp["strong_score"]).all()
+
+
+def test_nms_with_reference_child_order_is_exact(ert, golden_planes):
+    """ert_nms_nodes on the reference's own trees (its child order) reproduces the reference pool exactly."""
+    for f in range(3):
+        for k in range(6):
+            nodes = golden_planes["f%d_p%d_nodes" % (f, k)]
+            pool = ert.nms_nodes(nodes, 640, 480)
+            assert (pool == golden_planes["f%d_p%d_pool" % (f, k)]).all(), (f, k)
+
+
+def test_features_and_cascades_vs_reference_golden(ert, port, golden_frames, golden_feats):
+    ch = port.channels(golden_frames[1])
+    rects = golden_feats["rects"]
+    for k in range(6):
+        sel = np.nonzero(rects[:, 0] == k)[0]
+        if not len(sel):
+            continue
+        r = rects[sel][:, 1:]
+        label, ss, ws, hist = ert.classify_regions(ch[k], r, want_hist=True)
+        assert (hist == golden_feats["hists"][sel]).all()
+        assert (ss == golden_feats["strong"][sel]).all() and (ws == golden_feats["weak"][sel]).all()
+        exp_label = np.where(golden_feats["strong"][sel] > NEG, 2, np.where(golden_feats["weak"][sel] > NEG, 1, 0))
+        assert (label == exp_label).all()
+        assert (ert.lbp_hist(ch[k], r) == golden_feats["hists"][sel].astype(np.float64)).all()
+    fv = golden_feats["hists"].astype(np.float64)
+    assert (ert.cascade_predict(0, fv) == golden_feats["strong"]).all()
+    assert (ert.cascade_predict(1, fv) == golden_feats["weak"]).all()
+    lab, ss, ws = ert.cascade_classify_u8(golden_feats["hists"])
+    assert (ss == golden_feats["strong"]).all() and (ws == golden_feats["weak"]).all()
+
+
+def test_aran_sizes_exhaustive_small(ert, port):
+    """every (w,h) up to 60x60 incl. the exact-integer sqrt cases and exact-2x decimations: histograms identical"""
+    rng = np.random.RandomState(3)
+    plane = rng.randint(0, 256, (64, 64)).astype(np.uint8)
+    rects = [(0, 0, w, h) for w in range(3, 61, 1) for h in range(3, 61, 3) if port.L.port_aran_minor(w, h, 26) >= 1]
+    rects += [(1, 2, 2 * a, 52) for a in range(4, 27)] + [(0, 0, 50, 18), (0, 0, 18, 50), (3, 3, 52, 52), (0, 0, 13, 26)]
+    rects = np.array(rects, np.int32)
+    got = ert.lbp_hist(plane, rects)
+    for i, (x, y, w, h) in enumerate(rects):
+        assert (got[i] == port.lbp_hist(plane[y:y + h, x:x + w])).all(), (w, h)
+
+
+def test_svm_batch_vs_reference_golden(ert, golden_svm):
+    """FP64 on both sides, different summation order in the RBF distance: labels equal, probabilities within
+    1e-4 relative (north_star tolerance; observed ~1e-12)."""
+    label, prob = ert.svm_predict_probability(golden_svm["x_u8"])
+    assert (label == golden_svm["label"]).all()
+    rel = np.abs(prob - golden_svm["prob"]) / np.maximum(np.abs(golden_svm["prob"]), 1e-300)
+    assert rel.max() < 1e-4, rel.max()
+    label2, prob2 = ert.svm_predict_probability(golden_svm["x_u8"].astype(np.float64) / 255.0)
+    assert (label2 == label).all() and np.abs(prob2 - prob).max() < 1e-12
+
+
+def test_device_resident_entry_and_async_pair(ert, golden_frames):
+    torch = pytest.importorskip("torch")
+    ref = ert.detect_classify(golden_frames)
+    d = torch.from_numpy(golden_frames).cuda()
+    torch.cuda.synchronize()
+    ert.enqueue_device(d.data_ptr(), 3, 640, 480, 640 * 3)
+    got = ert.fetch()
+    pinned = torch.from_numpy(golden_frames).pin_memory()
+    ert.enqueue_host(pinned.data_ptr(), 3, 640, 480, 640 * 3)
+    got2 = ert.fetch()
+    for a, b, c in zip(ref.planes, got.planes, got2.planes):
+        assert (a.nodes == b.nodes).all() and (a.pool == b.pool).all() and (a.label == b.label).all()
+        assert (a.nodes == c.nodes).all() and (a.pool == c.pool).all() and (a.label == c.label).all()
+
+
+def test_error_behaviour(ert):
+    import ertext
+    e2 = ertext.ErText(load_cascades=False)
+    try:
+        with pytest.raises(ertext.ErtError):
+            e2.detect_classify(np.zeros((1, 32, 32, 3), np.uint8))          # classify without cascades
+        r = e2.detect_classify(np.zeros((1, 32, 32, 3), np.uint8), upto=ertext.STAGE_NMS)
+        assert len(r.planes) == 6
+        with pytest.raises(ertext.ErtError):
+            e2.load_cascade(0, "/nonexistent/strong.classifier")             # loader error like the reference's `return false`
+        with pytest.raises(ertext.ErtError):
+            e2.svm_predict_probability(np.zeros((1, 1800)))                  # model not loaded
+    finally:
+        e2.close()
+    with pytest.raises(ertext.ErtError):
+        ert.classify_regions(np.zeros((20, 20), np.uint8), np.array([[10, 10, 20, 20]], np.int32))   # rect outside plane
+
+
+def test_synthetic_full_hd_frame_vs_oracle(ert, port):
+    """configs[1]-shaped input: one synthetic 1080p frame, all 6 planes."""
+    from ertext import synth
+    pytest.importorskip("cv2")
+    frame = synth.s_text_frame(1234)
+    res = ert.detect_classify(frame)
+    ch = port.channels(frame)
+    for k in range(6):
+        exp = port.plane(ch[k], scores=True, canonical_order=True)
+        got = res.planes[k]
+        assert (got.nodes == exp["nodes"]).all() and (got.pool == exp["pool"]).all() and (got.label == exp["label"]).all()
+        assert (got.strong_score == exp["strong_score"]).all() and (got.weak_score == exp["weak_score"]).all()
