@@ -138,3 +138,35 @@ def test_synthetic_full_hd_frame_vs_oracle(ert, port):
         got = res.planes[k]
         assert (got.nodes == exp["nodes"]).all() and (got.pool == exp["pool"]).all() and (got.label == exp["label"]).all()
         assert (got.strong_score == exp["strong_score"]).all() and (got.weak_score == exp["weak_score"]).all()
+
+
+def test_cpp_facade_like_the_reference_callers(ert, port, golden_frames, tmp_path):
+    """Compile tests/cpp/facade_demo.cpp against host/ERFilter.hpp + libertext.so and run it the way
+    image_mode / video_mode drive the reference's ERFilter; compare with the Python binding's results."""
+    import subprocess, os
+    from conftest import ROOT, PKG
+    exe = str(tmp_path / "facade_demo")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", os.path.join(ROOT, "tests", "cpp", "facade_demo.cpp"), "-o", exe,
+                           "-L", PKG, "-l:libertext.so", "-Wl,-rpath," + PKG])
+    frame = golden_frames[0]
+    planes = port.channels(frame)
+    (tmp_path / "bgr.raw").write_bytes(frame.tobytes())
+    (tmp_path / "planes.raw").write_bytes(planes.tobytes())
+    assets = os.path.join(ROOT, "assets", "classifier")
+    out = subprocess.run([exe, str(tmp_path / "bgr.raw"), str(tmp_path / "planes.raw"), "640", "480",
+                          os.path.join(assets, "strong.classifier"), os.path.join(assets, "weak.classifier")],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    res = ert.detect_classify(frame)
+    td = [l.split() for l in lines if l.startswith("TD")]
+    st = [l.split() for l in lines if l.startswith("ST")]
+    assert len(td) == 6 and len(st) == 6
+    for p in range(6):
+        pr = res.planes[p]
+        exp = [str(p), "pool", str(len(pr.pool)), "strong", str(int((pr.label == 2).sum())), "weak", str(int((pr.label == 1).sum()))]
+        assert td[p][1:8] == exp and st[p][1:8] == exp, (td[p], st[p], exp)
+        assert td[p][9] == st[p][9]          # same tree through both routes
+    fv = [l for l in lines if l.startswith("FV")][0].split()
+    assert float(fv[1]) == 576.0              # 4 blocks x 144
+    assert "ASSERT ok" in out.stdout
