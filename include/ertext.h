@@ -88,6 +88,8 @@ ERT_API int ert_set_min_area(ert_ctx *ctx, int min_area);
 ERT_API int ert_set_return_hist(ert_ctx *ctx, int on);
 /* option (debug / A-B): 0 = skip the shared-memory tile pass and link every edge in global memory */
 ERT_API int ert_set_tile_local_union(ert_ctx *ctx, int on);
+/* tuning: tile shape / CTA size of the tile-build kernel (0 = default 64x32 pixels, 256 threads) */
+ERT_API int ert_set_tile_config(ert_ctx *ctx, int id);
 /* capacity hints (defaults: 16384 kept nodes and 2048 pooled regions per plane) */
 ERT_API int ert_set_capacity(ert_ctx *ctx, int kept_per_plane, int pool_per_plane);
 

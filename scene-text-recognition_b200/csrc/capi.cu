@@ -124,6 +124,7 @@ struct ert_ctx {
 	bool own_stream = true;
 	cudaEvent_t ev[12];
 	int local_union = 1;
+	int tile_cfg = 0;
 	int return_hist = 0;
 	int kept_cap = 16384, pool_cap = 2048;
 	int launches = 0;
@@ -213,6 +214,7 @@ int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 	if (dmalloc(&c->wk.kept, (size_t)P * c->kept_cap) || dmalloc(&c->wk.kept_count, (size_t)P) || dmalloc(&c->wk.status, 1)) return -1;
 	ERT_CUDA_CHECK(cudaMemset(c->wk.status, 0, sizeof(uint32_t)));
 	c->wk.node_blocks = 32;
+	c->wk.tile_cfg = c->tile_cfg;
 	c->nms_stride = nms_scratch_stride(c->kept_cap);
 	if (dmalloc(&c->d_nms_scratch, c->nms_stride * P)) return -1;
 	if (dmalloc(&c->d_out_nodes, (size_t)P * c->kept_cap) || dmalloc(&c->d_out_pool, (size_t)P * c->pool_cap)) return -1;
@@ -410,6 +412,11 @@ int ert_set_thresh_step(ert_ctx *c, int step)
 int ert_set_min_area(ert_ctx *c, int m) { c->prm.min_area = m; return 0; }
 int ert_set_return_hist(ert_ctx *c, int on) { c->return_hist = on; return 0; }
 int ert_set_tile_local_union(ert_ctx *c, int on) { c->local_union = on ? 1 : 0; return 0; }
+int ert_set_tile_config(ert_ctx *c, int id)
+{
+	if (id < 0 || id >= tile_config_count()) { set_error("tile config %d out of range", id); return -1; }
+	c->tile_cfg = id; c->wk.tile_cfg = id; return 0;
+}
 int ert_set_capacity(ert_ctx *c, int kept, int pool)
 {
 	if (kept < 16 || pool < 16 || kept > (1 << 22)) { set_error("bad capacity"); return -1; }

@@ -16,6 +16,7 @@ constexpr int      KEY_IDX_BITS = 26;
 constexpr uint32_t KEY_IDX_MASK = (1u << KEY_IDX_BITS) - 1u;
 constexpr uint32_t KEY_NONE     = 0xFFFFFFFFu;
 constexpr int      MAX_LEVELS   = 63;           // level field is 6 bits
+constexpr uint32_t NODE_COMPLETE = 0xFFFFFFFFu;  // NodeAttr::pend marker: interior node, totals final after the tile pass
 
 __host__ __device__ __forceinline__ uint32_t make_key(uint32_t level, uint32_t idx) { return (level << KEY_IDX_BITS) | idx; }
 __host__ __device__ __forceinline__ uint32_t key_level(uint32_t k) { return k >> KEY_IDX_BITS; }

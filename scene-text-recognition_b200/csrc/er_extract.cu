@@ -149,8 +149,10 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	uint32_t *xmn = cnt + TPX;
 	uint32_t *xmx = xmn + TPX;
 	uint32_t *ymn = xmx + TPX;
+	uint32_t *ymx = ymn + TPX;
+	uint16_t *rootlist = reinterpret_cast<uint16_t *>(ymx + TPX);
 	__shared__ __align__(8) uint64_t bar;
-	__shared__ uint32_t s_nroots, s_base, s_cursor, s_nlinks;
+	__shared__ uint32_t s_nroots, s_base, s_cursor, s_nlinks, s_nemit, s_minlvl, s_maxlvl;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int plane = blockIdx.y;
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	NodeAttr *attrP = attr_g + (size_t)plane * N;
 
 	// ---- stage the tile through TMA (one bulk copy per row, all completing on one mbarrier) ----
-	if (tid == 0) { mbar_init(&bar, 1); s_nroots = 0; s_cursor = 0; s_nlinks = 0; }
+	if (tid == 0) { mbar_init(&bar, 1); s_nroots = 0; s_cursor = 0; s_nlinks = 0; s_nemit = 0; s_minlvl = 255; s_maxlvl = 0; }
 	__syncthreads();
 	if (warp == 0) {
 		if (lane == 0) mbar_expect_tx(&bar, (uint32_t)(rows * TW));
@@ -191,6 +193,9 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		__syncwarp();
 		lvl[p] = (uint8_t)L;
 		par[p] = (L == 255 || end == lane) ? KEY_NONE : (((uint32_t)L << 16) | (uint32_t)(seg * 32 + end));
+		const uint32_t lmin = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)L);
+		const uint32_t lmax = __reduce_max_sync(0xFFFFFFFFu, (L == 255) ? 0u : (uint32_t)L);
+		if (lane == 0) { if (lmin < 255u) atomicMin(&s_minlvl, lmin); atomicMax(&s_maxlvl, lmax); }
 	}
 	__syncthreads();
 
@@ -234,7 +239,10 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 					if (!act) {
 						const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
 						if (i < nl) {
-							const uint32_t e = links[i];
+							// the list is drained from its END (bottom-right of the tile first): the level root of a
+							// node is its last pixel in raster order, so it is met first and stays put while the rows
+							// above attach to it directly -- chains stay ~1 hop deep instead of one hop per row
+							const uint32_t e = links[nl - 1u - i];
 							const uint32_t p = e >> 16, q = e & 0xFFFFu;
 							a = ((uint32_t)lvl[p] << 16) | p;
 							b = ((uint32_t)lvl[q] << 16) | q;
@@ -295,10 +303,12 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		}
 		__syncthreads();
 	}
-	for (int p = tid; p < TPX; p += NT) { cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymn[p] = 0xFFFFFFFFu; }
+	for (int p = tid; p < TPX; p += NT) { cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymn[p] = 0xFFFFFFFFu; ymx[p] = 0; }
 	__syncthreads();
 
-	// ---- phase D: own-level pixel count and bbox per tile-local node, one update per run ----
+	// ---- phase D: own-level pixel count and bbox per tile-local node, one update per run.
+	// acc word: bits 0..14 pixels, bits 15..29 nodes, bit 31 = node touches a seam (BORDER) ----
+	constexpr uint32_t ACC_NODE = 1u << 15, ACC_MASK = 0x7FFFu, ACC_BORDER = 0x80000000u;
 	for (int seg = warp; seg < SEGS; seg += NWARP) {
 		const int p = seg * 32 + lane;
 		const int y = p / TW, x = p % TW;
@@ -318,41 +328,134 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 			atomicMax(&xmx[r], (uint32_t)x);
 			atomicMin(&ymn[r], (uint32_t)y);
 		}
+		if (isroot) { atomicAdd(&cnt[p], ACC_NODE); ymx[p] = (uint32_t)y; }   // the level root is the node's last own-level pixel
 		const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, isroot);
-		if (lane == 0 && rmask) atomicAdd(&s_nroots, (uint32_t)__popc(rmask));
+		uint32_t wb = 0;
+		if (lane == 0 && rmask) wb = atomicAdd(&s_nroots, (uint32_t)__popc(rmask));
+		wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
+		if (isroot) rootlist[wb + __popc(rmask & ((1u << lane) - 1u))] = (uint16_t)p;
 	}
 	__syncthreads();
-	if (tid == 0) { s_base = s_nroots ? atomicAdd(&node_count[plane], s_nroots) : 0u; s_cursor = 0; }
+
+	// ---- phase D2: which tile-local nodes can still change?  Those holding a pixel on a side of the tile
+	// that faces another tile (and the flood's start candidates, pixels 0 / 1 / W of the plane), and all their
+	// ancestors.  Everything else is INTERIOR: its subtree is final here and never has to leave the SM. ----
+	if (local_union) {
+		const int ring = 2 * (TW + TH);
+		for (int i = tid; i < ring + 3; i += NT) {
+			int x, y;
+			bool on = true;
+			if (i < TW) { x = i; y = 0; on = (Y0 > 0); }
+			else if (i < 2 * TW) { x = i - TW; y = rows - 1; on = (Y0 + rows < P.H); }
+			else if (i < 2 * TW + TH) { x = 0; y = i - 2 * TW; on = (X0 > 0); }
+			else if (i < ring) { x = cols - 1; y = i - 2 * TW - TH; on = (X0 + cols < P.W); }
+			else {   // start candidates of the flood: global pixels 0, 1, W
+				const int gi = i - ring;
+				const int gx = (gi == 1) ? 1 : 0, gy = (gi == 2) ? 1 : 0;
+				x = gx - X0; y = gy - Y0;
+			}
+			if (!on || x < 0 || y < 0 || x >= cols || y >= rows) continue;
+			const int p = y * TW + x;
+			const uint32_t L = lvl[p];
+			if (L == 255) continue;
+			const uint32_t pk = par[p];
+			uint32_t r = (pk == KEY_NONE || (pk >> 16) != L) ? (uint32_t)p : (pk & 0xFFFFu);
+			for (int guard = 0; guard < 64; ++guard) {
+				const uint32_t old = atomicOr(&cnt[r], ACC_BORDER);
+				if (old & ACC_BORDER) break;
+				const uint32_t up = par[r];
+				if (up == KEY_NONE) break;
+				r = up & 0xFFFFu;
+			}
+		}
+	} else {
+		for (int p = tid; p < TPX; p += NT) if (lvl[p] != 255) cnt[p] |= ACC_BORDER;
+	}
 	__syncthreads();
 
-	// ---- phase E: emit tile-local nodes (global key space) and the root of every border pixel ----
-	for (int seg = warp; seg < SEGS; seg += NWARP) {
-		const int p = seg * 32 + lane;
-		const int y = p / TW, x = p % TW;
-		const uint32_t L = lvl[p];
-		const uint32_t pk = par[p];
-		const bool isroot = (L != 255) && (pk == KEY_NONE || (pk >> 16) != L);
-		const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, isroot);
-		uint32_t wbase = 0;
-		if (lane == 0 && rmask) wbase = atomicAdd(&s_cursor, (uint32_t)__popc(rmask));
-		wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-		if (L == 255) continue;
-		const uint32_t gidx = (uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x);
-		if (isroot) {
-			uint32_t gpar = KEY_NONE;
-			if (pk != KEY_NONE) {
-				const uint32_t q = pk & 0xFFFFu;
-				gpar = make_key(pk >> 16, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
+	// ---- phase D3: fold interior subtrees bottom-up, one level per round (a tile holds few distinct levels) ----
+	const uint32_t nroots = s_nroots;
+	if (local_union) {
+		const int lo = (int)s_minlvl, hi_l = (int)s_maxlvl;
+		for (int Lc = lo; Lc < hi_l; ++Lc) {
+			for (uint32_t i = tid; i < nroots; i += NT) {
+				const uint32_t p = rootlist[i];
+				if (lvl[p] != Lc) continue;
+				const uint32_t acc = cnt[p];
+				if (acc & ACC_BORDER) continue;
+				const uint32_t up = par[p];
+				if (up == KEY_NONE) continue;
+				const uint32_t q = up & 0xFFFFu;
+				atomicAdd(&cnt[q], acc);           // pixels and node count travel together
+				atomicMin(&xmn[q], xmn[p]); atomicMax(&xmx[q], xmx[p]);
+				atomicMin(&ymn[q], ymn[p]); atomicMax(&ymx[q], ymx[p]);
 			}
-			parP[gidx] = gpar;
-			uint4 *a = reinterpret_cast<uint4 *>(&attrP[gidx]);
-			a[0] = make_uint4(cnt[p], 1u, 0u, 0u);
-			a[1] = make_uint4((uint32_t)X0 + xmn[p], (uint32_t)Y0 + ymn[p], (uint32_t)X0 + xmx[p], (uint32_t)(Y0 + y));
-			const uint32_t pos = s_base + wbase + (uint32_t)__popc(rmask & ((1u << lane) - 1u));
-			node_list[(size_t)plane * N + pos] = make_key(L, gidx);
-		} else if (x == 0 || y == 0 || x == cols - 1 || y == rows - 1) {
+			__syncthreads();
+		}
+	}
+
+	// ---- phase E: emit.  BORDER nodes go to the global forest with what they have gathered (own pixels +
+	// interior descendants); interior nodes are emitted only if the reference would keep them
+	// (area > MIN_AREA), already complete (pend = NODE_COMPLETE); seam pixels publish their root. ----
+	uint32_t my_emit = 0;
+	for (uint32_t i = tid; i < nroots; i += NT) {
+		const uint32_t acc = cnt[rootlist[i]];
+		const bool emit = (acc & ACC_BORDER) || (int)((acc & ACC_MASK) + ((acc >> 15) & ACC_MASK)) > P.min_area;
+		my_emit += emit ? 1u : 0u;
+	}
+	my_emit = __reduce_add_sync(0xFFFFFFFFu, my_emit);
+	if (lane == 0 && my_emit) atomicAdd(&s_nemit, my_emit);
+	__syncthreads();
+	if (tid == 0) { s_base = s_nemit ? atomicAdd(&node_count[plane], s_nemit) : 0u; s_cursor = 0; }
+	__syncthreads();
+	for (uint32_t i0 = warp * 32; i0 < nroots; i0 += NT) {
+		const uint32_t i = i0 + lane;
+		bool emit = false;
+		uint32_t p = 0, acc = 0;
+		if (i < nroots) {
+			p = rootlist[i];
+			acc = cnt[p];
+			emit = (acc & ACC_BORDER) || (int)((acc & ACC_MASK) + ((acc >> 15) & ACC_MASK)) > P.min_area;
+		}
+		const uint32_t emask = __ballot_sync(0xFFFFFFFFu, emit);
+		uint32_t wbase = 0;
+		if (lane == 0 && emask) wbase = atomicAdd(&s_cursor, (uint32_t)__popc(emask));
+		wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+		if (!emit) continue;
+		const int y = (int)p / TW, x = (int)p % TW;
+		const uint32_t L = lvl[p];
+		const uint32_t gidx = (uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x);
+		const uint32_t pk = par[p];
+		uint32_t gpar = KEY_NONE;
+		if (pk != KEY_NONE) {
 			const uint32_t q = pk & 0xFFFFu;
-			parP[gidx] = make_key(L, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
+			gpar = make_key(pk >> 16, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
+		}
+		parP[gidx] = gpar;
+		uint4 *a = reinterpret_cast<uint4 *>(&attrP[gidx]);
+		a[0] = make_uint4(acc & ACC_MASK, (acc >> 15) & ACC_MASK, (acc & ACC_BORDER) ? 0u : NODE_COMPLETE, 0u);
+		a[1] = make_uint4((uint32_t)X0 + xmn[p], (uint32_t)Y0 + ymn[p], (uint32_t)X0 + xmx[p], (uint32_t)Y0 + ymx[p]);
+		const uint32_t pos = s_base + wbase + (uint32_t)__popc(emask & ((1u << lane) - 1u));
+		node_list[(size_t)plane * N + pos] = make_key(L, gidx);
+	}
+	{
+		const int ring = 2 * (TW + TH);
+		for (int i = tid; i < ring + 3; i += NT) {
+			int x, y;
+			if (i < TW) { x = i; y = 0; }
+			else if (i < 2 * TW) { x = i - TW; y = rows - 1; }
+			else if (i < 2 * TW + TH) { x = 0; y = i - 2 * TW; }
+			else if (i < ring) { x = cols - 1; y = i - 2 * TW - TH; }
+			else { const int gi = i - ring; x = ((gi == 1) ? 1 : 0) - X0; y = ((gi == 2) ? 1 : 0) - Y0; }
+			if (x < 0 || y < 0 || x >= cols || y >= rows) continue;
+			const int p = y * TW + x;
+			const uint32_t L = lvl[p];
+			if (L == 255) continue;
+			const uint32_t pk = par[p];
+			if (pk == KEY_NONE || (pk >> 16) != L) continue;   // roots were written above
+			const uint32_t q = pk & 0xFFFFu;
+			parP[(uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x)] =
+				make_key(L, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
 		}
 	}
 }
@@ -439,11 +542,21 @@ __global__ void k_fold(ExtractParams P, uint32_t *__restrict__ par_g, NodeAttr *
 	const uint32_t n = node_count[plane];
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint32_t g = node_list[(size_t)plane * N + i];
-		const uint32_t f = find_g(parP, g);
 		NodeAttr *ag = &attrP[key_idx(g)];
+		if (ag->pend == NODE_COMPLETE) {
+			// interior node, finished inside its tile; only its parent may have been merged across a seam
+			const uint32_t pk = parP[key_idx(g)];
+			if (pk != KEY_NONE) {
+				const uint32_t fp = find_g(parP, pk);
+				if (fp != pk) parP[key_idx(g)] = fp;
+			}
+			continue;
+		}
+		const uint32_t f = find_g(parP, g);
 		if (f != g) {
 			NodeAttr *af = &attrP[key_idx(f)];
 			atomicAdd(&af->cnt, ag->cnt);
+			if (ag->nn > 1) atomicAdd(&af->nn, ag->nn - 1u);   // its interior descendants are nodes of the final node's subtree
 			atomicMin(&af->x0, ag->x0); atomicMin(&af->y0, ag->y0);
 			atomicMax(&af->x1, ag->x1); atomicMax(&af->y1, ag->y1);
 			ag->nn = 0;   // alias marker
@@ -574,11 +687,24 @@ __global__ void k_emit_kept(ExtractParams P, const uint32_t *__restrict__ par_g,
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-constexpr int TILE_W = 64, TILE_H = 32, TILE_NT = 256;
-
 int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 
-size_t tile_smem_bytes() { return (size_t)TILE_W * TILE_H * (1 + 5 * 4); }
+// tile configurations (selectable at run time for tuning; id 0 is the default)
+struct TileCfg { int tw, th, nt; };
+static const TileCfg g_tile_cfgs[] = {{64, 32, 256}, {64, 64, 256}, {64, 64, 512}, {128, 32, 256}, {128, 32, 512}, {128, 64, 512}, {64, 32, 128}, {32, 32, 128}};
+int tile_config_count() { return (int)(sizeof(g_tile_cfgs) / sizeof(g_tile_cfgs[0])); }
+
+template <int TW, int TH, int NT>
+static int launch_tile(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st)
+{
+	const size_t smem = (size_t)TW * TH * (1 + 6 * 4 + 2);
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TW, TH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const int tiles_x = (P.W + TW - 1) / TW, tiles_y = (P.H + TH - 1) / TH;
+	dim3 grid(tiles_x * tiles_y, P.n_planes);
+	k_tile_build<TW, TH, NT><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union);
+	ERT_CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
 
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st)
 {
@@ -591,19 +717,24 @@ int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, i
 int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
                    cudaEvent_t ev_tile_begin, cudaEvent_t ev_tile_end)
 {
-	const size_t smem = tile_smem_bytes();
-		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TILE_W, TILE_H, TILE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
+	const TileCfg tc = g_tile_cfgs[(wk.tile_cfg >= 0 && wk.tile_cfg < tile_config_count()) ? wk.tile_cfg : 0];
+	const int TILE_W = tc.tw, TILE_H = tc.th;
 	ERT_CUDA_CHECK(cudaMemsetAsync(wk.node_count, 0, sizeof(uint32_t) * P.n_planes, st));
 	ERT_CUDA_CHECK(cudaMemsetAsync(wk.kept_count, 0, sizeof(uint32_t) * P.n_planes, st));
-	{
-		dim3 grid(tiles_x * tiles_y, P.n_planes);
-		if (ev_tile_begin) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_begin, st));
-		k_tile_build<TILE_W, TILE_H, TILE_NT><<<grid, TILE_NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count,
-		                                                                  wk.status, tiles_x, local_union);
-		ERT_CUDA_CHECK(cudaGetLastError());
-		if (ev_tile_end) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_end, st));
+	if (ev_tile_begin) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_begin, st));
+	int rc = -1;
+	switch (wk.tile_cfg) {
+	case 1: rc = launch_tile<64, 64, 256>(P, d_planes, wk, local_union, st); break;
+	case 2: rc = launch_tile<64, 64, 512>(P, d_planes, wk, local_union, st); break;
+	case 3: rc = launch_tile<128, 32, 256>(P, d_planes, wk, local_union, st); break;
+	case 4: rc = launch_tile<128, 32, 512>(P, d_planes, wk, local_union, st); break;
+	case 5: rc = launch_tile<128, 64, 512>(P, d_planes, wk, local_union, st); break;
+	case 6: rc = launch_tile<64, 32, 128>(P, d_planes, wk, local_union, st); break;
+	case 7: rc = launch_tile<32, 32, 128>(P, d_planes, wk, local_union, st); break;
+	default: rc = launch_tile<64, 32, 256>(P, d_planes, wk, local_union, st); break;
 	}
+	if (rc) return rc;
+	if (ev_tile_end) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_end, st));
 	{
 		// with local_union == 0 every pixel is its own tile-local node and ALL edges are seams (debug A/B mode)
 		const int tw = local_union ? TILE_W : 1, th = local_union ? TILE_H : 1;

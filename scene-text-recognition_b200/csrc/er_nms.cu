@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 }
 
 constexpr int NMS_NT = 512;
-constexpr int NMS_SMEM_NODES = 4096;
+constexpr int NMS_SMEM_NODES = 2048;   // larger planes fall back to the global scratch view
 
 size_t nms_scratch_stride(int kept_cap)
 {

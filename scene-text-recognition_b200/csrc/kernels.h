@@ -15,6 +15,7 @@ struct ExtractWork {
 	uint32_t *kept_count;   // [n_planes]
 	uint32_t *status;       // [1]
 	int node_blocks;        // grid.x of the node-list kernels
+	int tile_cfg;           // index into the tile configuration table
 };
 
 struct NmsParams {
@@ -49,6 +50,7 @@ struct SvmDev {
 };
 
 int extract_pitch(int W);
+int tile_config_count();
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st);
 int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
                    cudaEvent_t ev_tile_begin = nullptr, cudaEvent_t ev_tile_end = nullptr);
