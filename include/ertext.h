@@ -90,6 +90,8 @@ ERT_API int ert_set_return_hist(ert_ctx *ctx, int on);
 ERT_API int ert_set_tile_local_union(ert_ctx *ctx, int on);
 /* tuning: tile shape / CTA size of the tile-build kernel (0 = default 64x32 pixels, 256 threads) */
 ERT_API int ert_set_tile_config(ert_ctx *ctx, int id);
+/* debug: per-phase cycle sums (clock64, thread 0 of every CTA) of the tile-build kernel since the last call */
+ERT_API int ert_debug_phase_cycles(ert_ctx *ctx, int enable, unsigned long long *out16);
 /* capacity hints (defaults: 16384 kept nodes and 2048 pooled regions per plane) */
 ERT_API int ert_set_capacity(ert_ctx *ctx, int kept_per_plane, int pool_per_plane);
 

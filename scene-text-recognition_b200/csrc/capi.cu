@@ -133,6 +133,7 @@ struct ert_ctx {
 	SvmHost svm;
 	uint8_t aran_tbl_h[64];
 	uint8_t *d_aran_tbl = nullptr;
+	unsigned long long *d_prof = nullptr;
 
 	// workspace geometry
 	int W = 0, H = 0, pitch = 0, planes_cap = 0, frames_cap = 0;
@@ -215,6 +216,7 @@ int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 	ERT_CUDA_CHECK(cudaMemset(c->wk.status, 0, sizeof(uint32_t)));
 	c->wk.node_blocks = 32;
 	c->wk.tile_cfg = c->tile_cfg;
+	c->wk.prof = c->d_prof;
 	c->nms_stride = nms_scratch_stride(c->kept_cap);
 	if (dmalloc(&c->d_nms_scratch, c->nms_stride * P)) return -1;
 	if (dmalloc(&c->d_out_nodes, (size_t)P * c->kept_cap) || dmalloc(&c->d_out_pool, (size_t)P * c->pool_cap)) return -1;
@@ -412,6 +414,14 @@ int ert_set_thresh_step(ert_ctx *c, int step)
 int ert_set_min_area(ert_ctx *c, int m) { c->prm.min_area = m; return 0; }
 int ert_set_return_hist(ert_ctx *c, int on) { c->return_hist = on; return 0; }
 int ert_set_tile_local_union(ert_ctx *c, int on) { c->local_union = on ? 1 : 0; return 0; }
+int ert_debug_phase_cycles(ert_ctx *c, int enable, unsigned long long *out16)
+{
+	if (enable && !c->d_prof) { ERT_CUDA_CHECK(cudaMalloc((void **)&c->d_prof, 16 * sizeof(unsigned long long))); ERT_CUDA_CHECK(cudaMemset(c->d_prof, 0, 16 * sizeof(unsigned long long))); }
+	if (out16 && c->d_prof) { ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream)); ERT_CUDA_CHECK(cudaMemcpy(out16, c->d_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost)); ERT_CUDA_CHECK(cudaMemset(c->d_prof, 0, 16 * sizeof(unsigned long long))); }
+	if (!enable && c->d_prof) { cudaFree(c->d_prof); c->d_prof = nullptr; }
+	c->wk.prof = c->d_prof;
+	return 0;
+}
 int ert_set_tile_config(ert_ctx *c, int id)
 {
 	if (id < 0 || id >= tile_config_count()) { set_error("tile config %d out of range", id); return -1; }

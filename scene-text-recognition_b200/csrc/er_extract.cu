@@ -3,7 +3,7 @@
 //
 // Pipeline per batch of planes (a plane = one u8 channel image, 6 per BGR frame):
 //   k_channels      BGR -> Y, Cr, Cb planes (inverted planes are derived on the fly)
-//   k_tile_build    per 64x32 tile: TMA bulk-copy the tile into shared memory, quantise to levels,
+//   k_tile_build    per 64x32 tile (512 threads): TMA bulk-copy the tile into shared memory, quantise to levels,
 //                   build the tile-local component forest with a keyed lock-free union-find in
 //                   shared memory, count own-level pixels / bbox per tile-local node, emit nodes
 //   k_seam_link     stitch tiles: the same keyed union-find on the (few) edges that cross tile seams
@@ -136,12 +136,14 @@ template <int TW, int TH, int NT>
 __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneSrc *__restrict__ planes,
                                                    uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
                                                    uint32_t *__restrict__ node_list, uint32_t *__restrict__ node_count,
-                                                   uint32_t *status, int tiles_x, int local_union)
+                                                   uint32_t *status, int tiles_x, int local_union, unsigned long long *prof)
 {
+	long long t_prev = prof ? clock64() : 0;
+#define ERT_PHASE(i) do { if (prof && threadIdx.x == 0) { const long long t_now = clock64(); atomicAdd(&prof[i], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
 	constexpr int TPX = TW * TH;
 	constexpr int SEGS = TPX / 32;
 	constexpr int NWARP = NT / 32;
-	static_assert(TW % 32 == 0 && TPX <= 65536, "tile shape");
+	static_assert(TW % 32 == 0 && TPX <= 32768, "tile shape");
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t *lvl = smem;                                     // TMA destination, converted to levels in place
 	uint32_t *par = reinterpret_cast<uint32_t *>(smem + TPX);
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	}
 	mbar_wait(&bar, 0);
 
+	ERT_PHASE(0);
 	// ---- phase A: quantise, horizontal same-level runs become chains without atomics ----
 	for (int seg = warp; seg < SEGS; seg += NWARP) {
 		const int p = seg * 32 + lane;
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	}
 	__syncthreads();
 
+	ERT_PHASE(1);
 	// ---- phase B: the remaining in-tile edges.  B1 compacts them into a work list in shared memory
 	// (aliasing cnt/xmn, which are not live yet); B2 drains the list with warp-converged state machines:
 	// every lane owns one edge at a time, all lanes advance one hop per iteration (no divergent inner
@@ -226,6 +230,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 			if (ev) links[base + __popc(mh) + __popc(mv & lt)] = ((uint32_t)p << 16) | (uint32_t)(p + TW);
 		}
 		__syncthreads();
+		ERT_PHASE(2);
 		{
 			const uint32_t nl = s_nlinks;
 			uint32_t a = 0, b = 0;
@@ -270,6 +275,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		}
 		__syncthreads();
 
+		ERT_PHASE(3);
 		// ---- phase C: every pixel points at its level root, every root at its parent's level root;
 		// also (re)initialise the accumulators that aliased the work list ----
 		for (int p0 = warp * 32; p0 < TPX; p0 += NT) {
@@ -303,6 +309,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		}
 		__syncthreads();
 	}
+	ERT_PHASE(4);
 	for (int p = tid; p < TPX; p += NT) { cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymn[p] = 0xFFFFFFFFu; ymx[p] = 0; }
 	__syncthreads();
 
@@ -337,6 +344,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	}
 	__syncthreads();
 
+	ERT_PHASE(5);
 	// ---- phase D2: which tile-local nodes can still change?  Those holding a pixel on a side of the tile
 	// that faces another tile (and the flood's start candidates, pixels 0 / 1 / W of the plane), and all their
 	// ancestors.  Everything else is INTERIOR: its subtree is final here and never has to leave the SM. ----
@@ -373,6 +381,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	}
 	__syncthreads();
 
+	ERT_PHASE(6);
 	// ---- phase D3: fold interior subtrees bottom-up, one level per round (a tile holds few distinct levels) ----
 	const uint32_t nroots = s_nroots;
 	if (local_union) {
@@ -394,6 +403,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		}
 	}
 
+	ERT_PHASE(7);
 	// ---- phase E: emit.  BORDER nodes go to the global forest with what they have gathered (own pixels +
 	// interior descendants); interior nodes are emitted only if the reference would keep them
 	// (area > MIN_AREA), already complete (pend = NODE_COMPLETE); seam pixels publish their root. ----
@@ -458,7 +468,10 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 				make_key(L, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
 		}
 	}
+	ERT_PHASE(8);
+#undef ERT_PHASE
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // global-memory keyed union-find (seams)
@@ -691,7 +704,7 @@ int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 
 // tile configurations (selectable at run time for tuning; id 0 is the default)
 struct TileCfg { int tw, th, nt; };
-static const TileCfg g_tile_cfgs[] = {{64, 32, 256}, {64, 64, 256}, {64, 64, 512}, {128, 32, 256}, {128, 32, 512}, {128, 64, 512}, {64, 32, 128}, {32, 32, 128}};
+static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {64, 64, 512}, {128, 32, 512}, {32, 32, 256}, {128, 64, 512}};
 int tile_config_count() { return (int)(sizeof(g_tile_cfgs) / sizeof(g_tile_cfgs[0])); }
 
 template <int TW, int TH, int NT>
@@ -701,7 +714,7 @@ static int launch_tile(const ExtractParams &P, const PlaneSrc *d_planes, Extract
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TW, TH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const int tiles_x = (P.W + TW - 1) / TW, tiles_y = (P.H + TH - 1) / TH;
 	dim3 grid(tiles_x * tiles_y, P.n_planes);
-	k_tile_build<TW, TH, NT><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union);
+	k_tile_build<TW, TH, NT><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union, wk.prof);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
@@ -724,14 +737,12 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	if (ev_tile_begin) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_begin, st));
 	int rc = -1;
 	switch (wk.tile_cfg) {
-	case 1: rc = launch_tile<64, 64, 256>(P, d_planes, wk, local_union, st); break;
+	case 1: rc = launch_tile<64, 32, 256>(P, d_planes, wk, local_union, st); break;
 	case 2: rc = launch_tile<64, 64, 512>(P, d_planes, wk, local_union, st); break;
-	case 3: rc = launch_tile<128, 32, 256>(P, d_planes, wk, local_union, st); break;
-	case 4: rc = launch_tile<128, 32, 512>(P, d_planes, wk, local_union, st); break;
+	case 3: rc = launch_tile<128, 32, 512>(P, d_planes, wk, local_union, st); break;
+	case 4: rc = launch_tile<32, 32, 256>(P, d_planes, wk, local_union, st); break;
 	case 5: rc = launch_tile<128, 64, 512>(P, d_planes, wk, local_union, st); break;
-	case 6: rc = launch_tile<64, 32, 128>(P, d_planes, wk, local_union, st); break;
-	case 7: rc = launch_tile<32, 32, 128>(P, d_planes, wk, local_union, st); break;
-	default: rc = launch_tile<64, 32, 256>(P, d_planes, wk, local_union, st); break;
+	default: rc = launch_tile<64, 32, 512>(P, d_planes, wk, local_union, st); break;
 	}
 	if (rc) return rc;
 	if (ev_tile_end) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_end, st));

@@ -16,6 +16,7 @@ struct ExtractWork {
 	uint32_t *status;       // [1]
 	int node_blocks;        // grid.x of the node-list kernels
 	int tile_cfg;           // index into the tile configuration table
+	unsigned long long *prof;   // optional [16] per-phase cycle sums of k_tile_build (debug)
 };
 
 struct NmsParams {

@@ -36,7 +36,7 @@ class ErtResult(C.Structure):
 
 EXPORTS = [
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
-    "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_set_capacity", "ert_load_cascade",
+    "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
     "ert_load_svm", "ert_svm_nr_class", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
     "ert_fetch_result", "ert_planes_detect", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
     "ert_cascade_predict_batch", "ert_cascade_classify_u8", "ert_svm_predict_probability_batch",
@@ -64,6 +64,7 @@ def load_library():
     for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_int]
     L.ert_set_capacity.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ert_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
     L.ert_load_cascade.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.ert_load_svm.argtypes = [C.c_void_p, C.c_char_p]
     L.ert_svm_nr_class.argtypes = [C.c_void_p]
@@ -175,6 +176,11 @@ class ErText:
 
     def set_tile_config(self, i):
         self._check(self.L.ert_set_tile_config(self.ctx, i))
+
+    def phase_cycles(self, enable=True):
+        out = (C.c_uint64 * 16)()
+        self._check(self.L.ert_debug_phase_cycles(self.ctx, int(enable), out))
+        return list(out)
 
     def set_capacity(self, kept, pool):
         self._check(self.L.ert_set_capacity(self.ctx, kept, pool))

@@ -9,10 +9,12 @@ from ertext import synth
 frames = synth.s_text_batch(1234, 8)
 e = ertext.ErText()
 ref = None
-names = ["64x32x256", "64x64x256", "64x64x512", "128x32x256", "128x32x512", "128x64x512", "64x32x128", "32x32x128"]
+names = ["64x32x512", "64x32x256", "64x64x512", "128x32x512", "32x32x256", "128x64x512"]
 only = [int(a) for a in sys.argv[1:]] or list(range(len(names)))
+e.phase_cycles(True)
 for cfg in only:
     e.set_tile_config(cfg)
+    e.detect_classify(frames); e.phase_cycles(True)
     best = None
     for it in range(4):
         r = e.detect_classify(frames)
@@ -23,5 +25,7 @@ for cfg in only:
     if ref is None:
         ref = sig
     same = sig == ref
+    pc = e.phase_cycles(True); tot = float(sum(pc)) or 1.0
+    print("   phases %: setup %.1f A %.1f B1 %.1f B2 %.1f init %.1f D %.1f C %.1f D2 %.1f D3 %.1f E %.1f" % tuple(100 * v / tot for v in pc[:9] + [0]) if False else "   phases %%: " + " ".join("%s %.1f" % (n, 100 * v / tot) for n, v in zip(["setup+TMA", "A", "B1", "B2", "C", "init+D", "D2", "D3", "E"], pc[:9])))
     print("cfg %d %-11s tile %.3f ms  extract %.3f  nms %.3f  classify %.3f  total %.3f  status %d  same_as_first %s" % (
         cfg, names[cfg], best[6], best[0], best[1], best[2], best[5], r.status, same), flush=True)
