@@ -347,8 +347,20 @@ static int sortent_cmp(const void *a, const void *b)
 	if (x->k != y->k) return x->k < y->k ? -1 : 1;
 	return x->id < y->id ? -1 : (x->id > y->id);
 }
+static PTree *g_sort_tree;
+static int sortent_cmp9(const void *a, const void *b)
+{
+	const SortEnt *x = (const SortEnt *)a, *y = (const SortEnt *)b;
+	if (x->k != y->k) return x->k < y->k ? -1 : 1;
+	const PNode *p = &g_sort_tree->nd[x->id], *q = &g_sort_tree->nd[y->id];
+	if (p->area != q->area) return p->area > q->area ? -1 : 1;
+	if (p->x1 != q->x1) return p->x1 > q->x1 ? -1 : 1;
+	if (p->y1 != q->y1) return p->y1 > q->y1 ? -1 : 1;
+	return x->id < y->id ? -1 : (x->id > y->id);
+}
 PORT_API void port_sort_children(PTree *t, int mode)
 {
+	g_sort_tree = t;
 	SortEnt *tmp = (SortEnt *)malloc(sizeof(SortEnt) * (size_t)(t->n + 1));
 	for (int i = 0; i < t->n; i++) {
 		if (!t->nd[i].alive || t->nd[i].child < 0) continue;
@@ -365,13 +377,13 @@ PORT_API void port_sort_children(PTree *t, int mode)
 			case 6: key = -(long long)k; break;
 			case 7: key = -((long long)e->y1 * 100000 + e->x0); break;
 			case 8: key = -((long long)e->y0 * 100000 + e->x1); break;
-			case 9: /* the GPU path's canonical order: descending (y0, x0, level, area); x1,y1 below */
-				key = -((((long long)e->y0 * 8192 + e->x0) * 64 + e->level) * 4194304LL + (e->area & 4194303)); break;
+			case 9: /* the GPU path's canonical order: descending (y0, x0, level), then area, x1, y1 (see sortent_cmp9) */
+				key = -(((long long)e->y0 * 8192 + e->x0) * 64 + e->level); break;
 			default: key = k; break;
 			}
 			tmp[k].k = key; tmp[k].id = c; k++;
 		}
-		qsort(tmp, (size_t)k, sizeof(SortEnt), sortent_cmp);
+		qsort(tmp, (size_t)k, sizeof(SortEnt), mode == 9 ? sortent_cmp9 : sortent_cmp);
 		t->nd[i].child = tmp[0].id;
 		for (int j = 0; j < k; j++) t->nd[tmp[j].id].next = (j + 1 < k) ? tmp[j + 1].id : -1;
 	}

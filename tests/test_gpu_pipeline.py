@@ -170,3 +170,36 @@ def test_cpp_facade_like_the_reference_callers(ert, port, golden_frames, tmp_pat
     fv = [l for l in lines if l.startswith("FV")][0].split()
     assert float(fv[1]) == 576.0              # 4 blocks x 144
     assert "ASSERT ok" in out.stdout
+
+
+def test_4k_three_plane_four_scale_pyramid(ert, port):
+    """BASELINE config 4: 3840x2160, planes Y/Cr/Cb, scales 1, 1/2, 1/4, 1/8 (the reference has no pyramid: a level
+    is the same per-plane path on the cv2-resized plane).  Full parity vs the oracle on every level."""
+    cv2 = pytest.importorskip("cv2")
+    from ertext import synth
+    frame = synth.s_text_frame(77, 3840, 2160, n_glyphs=300)
+    planes = port.channels(frame)[:3]
+    for s in (1, 2, 4, 8):
+        w, h = 3840 // s, 2160 // s
+        lvl = np.stack([pl if s == 1 else cv2.resize(pl, (w, h), interpolation=cv2.INTER_LINEAR) for pl in planes])
+        res = ert.planes_detect(lvl)
+        assert res.status == 0
+        for k in range(3):
+            exp = port.plane(lvl[k], scores=True, canonical_order=True)
+            got = res.planes[k]
+            assert got.nodes.shape == exp["nodes"].shape and (got.nodes == exp["nodes"]).all(), (s, k)
+            assert (got.pool == exp["pool"]).all() and (got.label == exp["label"]).all(), (s, k)
+            assert (got.strong_score == exp["strong_score"]).all() and (got.weak_score == exp["weak_score"]).all(), (s, k)
+
+
+def test_noise_full_hd_worst_case(ert, port):
+    """S-noise (0.39 tree nodes per pixel): capacity and parity on the worst-case plane."""
+    from ertext import synth
+    frame = synth.s_noise_frame(0)
+    res = ert.detect_classify(frame)
+    assert res.status == 0
+    ch = port.channels(frame)
+    for k in (0, 4):
+        exp = port.plane(ch[k], scores=True, canonical_order=True)
+        got = res.planes[k]
+        assert (got.nodes == exp["nodes"]).all() and (got.pool == exp["pool"]).all() and (got.label == exp["label"]).all()
