@@ -101,6 +101,8 @@ ERT_API int ert_load_cascade(ert_ctx *ctx, int which, const char *path);
 /* svm_load_model  (src/svm.cpp:2876; inc/svm.h:77).  c_svc + rbf probability models. */
 ERT_API int ert_load_svm(ert_ctx *ctx, const char *path);
 ERT_API int ert_svm_nr_class(ert_ctx *ctx);   /* svm_get_nr_class (inc/svm.h:81) */
+/* u8 features: 1 (default) = RBF distances as two exact-integer tcgen05 GEMMs (kind::i8); 0 = FP64 CUDA-core kernel */
+ERT_API int ert_set_svm_tensor_cores(ert_ctx *ctx, int on);
 ERT_API int ert_svm_dims(ert_ctx *ctx);
 
 /* ---- the batched hot path ---------------------------------------------------------------

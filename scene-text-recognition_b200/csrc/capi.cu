@@ -80,10 +80,15 @@ struct SvmHost {
 	std::vector<int> label, nsv, start;
 	double *d_sv = nullptr, *d_coef = nullptr, *d_rho = nullptr, *d_probA = nullptr, *d_probB = nullptr;
 	int *d_label = nullptr, *d_nsv = nullptr, *d_start = nullptr;
+	std::vector<uint8_t> svj; std::vector<int8_t> sve; std::vector<double> ss;
+	uint8_t *d_svj = nullptr; int8_t *d_sve = nullptr; double *d_ss = nullptr;
+	double inv_s255 = 0;
+	bool use_tc = true;
 	SvmDev dev() const
 	{
 		SvmDev m; m.nr_class = nr_class; m.l = l; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef;
 		m.rho = d_rho; m.probA = d_probA; m.probB = d_probB; m.label = d_label; m.nsv = d_nsv; m.start = d_start;
+		m.svj = use_tc ? d_svj : nullptr; m.sve = d_sve; m.ss = d_ss; m.inv_s255 = inv_s255;
 		return m;
 	}
 };
@@ -400,6 +405,7 @@ void ert_destroy(ert_ctx *c)
 	for (int k = 0; k < 2; k++) { cudaFree(c->casc[k].d_stumps); cudaFree(c->casc[k].d_len); cudaFree(c->casc[k].d_thr); }
 	cudaFree(c->svm.d_sv); cudaFree(c->svm.d_coef); cudaFree(c->svm.d_rho); cudaFree(c->svm.d_probA); cudaFree(c->svm.d_probB);
 	cudaFree(c->svm.d_label); cudaFree(c->svm.d_nsv); cudaFree(c->svm.d_start);
+	cudaFree(c->svm.d_svj); cudaFree(c->svm.d_sve); cudaFree(c->svm.d_ss);
 	c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
 	for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -567,6 +573,37 @@ int ert_load_svm(ert_ctx *c, const char *path)
 	m.start.assign((size_t)m.nr_class, 0);
 	for (int i = 1; i < m.nr_class; i++) m.start[i] = m.start[i - 1] + m.nsv[i - 1];
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	// tensor-core tables: v = j/255 + eps with j = round(255 v); e = round(S * eps), S = 127 / max|eps|
+	if (m.dims <= svm_tc_kpad() && m.l <= svm_tc_npad()) {
+		const int KP = svm_tc_kpad(), NP = svm_tc_npad();
+		m.svj.assign((size_t)NP * KP, 0); m.sve.assign((size_t)NP * KP, 0); m.ss.assign((size_t)m.l, 0.0);
+		double maxeps = 0;
+		bool ok = true;
+		for (int i = 0; i < m.l && ok; i++)
+			for (int d = 0; d < m.dims; d++) {
+				const double v = m.sv[(size_t)i * m.dims + d];
+				if (v < 0 || v > 1.0 + 1e-9) { ok = false; break; }
+				const double j = floor(v * 255.0 + 0.5);
+				maxeps = std::max(maxeps, fabs(v - j / 255.0));
+			}
+		if (ok) {
+			const double S = (maxeps > 0) ? 127.0 / maxeps : 1.0;
+			for (int i = 0; i < m.l; i++) {
+				double acc = 0;
+				for (int d = 0; d < m.dims; d++) {
+					const double v = m.sv[(size_t)i * m.dims + d];
+					const double j = floor(v * 255.0 + 0.5);
+					m.svj[(size_t)i * KP + d] = (uint8_t)j;
+					m.sve[(size_t)i * KP + d] = (int8_t)lrint((v - j / 255.0) * S);
+					acc += v * v;
+				}
+				m.ss[i] = acc;
+			}
+			m.inv_s255 = 1.0 / (255.0 * S);
+			if (dev_upload(&m.d_svj, m.svj) || dev_upload(&m.d_sve, m.sve) || dev_upload(&m.d_ss, m.ss)) return -1;
+		}
+	}
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
 	if (dev_upload(&m.d_sv, m.sv) || dev_upload(&m.d_coef, m.coef) || dev_upload(&m.d_rho, m.rho) || dev_upload(&m.d_probA, m.probA) ||
 	    dev_upload(&m.d_probB, m.probB) || dev_upload(&m.d_label, m.label) || dev_upload(&m.d_nsv, m.nsv) || dev_upload(&m.d_start, m.start)) return -1;
 	m.loaded = true;
@@ -574,6 +611,7 @@ int ert_load_svm(ert_ctx *c, const char *path)
 }
 
 int ert_svm_nr_class(ert_ctx *c) { return c->svm.loaded ? c->svm.nr_class : -1; }
+int ert_set_svm_tensor_cores(ert_ctx *c, int on) { c->svm.use_tc = on != 0; return 0; }
 int ert_svm_dims(ert_ctx *c) { return c->svm.loaded ? c->svm.dims : -1; }
 
 // ---- the batched hot path ----------------------------------------------------------------------
@@ -794,7 +832,9 @@ static int svm_common(ert_ctx *c, const double *xf, const uint8_t *xu, int n, do
 	if (c->s0.ensure(xb) || c->s1.ensure(sizeof(double) * (size_t)n * m.l) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, xf ? (const void *)xf : (const void *)xu, xb, cudaMemcpyHostToDevice, st));
 	double *d_label = (double *)c->s3.p, *d_prob = d_label + n;
-	if (launch_svm_predict(m.dev(), xf ? (const double *)c->s0.p : nullptr, xu ? (const uint8_t *)c->s0.p : nullptr, n, (double *)c->s1.p, d_label, d_prob, st)) return -1;
+	uint8_t *tcws = nullptr;
+	if (xu && m.use_tc && m.d_svj) { if (c->s4.ensure(svm_tc_ws_bytes(n))) return -1; tcws = (uint8_t *)c->s4.p; }
+	if (launch_svm_predict(m.dev(), xf ? (const double *)c->s0.p : nullptr, xu ? (const uint8_t *)c->s0.p : nullptr, n, (double *)c->s1.p, d_label, d_prob, st, tcws)) return -1;
 	if (label) ERT_CUDA_CHECK(cudaMemcpyAsync(label, d_label, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
 	if (prob) ERT_CUDA_CHECK(cudaMemcpyAsync(prob, d_prob, sizeof(double) * (size_t)n * m.nr_class, cudaMemcpyDeviceToHost, st));
 	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -838,10 +878,12 @@ int ert_bench_svm_u8(ert_ctx *c, const uint8_t *x, int n, int iters, double *ms_
 	if (c->s0.ensure((size_t)n * m.dims) || c->s1.ensure(sizeof(double) * (size_t)n * m.l) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, x, (size_t)n * m.dims, cudaMemcpyHostToDevice, st));
 	double *d_label = (double *)c->s3.p, *d_prob = d_label + n;
-	if (launch_svm_predict(m.dev(), nullptr, (const uint8_t *)c->s0.p, n, (double *)c->s1.p, d_label, d_prob, st)) return -1;
+	uint8_t *tcws = nullptr;
+	if (m.use_tc && m.d_svj) { if (c->s4.ensure(svm_tc_ws_bytes(n))) return -1; tcws = (uint8_t *)c->s4.p; }
+	if (launch_svm_predict(m.dev(), nullptr, (const uint8_t *)c->s0.p, n, (double *)c->s1.p, d_label, d_prob, st, tcws)) return -1;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[6], st));
 	for (int i = 0; i < iters; i++)
-		if (launch_svm_predict(m.dev(), nullptr, (const uint8_t *)c->s0.p, n, (double *)c->s1.p, d_label, d_prob, st)) return -1;
+		if (launch_svm_predict(m.dev(), nullptr, (const uint8_t *)c->s0.p, n, (double *)c->s1.p, d_label, d_prob, st, tcws)) return -1;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[7], st));
 	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
 	float ms = 0;

@@ -48,6 +48,11 @@ struct SvmDev {
 	const double *coef;      // [nr_class-1][l]
 	const double *rho, *probA, *probB;   // [nr_class*(nr_class-1)/2]
 	const int *label, *nsv, *start;      // [nr_class]
+	// tensor-core tables (u8 features): j = round(255 v) and e = round(S (v - j/255)), padded [2048][1920]; |sv|^2
+	const uint8_t *svj;
+	const int8_t *sve;
+	const double *ss;
+	double inv_s255;        // 1 / (255 * S)
 };
 
 int extract_pitch(int W);
@@ -70,6 +75,9 @@ int launch_cascade_f64(const double *fv, size_t row_stride, int n_rows, const Ca
                        int32_t *label, double *sscore, double *wscore, cudaStream_t st);
 
 int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *kvalue_ws, double *label, double *prob,
-                       cudaStream_t st);
+                       cudaStream_t st, uint8_t *tc_ws = nullptr);
+size_t svm_tc_ws_bytes(int n);
+int svm_tc_kpad();
+int svm_tc_npad();
 
 } // namespace ert

@@ -7,10 +7,9 @@
 //                  "distance GEMM" (64x64 output tile per CTA, 4x4 per thread, operands staged in
 //                  shared memory).  FP64 keeps the parsed support-vector values exact; the integer
 //                  tensor-core formulation (u8 x u8 -> s32) is the planned fast path.
-//   k_svm_prob   : one warp per vector: 2080 pairwise decision values with the reference's
-//                  sequential, non-fused accumulation order, Platt sigmoid, clamp, and the
-//                  Wu-Lin-Weng coupling iteration with the reference's exact operation order
-//                  (so any difference to the CPU comes only from the last bits of K).
+//   k_svm_prob   : one warp per vector: 2080 pairwise decision values (per-pair order of the reference),
+//                  Platt sigmoid, clamp, and the Wu-Lin-Weng coupling iteration with p / Qp in registers,
+//                  shuffle broadcasts and one reciprocal per Gauss-Seidel step (last-bit differences only).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -70,7 +69,170 @@ __global__ void __launch_bounds__(256) k_svm_kvalue(SvmDev m, const XT *__restri
 		}
 }
 
-constexpr int PROB_WARPS = 2;
+// ---------------------------------------------------------------------------------------------
+// Tensor-core formulation of the RBF distance (u8 features only).
+//   x.sv = sum_d (k_d/255) * (j_d/255 + eps_d)  with k_d the u8 feature, j_d = round(255 v_d), eps_d = v_d - j_d/255
+//        = DJ / 255^2 + DE / (255 * S),   DJ = sum k_d j_d  (u8 x u8 -> s32, exact),
+//                                         DE = sum k_d e_d  (u8 x s8 -> s32), e_d = round(S * eps_d), S = 127 / max|eps|
+//   d^2  = |x|^2 + |sv|^2 - 2 x.sv ;  |x|^2 = sum k^2 / 255^2 (exact integer sum), |sv|^2 in FP64 from the parsed values.
+// The OCR.model values are 6-significant-digit decimals of j/255 (|eps| <= 4.9e-7), so the second GEMM restores
+// them to ~1e-9; both are dense [N x 1800] x [1800 x 1910] GEMMs -> tcgen05.mma kind::i8, accumulators in TMEM.
+//
+// One CTA per 128 (vectors) x 256 (support vectors) output tile; K is consumed in 128-byte chunks: all threads
+// stage A (128 rows), B_J and B_E (256 rows each) into shared memory in the canonical no-swizzle K-major
+// core-matrix layout (8 rows x 16 B), one thread issues 4 + 4 MMAs (K = 32 each), tcgen05.commit signals an
+// mbarrier, everybody waits, next chunk.  Epilogue: tcgen05.ld 32 lanes x 16 columns per warp -> exp -> FP64 K.
+// (Single-stage on purpose in round 1: the whole GEMM is ~2 % of the SVM time once it runs on tensor cores.)
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_M = 128, TC_N = 256, TC_KC = 128;        // tile and K-chunk (bytes)
+constexpr int TC_KPAD = 1920;                             // 1800 padded to a multiple of TC_KC
+constexpr int TC_NPAD = 2048;                             // 1910 support vectors padded to 8 tiles of 256
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t tc_make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+	// UMMA shared-memory matrix descriptor, SWIZZLE_NONE, K-major: ((8,n),2):((1,SBO),LBO) in 16-byte units
+	uint64_t d = 0;
+	d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+	d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+	d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+	d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+	return d;
+}
+
+__global__ void __launch_bounds__(128) k_svm_prep_x(const uint8_t *__restrict__ x, int n, int dims, uint8_t *__restrict__ xp, uint32_t *__restrict__ xx)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int row = blockIdx.x * 4 + warp;
+	if (row >= n) return;
+	const uint8_t *src = x + (size_t)row * dims;
+	uint8_t *dst = xp + (size_t)row * TC_KPAD;
+	uint32_t acc = 0;
+	for (int d = lane; d < TC_KPAD; d += 32) {
+		const uint32_t v = (d < dims) ? src[d] : 0u;
+		dst[d] = (uint8_t)v;
+		acc += v * v;
+	}
+	acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+	if (lane == 0) xx[row] = acc;
+}
+
+__global__ void __launch_bounds__(128, 1) k_svm_kvalue_tc(const uint8_t *__restrict__ xp, const uint32_t *__restrict__ xx, int n,
+                                                         const uint8_t *__restrict__ svj, const int8_t *__restrict__ sve,
+                                                         const double *__restrict__ ss, int l, double gamma, double inv_s255,
+                                                         double *__restrict__ kv)
+{
+	extern __shared__ __align__(1024) uint8_t tsm[];
+	uint8_t *sA = tsm;                         // 128 rows x 128 B  = 16 KB
+	uint8_t *sBJ = tsm + 16384;                // 256 rows x 128 B  = 32 KB
+	uint8_t *sBE = tsm + 16384 + 32768;        // 32 KB
+	__shared__ __align__(8) uint64_t bar;
+	__shared__ uint32_t s_tmem;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int n0 = blockIdx.y * TC_M, s0 = blockIdx.x * TC_N;
+
+	if (warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&s_tmem)), "r"(512u) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	if (tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&bar)), "r"(1u) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem = s_tmem;
+
+	// instruction descriptors: D = S32, A = u8 (K-major), B = u8 / s8 (K-major), M = 128, N = 256
+	const uint32_t idesc_base = (2u << 4) | (0u << 7) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+	const uint32_t idesc_j = idesc_base | (0u << 10);
+	const uint32_t idesc_e = idesc_base | (1u << 10);
+	const uint32_t aA = tc_smem_u32(sA), aBJ = tc_smem_u32(sBJ), aBE = tc_smem_u32(sBE);
+
+	uint32_t phase = 0;
+	for (int kc = 0; kc < TC_KPAD / TC_KC; ++kc) {
+		// stage the chunk: granule (r, g) of 16 bytes -> core matrix (g, r/8), row r%8
+		for (int q = tid; q < TC_M * 8; q += 128) {
+			const int r = q >> 3, g = q & 7;
+			uint4 v = make_uint4(0, 0, 0, 0);
+			if (n0 + r < n) v = *reinterpret_cast<const uint4 *>(xp + (size_t)(n0 + r) * TC_KPAD + kc * TC_KC + g * 16);
+			*reinterpret_cast<uint4 *>(sA + ((g * (TC_M / 8) + (r >> 3)) * 8 + (r & 7)) * 16) = v;
+		}
+		for (int q = tid; q < TC_N * 8; q += 128) {
+			const int r = q >> 3, g = q & 7;
+			const size_t off = (size_t)(s0 + r) * TC_KPAD + kc * TC_KC + g * 16;
+			const int so = ((g * (TC_N / 8) + (r >> 3)) * 8 + (r & 7)) * 16;
+			*reinterpret_cast<uint4 *>(sBJ + so) = *reinterpret_cast<const uint4 *>(svj + off);
+			*reinterpret_cast<uint4 *>(sBE + so) = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(sve) + off);
+		}
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+		__syncthreads();
+		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+		if (tid == 0) {
+#pragma unroll
+			for (int k4 = 0; k4 < TC_KC / 32; ++k4) {
+				const uint64_t da = tc_make_desc(aA + (uint32_t)(2 * k4) * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
+				const uint64_t dj = tc_make_desc(aBJ + (uint32_t)(2 * k4) * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
+				const uint64_t de = tc_make_desc(aBE + (uint32_t)(2 * k4) * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
+				const uint32_t acc = (kc > 0 || k4 > 0) ? 1u : 0u;
+				asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+				             "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+				             ::"r"(tmem), "l"(da), "l"(dj), "r"(idesc_j), "r"(acc) : "memory");
+				asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+				             "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+				             ::"r"(tmem + 256u), "l"(da), "l"(de), "r"(idesc_e), "r"(acc) : "memory");
+			}
+			asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&bar)) : "memory");
+		}
+		// wait until the MMAs of this chunk have consumed shared memory
+		{
+			uint32_t ok;
+			int spins = 0;
+			do {
+				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+				             : "=r"(ok) : "r"(tc_smem_u32(&bar)), "r"(phase) : "memory");
+			} while (!ok && ++spins < (1 << 22));   // bounded: a lost commit must not hang the GPU
+		}
+		phase ^= 1u;
+	}
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+	// epilogue: warp w owns TMEM lanes 32w..32w+31 = tile rows; 16 columns per tcgen05.ld
+	const int row = n0 + warp * 32 + lane;
+	const double xxr = (row < n) ? (double)xx[row] / 65025.0 : 0.0;
+	const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+	for (int c0 = 0; c0 < TC_N; c0 += 16) {
+		uint32_t rj[16], re[16];
+		asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		             : "=r"(rj[0]), "=r"(rj[1]), "=r"(rj[2]), "=r"(rj[3]), "=r"(rj[4]), "=r"(rj[5]), "=r"(rj[6]), "=r"(rj[7]),
+		               "=r"(rj[8]), "=r"(rj[9]), "=r"(rj[10]), "=r"(rj[11]), "=r"(rj[12]), "=r"(rj[13]), "=r"(rj[14]), "=r"(rj[15])
+		             : "r"(lane_base + (uint32_t)c0) : "memory");
+		asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		             : "=r"(re[0]), "=r"(re[1]), "=r"(re[2]), "=r"(re[3]), "=r"(re[4]), "=r"(re[5]), "=r"(re[6]), "=r"(re[7]),
+		               "=r"(re[8]), "=r"(re[9]), "=r"(re[10]), "=r"(re[11]), "=r"(re[12]), "=r"(re[13]), "=r"(re[14]), "=r"(re[15])
+		             : "r"(lane_base + 256u + (uint32_t)c0) : "memory");
+		asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+		if (row < n) {
+#pragma unroll
+			for (int j = 0; j < 16; ++j) {
+				const int s = s0 + c0 + j;
+				if (s < l) {
+					const double dot = (double)(int32_t)rj[j] / 65025.0 + (double)(int32_t)re[j] * inv_s255;
+					const double d2 = xxr + ss[s] - 2.0 * dot;
+					kv[(size_t)row * l + s] = exp(-gamma * d2);
+				}
+			}
+		}
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+constexpr int PROB_WARPS = 4;
 constexpr int MAXK = 96;   // classes supported by the 3-slots-per-lane layout
 
 __device__ __forceinline__ double sigmoid_predict_dev(double dec, double A, double B)
@@ -86,95 +248,140 @@ __global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const do
 	extern __shared__ __align__(16) double dsm[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int k = m.nr_class;
-	double *r = dsm + (size_t)warp * ((size_t)k * k + 3 * MAXK);
-	double *p = r + (size_t)k * k;
-	double *Qp = p + MAXK;
-	double *Qtt = Qp + MAXK;
+	const int tri = k * (k + 1) / 2;                          // upper triangle incl. diagonal: idx(a<=b) = a*k - a*(a-1)/2 + b - a
+	double *Q = dsm + (size_t)warp * ((size_t)tri + MAXK);    // first r[i][j] (i<j; r[j][i] = 1 - r[i][j]), then Q in place
+	double *ps = Q + tri;                                     // p, shared copy for the matrix-vector product
+#define QIDX(a, b) ((a) * k - (a) * ((a) - 1) / 2 + (b) - (a))
 	const int v = blockIdx.x * PROB_WARPS + warp;
 	if (v >= n) return;
 	const double *kvv = kv + (size_t)v * m.l;
 
-	// pairwise decision values -> pairwise probabilities
+	// pairwise decision values (svm_predict_values, src/svm.cpp:2527-2551, same summation order per pair)
+	// -> sigmoid_predict -> clamp [1e-7, 1-1e-7]
 	for (int i = 0; i < k; i++) {
-		if (lane == 0) r[i * k + i] = 0.0;
 		for (int j = i + 1 + lane; j < k; j += 32) {
 			const int pidx = i * k - i * (i + 1) / 2 + (j - i - 1);
 			const double *c1 = m.coef + (size_t)(j - 1) * m.l, *c2 = m.coef + (size_t)i * m.l;
 			const int si = m.start[i], sj = m.start[j], ci = m.nsv[i], cj = m.nsv[j];
 			double sum = 0.0;
-			for (int q = 0; q < ci; q++) sum = __dadd_rn(sum, __dmul_rn(c1[si + q], kvv[si + q]));
-			for (int q = 0; q < cj; q++) sum = __dadd_rn(sum, __dmul_rn(c2[sj + q], kvv[sj + q]));
-			sum = __dadd_rn(sum, -m.rho[pidx]);
+			for (int q = 0; q < ci; q++) sum = fma(c1[si + q], kvv[si + q], sum);
+			for (int q = 0; q < cj; q++) sum = fma(c2[sj + q], kvv[sj + q], sum);
+			sum -= m.rho[pidx];
 			double pr = sigmoid_predict_dev(sum, m.probA[pidx], m.probB[pidx]);
 			const double lo = 1e-7;
 			pr = fmin(fmax(pr, lo), 1.0 - lo);
-			r[i * k + j] = pr;
-			r[j * k + i] = 1.0 - pr;
+			Q[QIDX(i, j)] = pr;
 		}
 	}
 	__syncwarp();
 
-	// multiclass_probability: Q[t][t] = sum_{j != t} r[j][t]^2 ; Q[t][j] = -r[j][t] * r[t][j]
-	for (int t = lane; t < k; t += 32) {
+	// multiclass_probability (src/svm.cpp:1829-1890): Q[t][t] = sum_{j != t} r[j][t]^2, Q[t][j] = -r[j][t] r[t][j].
+	// p and Qp live in registers (3 slots per lane: t = lane, lane+32, lane+64); the Gauss-Seidel sweep broadcasts
+	// Qp[t] by shuffle, so the inner loop has no shared-memory writes and no barriers; 1/(1+diff) is computed once
+	// per step instead of dividing every element (results differ from libsvm's in the last bits only).
+	double qtt[3], pr_[3], qp[3];
+#pragma unroll
+	for (int sl = 0; sl < 3; sl++) {
+		const int t = lane + 32 * sl;
 		double q = 0.0;
-		for (int j = 0; j < k; j++) if (j != t) q = __dadd_rn(q, __dmul_rn(r[j * k + t], r[j * k + t]));
-		Qtt[t] = q;
-		p[t] = 1.0 / k;
+		if (t < k) for (int j = 0; j < k; j++) if (j != t) { const double rjt = (j < t) ? Q[QIDX(j, t)] : 1.0 - Q[QIDX(t, j)]; q = fma(rjt, rjt, q); }
+		qtt[sl] = q; pr_[sl] = (t < k) ? 1.0 / k : 0.0; qp[sl] = 0.0;
 	}
 	__syncwarp();
+	for (int i = 0; i < k; i++)
+		for (int j = i + 1 + lane; j < k; j += 32) {
+			const double sij = Q[QIDX(i, j)];
+			Q[QIDX(i, j)] = -((1.0 - sij) * sij);
+		}
+#pragma unroll
+	for (int sl = 0; sl < 3; sl++) { const int t = lane + 32 * sl; if (t < k) { Q[QIDX(t, t)] = qtt[sl]; ps[t] = pr_[sl]; } }
+	__syncwarp();
+
 	const int max_iter = max(100, k);
 	const double eps = 0.005 / k;
 	for (int iter = 0; iter < max_iter; iter++) {
-		for (int t = lane; t < k; t += 32) {
-			double s = 0.0;
-			for (int j = 0; j < k; j++) {
-				const double q = (j == t) ? Qtt[t] : -__dmul_rn(r[j * k + t], r[t * k + j]);
-				s = __dadd_rn(s, __dmul_rn(q, p[j]));
+		double part = 0.0, err = 0.0;
+#pragma unroll
+		for (int sl = 0; sl < 3; sl++) {
+			const int t = lane + 32 * sl;
+			double sacc = 0.0;
+			if (t < k) {
+				for (int j = 0; j < t; j++) sacc = fma(Q[QIDX(j, t)], ps[j], sacc);
+				const double *row = Q + QIDX(t, t) - t;   // row[j] = Q[t][j] for j >= t
+				for (int j = t; j < k; j++) sacc = fma(row[j], ps[j], sacc);
 			}
-			Qp[t] = s;
+			qp[sl] = sacc;
+			part = fma(pr_[sl], sacc, part);
+		}
+		double pQp = part;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) pQp += __shfl_xor_sync(0xFFFFFFFFu, pQp, o);
+#pragma unroll
+		for (int sl = 0; sl < 3; sl++) if (lane + 32 * sl < k) err = fmax(err, fabs(qp[sl] - pQp));
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) err = fmax(err, __shfl_xor_sync(0xFFFFFFFFu, err, o));
+		if (err < eps) break;
+		for (int t = 0; t < k; t++) {
+			const int sl_t = t >> 5, owner = t & 31;
+			const double qpt = __shfl_sync(0xFFFFFFFFu, sl_t == 0 ? qp[0] : (sl_t == 1 ? qp[1] : qp[2]), owner);
+			const double qt = __shfl_sync(0xFFFFFFFFu, sl_t == 0 ? qtt[0] : (sl_t == 1 ? qtt[1] : qtt[2]), owner);
+			const double diff = (pQp - qpt) / qt;
+			const double inv = 1.0 / (1.0 + diff);
+			pQp = (pQp + diff * fma(diff, qt, 2.0 * qpt)) * inv * inv;
+#pragma unroll
+			for (int sl = 0; sl < 3; sl++) {
+				const int j = lane + 32 * sl;
+				if (j < k) {
+					const double qtj = (j < t) ? Q[QIDX(j, t)] : Q[QIDX(t, j)];
+					qp[sl] = fma(diff, qtj, qp[sl]) * inv;
+					pr_[sl] = ((j == t) ? pr_[sl] + diff : pr_[sl]) * inv;
+				}
+			}
 		}
 		__syncwarp();
-		double pQp = 0.0;
-		for (int t = 0; t < k; t++) pQp = __dadd_rn(pQp, __dmul_rn(p[t], Qp[t]));   // every lane, same order
-		double max_err = 0.0;
-		for (int t = 0; t < k; t++) max_err = fmax(max_err, fabs(__dadd_rn(Qp[t], -pQp)));
-		if (max_err < eps) break;
-		for (int t = 0; t < k; t++) {
-			const double qtt = Qtt[t], qpt = Qp[t];
-			const double diff = __ddiv_rn(__dadd_rn(-qpt, pQp), qtt);
-			const double one_d = __dadd_rn(1.0, diff);
-			pQp = __ddiv_rn(__ddiv_rn(__dadd_rn(pQp, __dmul_rn(diff, __dadd_rn(__dmul_rn(diff, qtt), __dmul_rn(2.0, qpt)))), one_d), one_d);
-			__syncwarp();
-			for (int j = lane; j < k; j += 32) {
-				const double q = (j == t) ? qtt : -__dmul_rn(r[j * k + t], r[t * k + j]);
-				const double pj = (j == t) ? __dadd_rn(p[j], diff) : p[j];
-				Qp[j] = __ddiv_rn(__dadd_rn(Qp[j], __dmul_rn(diff, q)), one_d);
-				p[j] = __ddiv_rn(pj, one_d);
-			}
-			__syncwarp();
-		}
+#pragma unroll
+		for (int sl = 0; sl < 3; sl++) { const int t = lane + 32 * sl; if (t < k) ps[t] = pr_[sl]; }
+		__syncwarp();
 	}
 	__syncwarp();
-	int best = 0;
-	for (int t = 1; t < k; t++) if (p[t] > p[best]) best = t;
-	for (int t = lane; t < k; t += 32) prob_out[(size_t)v * k + t] = p[t];
-	if (lane == 0) label_out[v] = (double)m.label[best];
+#pragma unroll
+	for (int sl = 0; sl < 3; sl++) { const int t = lane + 32 * sl; if (t < k) { ps[t] = pr_[sl]; prob_out[(size_t)v * k + t] = pr_[sl]; } }
+	__syncwarp();
+	if (lane == 0) {
+		int best = 0;
+		for (int t = 1; t < k; t++) if (ps[t] > ps[best]) best = t;
+		label_out[v] = (double)m.label[best];
+	}
+#undef QIDX
 }
 
 int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *kvalue_ws, double *label, double *prob,
-                       cudaStream_t st)
+                       cudaStream_t st, uint8_t *tc_ws)
 {
 	if (n <= 0) return 0;
 	if (m.nr_class > MAXK) { set_error("svm: nr_class %d > %d unsupported", m.nr_class, MAXK); return -1; }
 	dim3 grid((m.l + KT - 1) / KT, (n + KT - 1) / KT);
-	if (x_u8) k_svm_kvalue<uint8_t><<<grid, 256, 0, st>>>(m, x_u8, n, kvalue_ws);
+	if (x_u8 && m.svj && tc_ws && m.dims <= TC_KPAD && m.l <= TC_NPAD) {
+		uint8_t *xp = tc_ws;
+		uint32_t *xx = reinterpret_cast<uint32_t *>(tc_ws + (((size_t)n * TC_KPAD + 255) / 256) * 256);
+		k_svm_prep_x<<<(n + 3) / 4, 128, 0, st>>>(x_u8, n, m.dims, xp, xx);
+		ERT_CUDA_CHECK(cudaGetLastError());
+		const size_t smem = 16384 + 2 * 32768;
+		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_kvalue_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		dim3 g2(TC_NPAD / TC_N, (n + TC_M - 1) / TC_M);
+		k_svm_kvalue_tc<<<g2, 128, smem, st>>>(xp, xx, n, m.svj, m.sve, m.ss, m.l, m.gamma, m.inv_s255, kvalue_ws);
+	} else if (x_u8) k_svm_kvalue<uint8_t><<<grid, 256, 0, st>>>(m, x_u8, n, kvalue_ws);
 	else k_svm_kvalue<double><<<grid, 256, 0, st>>>(m, x_f64, n, kvalue_ws);
 	ERT_CUDA_CHECK(cudaGetLastError());
-	const size_t smem = (size_t)PROB_WARPS * ((size_t)m.nr_class * m.nr_class + 3 * MAXK) * sizeof(double);
+	const size_t smem = (size_t)PROB_WARPS * ((size_t)m.nr_class * (m.nr_class + 1) / 2 + MAXK) * sizeof(double);
 		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	k_svm_prob<<<(n + PROB_WARPS - 1) / PROB_WARPS, PROB_WARPS * 32, smem, st>>>(m, kvalue_ws, n, label, prob);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
+
+size_t svm_tc_ws_bytes(int n) { return (((size_t)n * TC_KPAD + 255) / 256) * 256 + (size_t)n * 4 + 256; }
+int svm_tc_kpad() { return TC_KPAD; }
+int svm_tc_npad() { return TC_NPAD; }
 
 } // namespace ert

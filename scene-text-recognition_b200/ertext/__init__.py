@@ -37,7 +37,7 @@ class ErtResult(C.Structure):
 EXPORTS = [
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
     "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
-    "ert_load_svm", "ert_svm_nr_class", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
+    "ert_load_svm", "ert_svm_nr_class", "ert_set_svm_tensor_cores", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
     "ert_fetch_result", "ert_planes_detect", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
     "ert_cascade_predict_batch", "ert_cascade_classify_u8", "ert_svm_predict_probability_batch",
     "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
@@ -68,6 +68,7 @@ def load_library():
     L.ert_load_cascade.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.ert_load_svm.argtypes = [C.c_void_p, C.c_char_p]
     L.ert_svm_nr_class.argtypes = [C.c_void_p]
+    L.ert_set_svm_tensor_cores.argtypes = [C.c_void_p, C.c_int]
     L.ert_svm_dims.argtypes = [C.c_void_p]
     RP = C.POINTER(C.POINTER(ErtResult))
     L.ert_detect_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, RP]
@@ -311,6 +312,9 @@ class ErText:
             label = np.zeros(n); prob = np.zeros((n, k))
             self._check(self.L.ert_svm_predict_probability_batch(self.ctx, _ptr(x, _f64p), n, _ptr(label, _f64p), _ptr(prob, _f64p)))
         return label, prob
+
+    def set_svm_tensor_cores(self, on):
+        self._check(self.L.ert_set_svm_tensor_cores(self.ctx, int(on)))
 
     def svm_dims(self):
         return self.L.ert_svm_dims(self.ctx)

@@ -89,8 +89,18 @@ def test_svm_batch_vs_reference_golden(ert, golden_svm):
     assert (label == golden_svm["label"]).all()
     rel = np.abs(prob - golden_svm["prob"]) / np.maximum(np.abs(golden_svm["prob"]), 1e-300)
     assert rel.max() < 1e-4, rel.max()
+    # f64 entry point (FP64 CUDA-core distance kernel, the exact path) agrees with the reference to the last bits
     label2, prob2 = ert.svm_predict_probability(golden_svm["x_u8"].astype(np.float64) / 255.0)
-    assert (label2 == label).all() and np.abs(prob2 - prob).max() < 1e-12
+    rel2 = np.abs(prob2 - golden_svm["prob"]) / np.maximum(np.abs(golden_svm["prob"]), 1e-300)
+    assert (label2 == golden_svm["label"]).all() and rel2.max() < 1e-10, rel2.max()
+    # u8 entry point: tensor-core (tcgen05 kind::i8, two exact-integer GEMMs) vs FP64 distance kernel
+    ert.set_svm_tensor_cores(0)
+    try:
+        label3, prob3 = ert.svm_predict_probability(golden_svm["x_u8"])
+    finally:
+        ert.set_svm_tensor_cores(1)
+    assert (label3 == label).all()
+    assert (np.abs(prob3 - prob) / np.maximum(prob3, 1e-300)).max() < 1e-6
 
 
 def test_device_resident_entry_and_async_pair(ert, golden_frames):
