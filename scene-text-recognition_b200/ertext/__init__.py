@@ -121,8 +121,9 @@ class PlaneResult:
 
 
 class BatchResult:
-    def __init__(self, planes, status, stage_ms, width, height):
+    def __init__(self, planes, status, stage_ms, width, height, flat=None):
         self.planes, self.status, self.stage_ms, self.width, self.height = planes, status, stage_ms, width, height
+        self.flat = flat   # (node_offset, nodes, pool_offset, pool_node, pool_label): the contiguous arrays of the C result
 
 
 class ErText:
@@ -213,7 +214,7 @@ class ErText:
             a, b = int(poff[p]), int(poff[p + 1])
             planes.append(PlaneResult(nodes[noff[p]:noff[p + 1]], pool[a:b], label[a:b], ss[a:b], ws[a:b],
                                       hist[a:b] if hist is not None else None))
-        return BatchResult(planes, int(r.status), list(r.stage_ms), r.width, r.height)
+        return BatchResult(planes, int(r.status), list(r.stage_ms), r.width, r.height, (noff, nodes, poff, pool, label))
 
     # ---- the batched hot path ------------------------------------------------------------------
     def detect_classify(self, bgr, upto=STAGE_CLASSIFY):

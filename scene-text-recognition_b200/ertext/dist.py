@@ -16,17 +16,18 @@ def shard_frames(n_frames, rank, world):
 
 
 def pack_records(batch_result, frame_ids):
-    """BatchResult (6 planes per local frame) -> int32 [n, REC_COLS] of pooled regions with a label."""
-    rows = []
-    for p, pr in enumerate(batch_result.planes):
-        f, ch = frame_ids[p // 6], p % 6
-        for k, ni in enumerate(pr.pool):
-            lab = int(pr.label[k])
-            if lab == 0:
-                continue
-            n = pr.nodes[ni]
-            rows.append((f, ch, n[0], n[1], n[2], n[3], n[4], n[5], lab))
-    return np.array(rows, np.int32).reshape(-1, REC_COLS)
+    """BatchResult (6 planes per local frame) -> int32 [n, REC_COLS] of pooled regions with a label (vectorised)."""
+    noff, nodes, poff, pool, label = batch_result.flat
+    if len(pool) == 0:
+        return np.zeros((0, REC_COLS), np.int32)
+    plane = np.repeat(np.arange(len(poff) - 1), np.diff(poff))
+    keep = label > 0
+    plane, pool, label = plane[keep], pool[keep], label[keep]
+    rows = nodes[noff[plane] + pool]
+    fid = np.asarray(frame_ids, np.int32)[plane // 6]
+    out = np.empty((len(plane), REC_COLS), np.int32)
+    out[:, 0] = fid; out[:, 1] = plane % 6; out[:, 2:8] = rows[:, :6]; out[:, 8] = label
+    return out
 
 
 def gather_records(records, device, max_rows=4096):
