@@ -276,71 +276,75 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		__syncthreads();
 
 		ERT_PHASE(3);
-		// ---- phase C: every pixel points at its level root, every root at its parent's level root;
-		// also (re)initialise the accumulators that aliased the work list ----
-		for (int p0 = warp * 32; p0 < TPX; p0 += NT) {
-			const int p = p0 + lane;
-			const uint32_t L = lvl[p];
-			uint32_t k = (L << 16) | (uint32_t)p;
-			bool act = (L != 255);
-			while (__any_sync(0xFFFFFFFFu, act)) {
-				if (act) {
-					const uint32_t q = par[k & 0xFFFFu];
-					if (q == KEY_NONE || (q >> 16) != (k >> 16)) act = false;
-					else k = q;
-				}
-			}
-			uint32_t pr = KEY_NONE;
-			if (L != 255) {
-				if (k != ((L << 16) | (uint32_t)p)) par[p] = k;
-				else pr = par[p];
-			}
-			// roots: resolve the parent's level root
-			uint32_t k2 = pr;
-			bool act2 = (pr != KEY_NONE);
-			while (__any_sync(0xFFFFFFFFu, act2)) {
-				if (act2) {
-					const uint32_t q = par[k2 & 0xFFFFu];
-					if (q == KEY_NONE || (q >> 16) != (k2 >> 16)) act2 = false;
-					else k2 = q;
-				}
-			}
-			if (pr != KEY_NONE && k2 != pr) par[p] = k2;
-		}
-		__syncthreads();
 	}
 	ERT_PHASE(4);
 	for (int p = tid; p < TPX; p += NT) { cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymn[p] = 0xFFFFFFFFu; ymx[p] = 0; }
 	__syncthreads();
 
-	// ---- phase D: own-level pixel count and bbox per tile-local node, one update per run.
+	// ---- phase D: own-level pixel count and bbox per tile-local node, one update per same-level run; the run's
+	// last pixel looks its level root up with a warp-converged walk (no separate flatten pass over all pixels).
 	// acc word: bits 0..14 pixels, bits 15..29 nodes, bit 31 = node touches a seam (BORDER) ----
 	constexpr uint32_t ACC_NODE = 1u << 15, ACC_MASK = 0x7FFFu, ACC_BORDER = 0x80000000u;
-	for (int seg = warp; seg < SEGS; seg += NWARP) {
-		const int p = seg * 32 + lane;
-		const int y = p / TW, x = p % TW;
-		const uint32_t L = lvl[p];
-		const uint32_t Lr = __shfl_down_sync(0xFFFFFFFFu, L, 1);
-		const bool same = local_union && (lane < 31) && (Lr == L) && (L != 255);
-		const uint32_t bmask = __ballot_sync(0xFFFFFFFFu, !same);
-		const uint32_t pk = par[p];
-		const bool isroot = (L != 255) && (pk == KEY_NONE || (pk >> 16) != L);
-		if (L != 255 && !same) {
-			const uint32_t prev = bmask & ((1u << lane) - 1u);
-			const int start = prev ? (32 - __clz(prev)) : 0;
-			const int len = lane - start + 1;
-			const uint32_t r = isroot ? (uint32_t)p : (pk & 0xFFFFu);
-			atomicAdd(&cnt[r], (uint32_t)len);
-			atomicMin(&xmn[r], (uint32_t)(x - (lane - start)));
-			atomicMax(&xmx[r], (uint32_t)x);
-			atomicMin(&ymn[r], (uint32_t)y);
+	{
+		volatile uint32_t *vpar = par;
+		for (int seg = warp; seg < SEGS; seg += NWARP) {
+			const int p = seg * 32 + lane;
+			const int y = p / TW, x = p % TW;
+			const uint32_t L = lvl[p];
+			const uint32_t Lr = __shfl_down_sync(0xFFFFFFFFu, L, 1);
+			const bool same = local_union && (lane < 31) && (Lr == L) && (L != 255);
+			const uint32_t bmask = __ballot_sync(0xFFFFFFFFu, !same);
+			const bool runend = (L != 255) && !same;
+			uint32_t k = (L << 16) | (uint32_t)p;
+			bool act = runend;
+			bool isroot = false;
+			while (__any_sync(0xFFFFFFFFu, act)) {
+				if (act) {
+					const uint32_t q = vpar[k & 0xFFFFu];
+					if (q == KEY_NONE || (q >> 16) != L) { act = false; isroot = ((k & 0xFFFFu) == (uint32_t)p); }
+					else k = q;
+				}
+			}
+			if (runend) {
+				const uint32_t prev = bmask & ((1u << lane) - 1u);
+				const int start = prev ? (32 - __clz(prev)) : 0;
+				const int len = lane - start + 1;
+				const uint32_t r = k & 0xFFFFu;
+				atomicAdd(&cnt[r], (uint32_t)len + (isroot ? ACC_NODE : 0u));
+				atomicMin(&xmn[r], (uint32_t)(x - (lane - start)));
+				atomicMax(&xmx[r], (uint32_t)x);
+				atomicMin(&ymn[r], (uint32_t)y);
+				if (isroot) ymx[p] = (uint32_t)y;   // the level root is the node's last own-level pixel
+			}
+			const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, isroot);
+			uint32_t wb = 0;
+			if (lane == 0 && rmask) wb = atomicAdd(&s_nroots, (uint32_t)__popc(rmask));
+			wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
+			if (isroot) rootlist[wb + __popc(rmask & ((1u << lane) - 1u))] = (uint16_t)p;
 		}
-		if (isroot) { atomicAdd(&cnt[p], ACC_NODE); ymx[p] = (uint32_t)y; }   // the level root is the node's last own-level pixel
-		const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, isroot);
-		uint32_t wb = 0;
-		if (lane == 0 && rmask) wb = atomicAdd(&s_nroots, (uint32_t)__popc(rmask));
-		wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
-		if (isroot) rootlist[wb + __popc(rmask & ((1u << lane) - 1u))] = (uint16_t)p;
+	}
+	__syncthreads();
+	ERT_PHASE(9);
+
+	// ---- phase C: every level root points at its parent's LEVEL ROOT (roots only: a few % of the pixels) ----
+	if (local_union) {
+		volatile uint32_t *vpar = par;
+		const uint32_t nr = s_nroots;
+		for (uint32_t i0 = warp * 32; i0 < nr; i0 += NT) {
+			const uint32_t i = i0 + lane;
+			uint32_t p = 0, k = KEY_NONE;
+			if (i < nr) { p = rootlist[i]; k = vpar[p]; }
+			const uint32_t k0 = k;
+			bool act = (k != KEY_NONE);
+			while (__any_sync(0xFFFFFFFFu, act)) {
+				if (act) {
+					const uint32_t q = vpar[k & 0xFFFFu];
+					if (q == KEY_NONE || (q >> 16) != (k >> 16)) act = false;
+					else k = q;
+				}
+			}
+			if (k != k0) par[p] = k;   // readers that still see k0 walk the same chain to the same root
+		}
 	}
 	__syncthreads();
 
@@ -366,8 +370,13 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 			const int p = y * TW + x;
 			const uint32_t L = lvl[p];
 			if (L == 255) continue;
-			const uint32_t pk = par[p];
-			uint32_t r = (pk == KEY_NONE || (pk >> 16) != L) ? (uint32_t)p : (pk & 0xFFFFu);
+			uint32_t kk = (L << 16) | (uint32_t)p;
+			for (int guard = 0; guard < 65536; ++guard) {   // to the level root
+				const uint32_t q = par[kk & 0xFFFFu];
+				if (q == KEY_NONE || (q >> 16) != L) break;
+				kk = q;
+			}
+			uint32_t r = kk & 0xFFFFu;
 			for (int guard = 0; guard < 64; ++guard) {
 				const uint32_t old = atomicOr(&cnt[r], ACC_BORDER);
 				if (old & ACC_BORDER) break;
@@ -461,9 +470,14 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 			const int p = y * TW + x;
 			const uint32_t L = lvl[p];
 			if (L == 255) continue;
-			const uint32_t pk = par[p];
-			if (pk == KEY_NONE || (pk >> 16) != L) continue;   // roots were written above
-			const uint32_t q = pk & 0xFFFFu;
+			uint32_t kk = (L << 16) | (uint32_t)p;
+			for (int guard = 0; guard < 65536; ++guard) {
+				const uint32_t q2 = par[kk & 0xFFFFu];
+				if (q2 == KEY_NONE || (q2 >> 16) != L) break;
+				kk = q2;
+			}
+			const uint32_t q = kk & 0xFFFFu;
+			if (q == (uint32_t)p) continue;   // level roots were written above
 			parP[(uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x)] =
 				make_key(L, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
 		}

@@ -26,6 +26,6 @@ for cfg in only:
         ref = sig
     same = sig == ref
     pc = e.phase_cycles(True); tot = float(sum(pc)) or 1.0
-    print("   phases %: setup %.1f A %.1f B1 %.1f B2 %.1f init %.1f D %.1f C %.1f D2 %.1f D3 %.1f E %.1f" % tuple(100 * v / tot for v in pc[:9] + [0]) if False else "   phases %%: " + " ".join("%s %.1f" % (n, 100 * v / tot) for n, v in zip(["setup+TMA", "A", "B1", "B2", "C", "init+D", "D2", "D3", "E"], pc[:9])))
+    print("   phases %: setup %.1f A %.1f B1 %.1f B2 %.1f init %.1f D %.1f C %.1f D2 %.1f D3 %.1f E %.1f" % tuple(100 * v / tot for v in pc[:9] + [0]) if False else "   phases %%: " + " ".join("%s %.1f" % (n, 100 * v / tot) for n, v in zip(["setup+TMA", "A", "B1", "B2", "-", "C(roots)", "D2", "D3", "E", "init+D"], pc[:10])))
     print("cfg %d %-11s tile %.3f ms  extract %.3f  nms %.3f  classify %.3f  total %.3f  status %d  same_as_first %s" % (
         cfg, names[cfg], best[6], best[0], best[1], best[2], best[5], r.status, same), flush=True)
