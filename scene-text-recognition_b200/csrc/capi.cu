@@ -295,7 +295,7 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 		ClassifyParams CP; CP.pitch = c->pitch; CP.pool_cap = c->pool_cap; CP.node_cap = c->kept_cap;
 		if (launch_lbp_hist(CP, n_planes, c->d_planes, c->d_out_nodes, c->d_out_pool, c->d_out_counts, c->d_aran_tbl, c->d_hist, st)) return -1;
 		if (launch_cascade_u8(c->d_hist, 1024, n_planes * c->pool_cap, c->d_out_counts, c->pool_cap, c->casc[0].dev(), c->casc[1].dev(),
-		                      c->d_label, c->d_ss, c->d_ws, st)) return -1;
+		                      (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), c->d_label, c->d_ss, c->d_ws, st)) return -1;
 		c->launches += 2;
 	}
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
@@ -753,7 +753,7 @@ static int classify_common(ert_ctx *c, const uint8_t *plane, int W, int H, int s
 	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
 	double *d_ws = d_ss + n;
 	if (need_cascade) {
-		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, st)) return -1;
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), d_label, d_ss, d_ws, st)) return -1;
 	}
 	ERT_CUDA_CHECK(cudaStreamSynchronize(st));   // staging vectors hn/hp may go out of scope now
 	if (label) ERT_CUDA_CHECK(cudaMemcpy(label, d_label, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
@@ -812,7 +812,7 @@ int ert_cascade_classify_u8(ert_ctx *c, const uint8_t *hist, int n, int32_t *lab
 	int32_t *d_label = (int32_t *)c->s3.p;
 	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
 	double *d_ws = d_ss + n;
-	if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, st)) return -1;
+	if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), d_label, d_ss, d_ws, st)) return -1;
 	if (label) ERT_CUDA_CHECK(cudaMemcpyAsync(label, d_label, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
 	if (ss) ERT_CUDA_CHECK(cudaMemcpyAsync(ss, d_ss, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
 	if (ws) ERT_CUDA_CHECK(cudaMemcpyAsync(ws, d_ws, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -856,10 +856,10 @@ int ert_bench_cascade_u8(ert_ctx *c, const uint8_t *hist, int n, int iters, doub
 	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
 	double *d_ws = d_ss + n;
 	for (int w = 0; w < 3; w++)
-		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, st)) return -1;
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), d_label, d_ss, d_ws, st)) return -1;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[6], st));
 	for (int i = 0; i < iters; i++)
-		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, st)) return -1;
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), d_label, d_ss, d_ws, st)) return -1;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[7], st));
 	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
 	float ms = 0;

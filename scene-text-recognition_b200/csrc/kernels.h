@@ -70,7 +70,7 @@ int launch_nms(const NmsParams &P, int n_planes, const KeptRec *kept, const uint
 int launch_lbp_hist(const ClassifyParams &P, int n_planes, const PlaneSrc *planes, const OutNode *nodes, const int32_t *pool,
                     const int32_t *counts, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st);
 int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const int32_t *counts, int pool_cap, const CascadeDev &strong,
-                      const CascadeDev &weak, int32_t *label, double *sscore, double *wscore, cudaStream_t st);
+                      const CascadeDev &weak, int n_strong, int n_weak, int32_t *label, double *sscore, double *wscore, cudaStream_t st);
 int launch_cascade_f64(const double *fv, size_t row_stride, int n_rows, const CascadeDev &strong, const CascadeDev &weak,
                        int32_t *label, double *sscore, double *wscore, cudaStream_t st);
 
