@@ -65,6 +65,15 @@ __device__ __forceinline__ int bb_inter(const uint16_t *a, const uint16_t *b)
 	return (x1 - x0 + 1) * (y1 - y0 + 1);
 }
 
+// (double)inter / (double)parea > coef, exactly as the reference evaluates it, but without the FP64 divide unless the
+// quotient is within 1e-9 (relative) of the threshold: there the rounding of the division decides and it is performed.
+__device__ __forceinline__ bool overlap_exceeds(int inter, int parea, double coef)
+{
+	const double a = (double)inter, t = coef * (double)parea;
+	if (fabs(a - t) > 1e-9 * t) return a > t;
+	return a / (double)parea > coef;
+}
+
 // in:  either the extract stage's kept list (kept != nullptr; parents given as root-pixel indices,
 //      resolved through attr[].arr) or caller nodes (in_nodes: DFS pre-order with explicit order).
 template <int NT>
@@ -205,9 +214,8 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 	__syncthreads();
 
 	// ---- (4) the reference's sequential walk (src/ER.cpp:426-502) ----
+	__shared__ int stack[72], chain[72];
 	if (tid == 0) {
-		int stack[72];
-		int chain[72];
 		int sp = 0, pre = 0, npool = 0;
 		const int T = P.stability_t;
 		int cur = 0;   // the root sorts first (parent -1)
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 			if (!v.done[cur]) {
 				int len = 0, p = cur;
 				const uint16_t *bc = &v.bx[4 * cur];
-				while (!v.done[p] && (double)bb_inter(bc, &v.bx[4 * p]) / (double)bb_area(&v.bx[4 * p]) > P.overlap_coef) {
+				while (!v.done[p] && overlap_exceeds(bb_inter(bc, &v.bx[4 * p]), bb_area(&v.bx[4 * p]), P.overlap_coef)) {
 					v.done[p] = 1;
 					if (len < 72) chain[len] = p;
 					len++;
@@ -230,14 +238,28 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 				}
 				if (len > 72) { atomicOr(status, ERR_NMS_OVERFLOW); len = 72; }
 				if (len >= 1 + T) {
+					// stability_i = a_i / (a_{i+T} - a_i) as IEEE doubles in the reference (x/0 = +inf).  For areas below 2^24
+					// two such quotients are equal as doubles iff they are equal as rationals, so the arg-max is decided by
+					// exact 64-bit cross-multiplication (no FP64 divides on this one-thread critical path).
 					int best = 0;
+					long long bn = 0, bd = 1;   // best = bn / bd (bd == 0: +inf)
 					double best_s = 0.0;
+					const bool small = (long long)P.W * P.H < (1ll << 24);
 					for (int i = 0; i < len - T; i++) {
 						const int ai = bb_area(&v.bx[4 * chain[i]]), aj = bb_area(&v.bx[4 * chain[i + T]]);
-						const double s = (double)ai / (double)(aj - ai);
-						if (i == 0) { best = 0; best_s = s; }
-						else if (s > best_s) { best = i; best_s = s; }
-						else if (s == best_s && ai < bb_area(&v.bx[4 * chain[best]])) { best = i; best_s = s; }
+						int cmp;   // sign of (s_i - s_best)
+						if (small) {
+							const long long n_i = ai, d_i = (long long)aj - ai;
+							if (i == 0) cmp = 1;
+							else if (d_i == 0 || bd == 0) cmp = (d_i == 0 && bd == 0) ? 0 : (d_i == 0 ? 1 : -1);
+							else { const long long l = n_i * bd, r = bn * d_i; cmp = (l > r) - (l < r); }
+							if (cmp > 0 || (cmp == 0 && i > 0 && ai < bb_area(&v.bx[4 * chain[best]]))) { best = i; bn = n_i; bd = d_i; }
+						} else {
+							const double sdiv = (double)ai / (double)(aj - ai);
+							if (i == 0) { best = 0; best_s = sdiv; }
+							else if (sdiv > best_s) { best = i; best_s = sdiv; }
+							else if (sdiv == best_s && ai < bb_area(&v.bx[4 * chain[best]])) { best = i; best_s = sdiv; }
+						}
 					}
 					const int b = chain[best];
 					const uint16_t *bb = &v.bx[4 * b];
