@@ -170,7 +170,7 @@ namespace {
 void free_workspace(ert_ctx *c)
 {
 	cudaFree(c->d_ycc); cudaFree(c->d_planes);
-	cudaFree(c->wk.par); cudaFree(c->wk.attr); cudaFree(c->wk.node_list); cudaFree(c->wk.node_count);
+	cudaFree(c->wk.par); cudaFree(c->wk.attr); cudaFree(c->wk.node_list); cudaFree(c->wk.node_count); cudaFree(c->wk.ring_rec);
 	cudaFree(c->wk.reach_root); cudaFree(c->wk.lone_level); cudaFree(c->wk.kept); cudaFree(c->wk.kept_count); cudaFree(c->wk.status);
 	cudaFree(c->d_nms_scratch); cudaFree(c->d_out_nodes); cudaFree(c->d_out_pool); cudaFree(c->d_out_counts); cudaFree(c->d_label);
 	cudaFree(c->d_ss); cudaFree(c->d_ws); cudaFree(c->d_hist);
@@ -216,6 +216,7 @@ int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 	ERT_CUDA_CHECK(cudaMemset(c->d_ycc, 0, c->ycc_bytes * P + 256));
 	if (dmalloc(&c->d_planes, (size_t)P)) return -1;
 	if (dmalloc(&c->wk.par, N * P) || dmalloc(&c->wk.attr, N * P) || dmalloc(&c->wk.node_list, N * P)) return -1;
+	if (dmalloc(&c->wk.ring_rec, ring_words_per_plane(W, H) * P)) return -1;
 	if (dmalloc(&c->wk.node_count, (size_t)P) || dmalloc(&c->wk.reach_root, (size_t)P) || dmalloc(&c->wk.lone_level, (size_t)P)) return -1;
 	if (dmalloc(&c->wk.kept, (size_t)P * c->kept_cap) || dmalloc(&c->wk.kept_count, (size_t)P) || dmalloc(&c->wk.status, 1)) return -1;
 	ERT_CUDA_CHECK(cudaMemset(c->wk.status, 0, sizeof(uint32_t)));

@@ -17,6 +17,7 @@
 // area = pixels + number of nodes in the subtree; bbox exact; kept = area > MIN_AREA or root.
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
 
 namespace ert {
 
@@ -136,7 +137,7 @@ template <int TW, int TH, int NT>
 __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneSrc *__restrict__ planes,
                                                    uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
                                                    uint32_t *__restrict__ node_list, uint32_t *__restrict__ node_count,
-                                                   uint32_t *status, int tiles_x, int local_union, unsigned long long *prof)
+                                                   uint32_t *status, int tiles_x, int local_union, unsigned long long *prof, uint32_t *__restrict__ ring_rec)
 {
 	long long t_prev = prof ? clock64() : 0;
 #define ERT_PHASE(i) do { if (prof && threadIdx.x == 0) { const long long t_now = clock64(); atomicAdd(&prof[i], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
@@ -459,6 +460,10 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	}
 	{
 		const int ring = 2 * (TW + TH);
+		// seam records: for every position on the four tile sides the GLOBAL key of the level root of the pixel
+		// there (KEY_NONE for walls / outside the plane), laid out contiguously per tile so that k_seam_link_rec
+		// reads both sides of a seam coalesced and starts every union at a root
+		uint32_t *rec = ring_rec ? ring_rec + ((size_t)plane * gridDim.x + blockIdx.x) * ring : nullptr;
 		for (int i = tid; i < ring + 3; i += NT) {
 			int x, y;
 			if (i < TW) { x = i; y = 0; }
@@ -466,20 +471,28 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 			else if (i < 2 * TW + TH) { x = 0; y = i - 2 * TW; }
 			else if (i < ring) { x = cols - 1; y = i - 2 * TW - TH; }
 			else { const int gi = i - ring; x = ((gi == 1) ? 1 : 0) - X0; y = ((gi == 2) ? 1 : 0) - Y0; }
-			if (x < 0 || y < 0 || x >= cols || y >= rows) continue;
-			const int p = y * TW + x;
-			const uint32_t L = lvl[p];
-			if (L == 255) continue;
-			uint32_t kk = (L << 16) | (uint32_t)p;
-			for (int guard = 0; guard < 65536; ++guard) {
-				const uint32_t q2 = par[kk & 0xFFFFu];
-				if (q2 == KEY_NONE || (q2 >> 16) != L) break;
-				kk = q2;
+			uint32_t rootkey = KEY_NONE;
+			bool is_root = false;
+			if (x >= 0 && y >= 0 && x < cols && y < rows) {
+				const int p = y * TW + x;
+				const uint32_t L = lvl[p];
+				if (L != 255) {
+					uint32_t kk = (L << 16) | (uint32_t)p;
+					for (int guard = 0; guard < 65536; ++guard) {
+						const uint32_t q2 = par[kk & 0xFFFFu];
+						if (q2 == KEY_NONE || (q2 >> 16) != L) break;
+						kk = q2;
+					}
+					const uint32_t q = kk & 0xFFFFu;
+					is_root = (q == (uint32_t)p);
+					rootkey = make_key(L, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
+				}
 			}
-			const uint32_t q = kk & 0xFFFFu;
-			if (q == (uint32_t)p) continue;   // level roots were written above
-			parP[(uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x)] =
-				make_key(L, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
+			if (rec && i < ring) rec[i] = rootkey;
+			// non-root pixels publish their root in par[] when something will look them up by pixel:
+			// the flood's start candidates always, seam pixels only in the record-less (debug) mode
+			if (rootkey != KEY_NONE && !is_root && (i >= ring || !rec))
+				parP[(uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x)] = rootkey;
 		}
 	}
 	ERT_PHASE(8);
@@ -553,6 +566,42 @@ __global__ void k_seam_link(ExtractParams P, const PlaneSrc *__restrict__ planes
 	}
 	if (skip) return;
 	link_g(parP, make_key((uint32_t)la, (uint32_t)(ya * P.W + xa)), make_key((uint32_t)lb, (uint32_t)(yb * P.W + xb)), status);
+}
+
+// seams from the tile kernel's records: edge = (record of the pixel on one side, record on the other side); a pair
+// identical to the pair one step earlier along the seam (inside the same tile pair) makes the same union and is skipped
+__global__ void k_seam_link_rec(ExtractParams P, const uint32_t *__restrict__ ring_rec, uint32_t *__restrict__ par_g, uint32_t *status,
+                                int TW, int TH, int tiles_x, int tiles_per_plane)
+{
+	const int plane = blockIdx.y;
+	const int RINGW = 2 * (TW + TH);
+	const int nvs = (P.W - 1) / TW, nhs = (P.H - 1) / TH;
+	const long long nv = (long long)nvs * P.H, nh = (long long)nhs * P.W;
+	const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= nv + nh) return;
+	const uint32_t *recP = ring_rec + (size_t)plane * tiles_per_plane * RINGW;
+	uint32_t *parP = par_g + (size_t)plane * P.W * P.H;
+	size_t ia, ib;
+	bool has_prev;
+	if (e < nv) {
+		// consecutive threads walk down one seam line: records of a tile side are contiguous
+		const int k = (int)(e / P.H) + 1, y = (int)(e % P.H);
+		const int ty = y / TH, yy = y % TH;
+		ia = ((size_t)ty * tiles_x + (k - 1)) * RINGW + 2 * TW + TH + yy;   // right side of the left tile
+		ib = ((size_t)ty * tiles_x + k) * RINGW + 2 * TW + yy;             // left side of the right tile
+		has_prev = yy != 0;
+	} else {
+		const long long e2 = e - nv;
+		const int k = (int)(e2 / P.W) + 1, x = (int)(e2 % P.W);
+		const int tx = x / TW, xx = x % TW;
+		ia = ((size_t)(k - 1) * tiles_x + tx) * RINGW + TW + xx;            // bottom side of the upper tile
+		ib = ((size_t)k * tiles_x + tx) * RINGW + xx;                       // top side of the lower tile
+		has_prev = xx != 0;
+	}
+	const uint32_t ra = recP[ia], rb = recP[ib];
+	if (ra == KEY_NONE || rb == KEY_NONE) return;
+	if (has_prev && recP[ia - 1] == ra && recP[ib - 1] == rb) return;
+	link_g(parP, ra, rb, status);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,6 +769,15 @@ int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 struct TileCfg { int tw, th, nt; };
 static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {64, 64, 512}, {128, 32, 512}, {32, 32, 256}, {128, 64, 512}};
 int tile_config_count() { return (int)(sizeof(g_tile_cfgs) / sizeof(g_tile_cfgs[0])); }
+size_t ring_words_per_plane(int W, int H)
+{
+	size_t m = 0;
+	for (int i = 0; i < tile_config_count(); i++) {
+		const TileCfg c = g_tile_cfgs[i];
+		m = std::max(m, (size_t)((W + c.tw - 1) / c.tw) * ((H + c.th - 1) / c.th) * 2 * (c.tw + c.th));
+	}
+	return m;
+}
 
 template <int TW, int TH, int NT>
 static int launch_tile(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st)
@@ -728,7 +786,8 @@ static int launch_tile(const ExtractParams &P, const PlaneSrc *d_planes, Extract
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TW, TH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const int tiles_x = (P.W + TW - 1) / TW, tiles_y = (P.H + TH - 1) / TH;
 	dim3 grid(tiles_x * tiles_y, P.n_planes);
-	k_tile_build<TW, TH, NT><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union, wk.prof);
+	k_tile_build<TW, TH, NT><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union, wk.prof,
+	                                                 local_union ? wk.ring_rec : nullptr);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
@@ -766,7 +825,10 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 		const long long edges = (long long)((P.W - 1) / tw) * P.H + (long long)((P.H - 1) / th) * P.W;
 		if (edges > 0) {
 			dim3 grid((unsigned)((edges + 255) / 256), P.n_planes);
-			k_seam_link<<<grid, 256, 0, st>>>(P, d_planes, wk.par, wk.status, tw, th);
+			if (local_union && wk.ring_rec) {
+				const int tiles_x = (P.W + tw - 1) / tw, tiles_y = (P.H + th - 1) / th;
+				k_seam_link_rec<<<grid, 256, 0, st>>>(P, wk.ring_rec, wk.par, wk.status, tw, th, tiles_x, tiles_x * tiles_y);
+			} else k_seam_link<<<grid, 256, 0, st>>>(P, d_planes, wk.par, wk.status, tw, th);
 			ERT_CUDA_CHECK(cudaGetLastError());
 		}
 	}

@@ -17,6 +17,7 @@ struct ExtractWork {
 	int node_blocks;        // grid.x of the node-list kernels
 	int tile_cfg;           // index into the tile configuration table
 	unsigned long long *prof;   // optional [16] per-phase cycle sums of k_tile_build (debug)
+	uint32_t *ring_rec;     // [n_planes][tiles][2*(TW+TH)] root keys on the tile sides (seam records)
 };
 
 struct NmsParams {
@@ -57,6 +58,7 @@ struct SvmDev {
 
 int extract_pitch(int W);
 int tile_config_count();
+size_t ring_words_per_plane(int W, int H);
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st);
 int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
                    cudaEvent_t ev_tile_begin = nullptr, cudaEvent_t ev_tile_end = nullptr);
