@@ -283,7 +283,7 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 	cudaStream_t st = c->stream;
 	const ExtractParams EP = make_extract_params(c, n_planes);
 	if (launch_extract(EP, c->d_planes, c->wk, c->local_union, st, c->ev[8], c->ev[9])) return -1;
-	c->launches += 6;
+	c->launches += 5;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[2], st));
 	const NmsParams NP = make_nms_params(c, c->W, c->H);
 	if (launch_nms(NP, n_planes, c->wk.kept, c->wk.kept_count, c->wk.attr, c->wk.reach_root, c->wk.lone_level, nullptr, nullptr,

@@ -9,8 +9,8 @@
 //   k_seam_link     stitch tiles: the same keyed union-find on the (few) edges that cross tile seams
 //   k_fold          fold nodes that were merged across seams into their final node; count children
 //   k_refit         bottom-up accumulation of (pixels, nodes, bbox) with arrival counters, no grid sync
-//   k_reach_root    the flood's start-pixel rule (src/ER.cpp:267-341): which tree is the reference's
-//   k_emit_kept     compact the nodes the reference keeps (area > MIN_AREA, or the root)
+//   k_emit_kept     the flood's start-pixel rule (src/ER.cpp:267-341) picks the reference's tree; compact the nodes
+//                   the reference keeps (area > MIN_AREA, or the root)
 //
 // Exact reference semantics reproduced: level = rint_half_even(v/step); levels >= hi
 // are walls; one node per (level L, 4-connected component of {level<=L} holding a level-L pixel);
@@ -94,9 +94,9 @@ __device__ __forceinline__ bool climb_s(volatile uint32_t *par, uint32_t &k)
 	const uint32_t p = par[k & 0xFFFFu];
 	if (p == KEY_NONE || (p >> 16) != (k >> 16)) return true;
 	const uint32_t g = par[p & 0xFFFFu];
-	if (g != KEY_NONE && (g >> 16) == (k >> 16)) { par[k & 0xFFFFu] = g; k = g; }
-	else k = p;
-	return false;
+	if (g != KEY_NONE && (g >> 16) == (k >> 16)) { par[k & 0xFFFFu] = g; k = g; return false; }
+	k = p;          // p's own pointer leaves the level: p IS the level root -- no extra round to find that out
+	return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -689,24 +689,18 @@ __global__ void k_refit(ExtractParams P, const uint32_t *__restrict__ par_g, Nod
 // k_reach_root : the flood starts at pixel 0; if that is a wall it escapes to pixel 1, else to
 // pixel W (neighbour order right, bottom); only that tree is the reference's result.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_reach_root(ExtractParams P, const PlaneSrc *__restrict__ planes, const uint32_t *__restrict__ par_g,
-                             uint32_t *__restrict__ reach_root, int32_t *__restrict__ lone_level)
+__device__ uint32_t reach_root_of(const ExtractParams &P, const PlaneSrc &ps, const uint32_t *parP, int32_t *lone)
 {
-	const int plane = blockIdx.x * blockDim.x + threadIdx.x;
-	if (plane >= P.n_planes) return;
-	const PlaneSrc ps = planes[plane];
-	const uint32_t *parP = par_g + (size_t)plane * P.W * P.H;
 	int s = -1, ls = 255;
 	const int l0 = level_at(ps, P, 0, 0);
 	if (l0 != 255) { s = 0; ls = l0; }
 	else if (P.W > 1 && (ls = level_at(ps, P, 1, 0)) != 255) s = 1;
 	else if (P.H > 1 && (ls = level_at(ps, P, 0, 1)) != 255) s = P.W;
 	if (s < 0) {
-		reach_root[plane] = KEY_NONE;
 		int v = __ldg(ps.src);
 		if (ps.invert) v = 255 - v;
-		lone_level[plane] = quantize_level(v, P.qscale);
-		return;
+		*lone = quantize_level(v, P.qscale);
+		return KEY_NONE;
 	}
 	uint32_t k = find_g(parP, make_key((uint32_t)ls, (uint32_t)s));
 	for (int guard = 0; guard < 64; ++guard) {
@@ -714,8 +708,8 @@ __global__ void k_reach_root(ExtractParams P, const PlaneSrc *__restrict__ plane
 		if (p == KEY_NONE) break;
 		k = p;
 	}
-	reach_root[plane] = k;
-	lone_level[plane] = -1;
+	*lone = -1;
+	return k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -723,15 +717,23 @@ __global__ void k_reach_root(ExtractParams P, const PlaneSrc *__restrict__ plane
 // ---------------------------------------------------------------------------------------------
 __global__ void k_emit_kept(ExtractParams P, const uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
                             const uint32_t *__restrict__ node_list, const uint32_t *__restrict__ node_count,
-                            const uint32_t *__restrict__ reach_root, KeptRec *__restrict__ kept, uint32_t *__restrict__ kept_count,
-                            uint32_t *status)
+                            const PlaneSrc *__restrict__ planes, uint32_t *__restrict__ reach_root, int32_t *__restrict__ lone_level,
+                            KeptRec *__restrict__ kept, uint32_t *__restrict__ kept_count, uint32_t *status)
 {
 	const int plane = blockIdx.y;
 	const size_t N = (size_t)P.W * P.H;
 	const uint32_t *parP = par_g + (size_t)plane * N;
 	NodeAttr *attrP = attr_g + (size_t)plane * N;
 	const uint32_t n = node_count[plane];
-	const uint32_t rr = reach_root[plane];
+	// the flood's start-pixel rule, evaluated once per block (a ~40-load dependent chain, cheaper than its own launch)
+	__shared__ uint32_t s_rr;
+	if (threadIdx.x == 0) {
+		int32_t lone = -1;
+		s_rr = reach_root_of(P, planes[plane], parP, &lone);
+		if (blockIdx.x == 0) { reach_root[plane] = s_rr; lone_level[plane] = lone; }
+	}
+	__syncthreads();
+	const uint32_t rr = s_rr;
 	if (rr == KEY_NONE) return;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint32_t g = node_list[(size_t)plane * N + i];
@@ -838,9 +840,8 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 		ERT_CUDA_CHECK(cudaGetLastError());
 		k_refit<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_list, wk.node_count);
 		ERT_CUDA_CHECK(cudaGetLastError());
-		k_reach_root<<<(P.n_planes + 63) / 64, 64, 0, st>>>(P, d_planes, wk.par, wk.reach_root, wk.lone_level);
-		ERT_CUDA_CHECK(cudaGetLastError());
-		k_emit_kept<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_list, wk.node_count, wk.reach_root, wk.kept, wk.kept_count, wk.status);
+		k_emit_kept<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_list, wk.node_count, d_planes, wk.reach_root, wk.lone_level, wk.kept,
+		                                  wk.kept_count, wk.status);
 		ERT_CUDA_CHECK(cudaGetLastError());
 	}
 	return 0;
