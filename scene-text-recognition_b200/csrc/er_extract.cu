@@ -144,16 +144,15 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	constexpr int TPX = TW * TH;
 	constexpr int SEGS = TPX / 32;
 	constexpr int NWARP = NT / 32;
-	static_assert(TW % 32 == 0 && TPX <= 32768, "tile shape");
+	static_assert(TW % 32 == 0 && TPX <= 32768 && TH <= 32, "tile shape");
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t *lvl = smem;                                     // TMA destination, converted to levels in place
 	uint32_t *par = reinterpret_cast<uint32_t *>(smem + TPX);
 	uint32_t *cnt = par + TPX;
 	uint32_t *xmn = cnt + TPX;
 	uint32_t *xmx = xmn + TPX;
-	uint32_t *ymn = xmx + TPX;
-	uint32_t *ymx = ymn + TPX;
-	uint16_t *rootlist = reinterpret_cast<uint16_t *>(ymx + TPX);
+	uint32_t *ymask = xmx + TPX;                             // one bit per tile row (TH <= 32)
+	uint16_t *rootlist = reinterpret_cast<uint16_t *>(ymask + TPX);
 	__shared__ __align__(8) uint64_t bar;
 	__shared__ uint32_t s_nroots, s_base, s_cursor, s_nlinks, s_nemit, s_minlvl, s_maxlvl;
 
@@ -227,8 +226,22 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 			if (lane == 0 && (mh | mv)) base = atomicAdd(&s_nlinks, (uint32_t)(__popc(mh) + __popc(mv)));
 			base = __shfl_sync(0xFFFFFFFFu, base, 0);
 			const uint32_t lt = (1u << lane) - 1u;
-			if (eh) links[base + __popc(mh & lt)] = ((uint32_t)p << 16) | (uint32_t)(p + 1);
-			if (ev) links[base + __popc(mh) + __popc(mv & lt)] = ((uint32_t)p << 16) | (uint32_t)(p + TW);
+			// endpoints are stored as the LAST pixel of each pixel's same-level run (what phase A made it point at):
+			// that pixel is the run's level root until the run is merged, so most edges start with both ends at a root
+			if (eh | ev) {
+				const uint32_t pp = par[p];
+				const uint32_t ep = (pp != KEY_NONE && (pp >> 16) == L) ? (pp & 0xFFFFu) : (uint32_t)p;
+				if (eh) {
+					const uint32_t q = (uint32_t)(p + 1), pq = par[q];
+					const uint32_t eq = (pq != KEY_NONE && (pq >> 16) == (uint32_t)lvl[q]) ? (pq & 0xFFFFu) : q;
+					links[base + __popc(mh & lt)] = (ep << 16) | eq;
+				}
+				if (ev) {
+					const uint32_t q = (uint32_t)(p + TW), pq = par[q];
+					const uint32_t eq = (pq != KEY_NONE && (pq >> 16) == (uint32_t)lvl[q]) ? (pq & 0xFFFFu) : q;
+					links[base + __popc(mh) + __popc(mv & lt)] = (ep << 16) | eq;
+				}
+			}
 		}
 		__syncthreads();
 		ERT_PHASE(2);
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		ERT_PHASE(3);
 	}
 	ERT_PHASE(4);
-	for (int p = tid; p < TPX; p += NT) { cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymn[p] = 0xFFFFFFFFu; ymx[p] = 0; }
+	for (int p = tid; p < TPX; p += NT) { cnt[p] = 0; xmn[p] = 0xFFFFFFFFu; xmx[p] = 0; ymask[p] = 0; }
 	__syncthreads();
 
 	// ---- phase D: own-level pixel count and bbox per tile-local node, one update per same-level run; the run's
@@ -303,7 +316,11 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 				if (act) {
 					const uint32_t q = vpar[k & 0xFFFFu];
 					if (q == KEY_NONE || (q >> 16) != L) { act = false; isroot = ((k & 0xFFFFu) == (uint32_t)p); }
-					else k = q;
+					else {
+						const uint32_t g = vpar[q & 0xFFFFu];           // two hops per round; q is the root if its pointer leaves the level
+						if (g == KEY_NONE || (g >> 16) != L) { k = q; act = false; }
+						else k = g;
+					}
 				}
 			}
 			if (runend) {
@@ -314,8 +331,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 				atomicAdd(&cnt[r], (uint32_t)len + (isroot ? ACC_NODE : 0u));
 				atomicMin(&xmn[r], (uint32_t)(x - (lane - start)));
 				atomicMax(&xmx[r], (uint32_t)x);
-				atomicMin(&ymn[r], (uint32_t)y);
-				if (isroot) ymx[p] = (uint32_t)y;   // the level root is the node's last own-level pixel
+				atomicOr(&ymask[r], 1u << y);
 			}
 			const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, isroot);
 			uint32_t wb = 0;
@@ -407,7 +423,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 				const uint32_t q = up & 0xFFFFu;
 				atomicAdd(&cnt[q], acc);           // pixels and node count travel together
 				atomicMin(&xmn[q], xmn[p]); atomicMax(&xmx[q], xmx[p]);
-				atomicMin(&ymn[q], ymn[p]); atomicMax(&ymx[q], ymx[p]);
+				atomicOr(&ymask[q], ymask[p]);
 			}
 			__syncthreads();
 		}
@@ -454,7 +470,8 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		parP[gidx] = gpar;
 		uint4 *a = reinterpret_cast<uint4 *>(&attrP[gidx]);
 		a[0] = make_uint4(acc & ACC_MASK, (acc >> 15) & ACC_MASK, (acc & ACC_BORDER) ? 0u : NODE_COMPLETE, 0u);
-		a[1] = make_uint4((uint32_t)X0 + xmn[p], (uint32_t)Y0 + ymn[p], (uint32_t)X0 + xmx[p], (uint32_t)Y0 + ymx[p]);
+		const uint32_t ym = ymask[p];
+		a[1] = make_uint4((uint32_t)X0 + xmn[p], (uint32_t)Y0 + (uint32_t)(__ffs(ym) - 1), (uint32_t)X0 + xmx[p], (uint32_t)Y0 + (uint32_t)(31 - __clz(ym)));
 		const uint32_t pos = s_base + wbase + (uint32_t)__popc(emask & ((1u << lane) - 1u));
 		node_list[(size_t)plane * N + pos] = make_key(L, gidx);
 	}
@@ -769,7 +786,7 @@ int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 
 // tile configurations (selectable at run time for tuning; id 0 is the default)
 struct TileCfg { int tw, th, nt; };
-static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {64, 64, 512}, {128, 32, 512}, {32, 32, 256}, {128, 64, 512}};
+static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {128, 32, 512}, {32, 32, 256}, {64, 16, 256}};
 int tile_config_count() { return (int)(sizeof(g_tile_cfgs) / sizeof(g_tile_cfgs[0])); }
 size_t ring_words_per_plane(int W, int H)
 {
@@ -784,7 +801,7 @@ size_t ring_words_per_plane(int W, int H)
 template <int TW, int TH, int NT>
 static int launch_tile(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st)
 {
-	const size_t smem = (size_t)TW * TH * (1 + 6 * 4 + 2);
+	const size_t smem = (size_t)TW * TH * (1 + 5 * 4 + 2);
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TW, TH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const int tiles_x = (P.W + TW - 1) / TW, tiles_y = (P.H + TH - 1) / TH;
 	dim3 grid(tiles_x * tiles_y, P.n_planes);
@@ -813,10 +830,9 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	int rc = -1;
 	switch (wk.tile_cfg) {
 	case 1: rc = launch_tile<64, 32, 256>(P, d_planes, wk, local_union, st); break;
-	case 2: rc = launch_tile<64, 64, 512>(P, d_planes, wk, local_union, st); break;
-	case 3: rc = launch_tile<128, 32, 512>(P, d_planes, wk, local_union, st); break;
-	case 4: rc = launch_tile<32, 32, 256>(P, d_planes, wk, local_union, st); break;
-	case 5: rc = launch_tile<128, 64, 512>(P, d_planes, wk, local_union, st); break;
+	case 2: rc = launch_tile<128, 32, 512>(P, d_planes, wk, local_union, st); break;
+	case 3: rc = launch_tile<32, 32, 256>(P, d_planes, wk, local_union, st); break;
+	case 4: rc = launch_tile<64, 16, 256>(P, d_planes, wk, local_union, st); break;
 	default: rc = launch_tile<64, 32, 512>(P, d_planes, wk, local_union, st); break;
 	}
 	if (rc) return rc;
