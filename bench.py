@@ -347,6 +347,8 @@ def cpu_baseline(a, host_batches):
 
 
 def main():
+    # keep stdout to the ONE JSON line: NCCL's version / debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
