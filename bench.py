@@ -27,6 +27,15 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "1080p frames/sec (ER detect+classify)"
 UNIT = "frames/s"
 
@@ -151,7 +160,7 @@ def run_reference(a, rank):
     frames = np.stack([base[i % fpg] for i in range(n_step)])
     fpg = n_step
     if ref is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so not present and the C port has no frame driver"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so not present and the C port has no frame driver"})
         return
     for _ in range(a.warmup):
         ref.detect_frames(frames[: max(1, min(fpg, cores))], mode=1, nthreads=cores)
@@ -173,7 +182,7 @@ def run_reference(a, rank):
         "gpu_launches": 0,
         "regions_per_frame": float(counts[:, 1].mean()) if counts is not None else None,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -328,7 +337,7 @@ def run_ours(a, rank, local_rank, world):
     }
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, host_batches)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -351,8 +360,12 @@ def cpu_baseline(a, host_batches):
 
 
 def main():
-    # keep stdout to the ONE JSON line: NCCL's version / debug banner goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # keep stdout to the ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there)
+    # are pointed at stderr; the JSON line goes to a private duplicate of the original stdout
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -361,7 +374,7 @@ def main():
         run_reference(a, rank)
         return
     if world != a.gpus and world == 1 and a.gpus > 1:
-        print(json.dumps({"error": "launch with torchrun --nproc-per-node %d for --gpus %d" % (a.gpus, a.gpus)}))
+        emit({"error": "launch with torchrun --nproc-per-node %d for --gpus %d" % (a.gpus, a.gpus)})
         sys.exit(2)
     run_ours(a, rank, local_rank, world)
 
