@@ -133,7 +133,7 @@ __device__ __forceinline__ void tma_row_g2s(void *dst_smem, const void *src_gmem
 // ---------------------------------------------------------------------------------------------
 // k_tile_build
 // ---------------------------------------------------------------------------------------------
-template <int TW, int TH, int NT>
+template <int TW, int TH, int NT, int RF, bool CHUNK>
 __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneSrc *__restrict__ planes,
                                                    uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
                                                    uint32_t *__restrict__ node_list, uint32_t *__restrict__ node_count,
@@ -213,13 +213,15 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 			const int p = seg * 32 + lane;
 			const int y = p / TW, x = p % TW;
 			const uint32_t L = lvl[p];
+			const uint32_t Lb = (y + 1 < TH) ? (uint32_t)lvl[p + TW] : 255u;        // pixel below
+			// horizontal neighbours come from the neighbouring lanes; only the segment's end lanes touch shared memory
+			uint32_t Lrt = __shfl_down_sync(0xFFFFFFFFu, L, 1), Llf = __shfl_up_sync(0xFFFFFFFFu, L, 1), Lbl = __shfl_up_sync(0xFFFFFFFFu, Lb, 1);
+			if (lane == 31) Lrt = (x + 1 < TW) ? (uint32_t)lvl[p + 1] : 255u;
+			if (lane == 0) { Llf = (x > 0) ? (uint32_t)lvl[p - 1] : 255u; Lbl = (x > 0 && y + 1 < TH) ? (uint32_t)lvl[p + TW - 1] : 255u; }
 			bool eh = false, ev = false;
 			if (L != 255) {
-				if (x + 1 < TW) { const uint32_t Lq = lvl[p + 1]; eh = (Lq != 255) && (Lq != L || lane == 31); }
-				if (y + 1 < TH) {
-					const uint32_t Lq = lvl[p + TW];
-					if (Lq != 255) ev = !((x > 0) && (lvl[p - 1] == L) && (lvl[p + TW - 1] == Lq));
-				}
+				eh = (Lrt != 255) && (Lrt != L || lane == 31);
+				if (Lb != 255) ev = !((x > 0) && (Llf == L) && (Lbl == Lb));
 			}
 			const uint32_t mh = __ballot_sync(0xFFFFFFFFu, eh), mv = __ballot_sync(0xFFFFFFFFu, ev);
 			uint32_t base = 0;
@@ -249,15 +251,22 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 			const uint32_t nl = s_nlinks;
 			uint32_t a = 0, b = 0;
 			bool act = false, more = true;
+			// CHUNK: every warp owns a contiguous share of the (roughly raster-ordered) list: no shared cursor
+			const uint32_t per_warp = (nl + NWARP - 1) / NWARP;
+			uint32_t wnext = (uint32_t)warp * per_warp;
+			const uint32_t wend = min(nl, wnext + per_warp);
 			for (int guard = 0; guard < (1 << 22); ++guard) {
 				const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !act);
-				if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= 12)) {
-					uint32_t base = 0;
-					if (lane == 0) base = atomicAdd(&s_cursor, (uint32_t)__popc(idle));
-					base = __shfl_sync(0xFFFFFFFFu, base, 0);
+				if (more && (idle == 0xFFFFFFFFu || __popc(idle) >= RF)) {
+					uint32_t base = 0, lim = nl;
+					if (CHUNK) { base = wnext; wnext += (uint32_t)__popc(idle); lim = wend; }
+					else {
+						if (lane == 0) base = atomicAdd(&s_cursor, (uint32_t)__popc(idle));
+						base = __shfl_sync(0xFFFFFFFFu, base, 0);
+					}
 					if (!act) {
 						const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
-						if (i < nl) {
+						if (i < lim) {
 							// the list is drained from its END (bottom-right of the tile first): the level root of a
 							// node is its last pixel in raster order, so it is met first and stays put while the rows
 							// above attach to it directly -- chains stay ~1 hop deep instead of one hop per row
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 							act = true;
 						}
 					}
-					if (base + (uint32_t)__popc(idle) >= nl) more = false;
+					if (base + (uint32_t)__popc(idle) >= lim) more = false;
 				}
 				if (!__any_sync(0xFFFFFFFFu, act)) { if (!more) break; else continue; }
 				if (act) {
@@ -786,7 +795,7 @@ int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 
 // tile configurations (selectable at run time for tuning; id 0 is the default)
 struct TileCfg { int tw, th, nt; };
-static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {128, 32, 512}, {32, 32, 256}, {64, 16, 256}};
+static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {128, 32, 512}, {32, 32, 256}, {64, 32, 512}};
 int tile_config_count() { return (int)(sizeof(g_tile_cfgs) / sizeof(g_tile_cfgs[0])); }
 size_t ring_words_per_plane(int W, int H)
 {
@@ -798,14 +807,14 @@ size_t ring_words_per_plane(int W, int H)
 	return m;
 }
 
-template <int TW, int TH, int NT>
+template <int TW, int TH, int NT, int RF, bool CHUNK>
 static int launch_tile(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st)
 {
 	const size_t smem = (size_t)TW * TH * (1 + 5 * 4 + 2);
-	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TW, TH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TW, TH, NT, RF, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const int tiles_x = (P.W + TW - 1) / TW, tiles_y = (P.H + TH - 1) / TH;
 	dim3 grid(tiles_x * tiles_y, P.n_planes);
-	k_tile_build<TW, TH, NT><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union, wk.prof,
+	k_tile_build<TW, TH, NT, RF, CHUNK><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union, wk.prof,
 	                                                 local_union ? wk.ring_rec : nullptr);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
@@ -829,11 +838,11 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	if (ev_tile_begin) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_begin, st));
 	int rc = -1;
 	switch (wk.tile_cfg) {
-	case 1: rc = launch_tile<64, 32, 256>(P, d_planes, wk, local_union, st); break;
-	case 2: rc = launch_tile<128, 32, 512>(P, d_planes, wk, local_union, st); break;
-	case 3: rc = launch_tile<32, 32, 256>(P, d_planes, wk, local_union, st); break;
-	case 4: rc = launch_tile<64, 16, 256>(P, d_planes, wk, local_union, st); break;
-	default: rc = launch_tile<64, 32, 512>(P, d_planes, wk, local_union, st); break;
+	case 1: rc = launch_tile<64, 32, 256, 8, true>(P, d_planes, wk, local_union, st); break;
+	case 2: rc = launch_tile<128, 32, 512, 8, true>(P, d_planes, wk, local_union, st); break;
+	case 3: rc = launch_tile<32, 32, 256, 8, true>(P, d_planes, wk, local_union, st); break;
+	case 4: rc = launch_tile<64, 32, 512, 12, false>(P, d_planes, wk, local_union, st); break;   // shared work queue instead of per-warp shares
+	default: rc = launch_tile<64, 32, 512, 8, true>(P, d_planes, wk, local_union, st); break;
 	}
 	if (rc) return rc;
 	if (ev_tile_end) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_end, st));
