@@ -120,6 +120,12 @@ ERT_API int ert_enqueue_host(ert_ctx *ctx, const uint8_t *bgr, int n_frames, int
 ERT_API int ert_detect_classify_device(ert_ctx *ctx, const void *d_bgr, int n_frames, int width, int height, int stride_bytes, int upto);
 ERT_API int ert_fetch_result(ert_ctx *ctx, const ert_result **out);
 
+/* ERFilter::compute_channels(src, YCrCb, channels)  (src/ER.cpp:114-128): BGR -> the six 8-bit planes
+ * Y, Cr, Cb, 255-Y, 255-Cr, 255-Cb (OpenCV's 8-bit BGR2YCrCb arithmetic), written to planes6 as six
+ * contiguous width*height images in host memory.  The batched entry points above fuse this step; this
+ * call exists for callers that need the planes themselves (er_track / er_ocr read them). */
+ERT_API int ert_compute_channels(ert_ctx *ctx, const uint8_t *bgr, int width, int height, int stride_bytes, uint8_t *planes6);
+
 /* ERFilter::er_tree_extract(Mat) / non_maximum_supression / classify on caller-supplied
  * single-channel planes (src/ER.cpp:240, 416, 507; inc/ER.h:125-127): n_planes images of the same
  * size, plane k at planes + k*plane_stride_bytes, rows stride_bytes apart, host memory. */

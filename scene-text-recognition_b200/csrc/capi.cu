@@ -663,6 +663,22 @@ int ert_detect_classify_device(ert_ctx *c, const void *d_bgr, int n_frames, int 
 
 int ert_fetch_result(ert_ctx *c, const ert_result **out) { return finish_result(c, out); }
 
+int ert_compute_channels(ert_ctx *c, const uint8_t *bgr, int W, int H, int stride, uint8_t *planes6)
+{
+	if (!c || !bgr || !planes6 || W < 1 || H < 1 || stride < 3 * W) { set_error("bad arguments"); return -1; }
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const int pitch = extract_pitch(W);
+	const size_t in_b = (size_t)stride * H, ycc_b = (size_t)pitch * H * 3, out_b = (size_t)W * H * 6;
+	if (c->s0.ensure(in_b) || c->s1.ensure(ycc_b) || c->s2.ensure(out_b)) return -1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, bgr, in_b, cudaMemcpyHostToDevice, st));
+	if (launch_channels((const uint8_t *)c->s0.p, in_b, stride, W, H, 1, (uint8_t *)c->s1.p, pitch, st)) return -1;
+	if (launch_unpack_planes((const uint8_t *)c->s1.p, pitch, W, H, (uint8_t *)c->s2.p, st)) return -1;
+	ERT_CUDA_CHECK(cudaMemcpyAsync(planes6, c->s2.p, out_b, cudaMemcpyDeviceToHost, st));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}
+
 int ert_planes_detect(ert_ctx *c, const uint8_t *planes, int n_planes, int W, int H, int stride, size_t plane_stride, int upto, const ert_result **out)
 {
 	if (!c || !planes || n_planes < 1 || stride < W) { set_error("bad arguments"); return -1; }

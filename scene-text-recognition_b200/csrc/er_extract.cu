@@ -820,6 +820,27 @@ static int launch_tile(const ExtractParams &P, const PlaneSrc *d_planes, Extract
 	return 0;
 }
 
+__global__ void k_unpack_planes(const uint8_t *__restrict__ ycc, int pitch, int W, int H, uint8_t *__restrict__ out6)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x >= W) return;
+	const size_t plane_bytes = (size_t)pitch * H, n = (size_t)W * H;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const uint8_t v = ycc[k * plane_bytes + (size_t)y * pitch + x];
+		out6[k * n + (size_t)y * W + x] = v;
+		out6[(k + 3) * n + (size_t)y * W + x] = (uint8_t)(255 - v);
+	}
+}
+
+int launch_unpack_planes(const uint8_t *d_ycc, int pitch, int W, int H, uint8_t *d_out6, cudaStream_t st)
+{
+	dim3 grid((W + 255) / 256, H);
+	k_unpack_planes<<<grid, 256, 0, st>>>(d_ycc, pitch, W, H, d_out6);
+	ERT_CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st)
 {
 	dim3 block(128), grid(((W + 3) / 4 + 127) / 128, H, n_frames);

@@ -60,6 +60,7 @@ int extract_pitch(int W);
 int tile_config_count();
 size_t ring_words_per_plane(int W, int H);
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st);
+int launch_unpack_planes(const uint8_t *d_ycc, int pitch, int W, int H, uint8_t *d_out6, cudaStream_t st);
 int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
                    cudaEvent_t ev_tile_begin = nullptr, cudaEvent_t ev_tile_end = nullptr);
 

@@ -38,7 +38,7 @@ EXPORTS = [
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
     "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
     "ert_load_svm", "ert_svm_nr_class", "ert_set_svm_tensor_cores", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
-    "ert_fetch_result", "ert_planes_detect", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
+    "ert_fetch_result", "ert_compute_channels", "ert_planes_detect", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
     "ert_cascade_predict_batch", "ert_cascade_classify_u8", "ert_svm_predict_probability_batch",
     "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
     "ert_bench_cascade_u8", "ert_bench_svm_u8",
@@ -75,6 +75,7 @@ def load_library():
     L.ert_detect_classify_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ert_enqueue_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ert_fetch_result.argtypes = [C.c_void_p, RP]
+    L.ert_compute_channels.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
     L.ert_planes_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, RP]
     L.ert_nms_nodes.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int)]
     L.ert_classify_regions.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f64p, _f64p, _u8p]
@@ -244,6 +245,14 @@ class ErText:
         rp = C.POINTER(ErtResult)()
         self._check(self.L.ert_fetch_result(self.ctx, C.byref(rp)))
         return self._unpack(rp)
+
+    def compute_channels(self, bgr):
+        """ERFilter::compute_channels: uint8 [H,W,3] BGR -> uint8 [6,H,W] (Y, Cr, Cb and their inverses)."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        h, w, _ = bgr.shape
+        out = np.zeros((6, h, w), np.uint8)
+        self._check(self.L.ert_compute_channels(self.ctx, _ptr(bgr, _u8p), w, h, w * 3, _ptr(out, _u8p)))
+        return out
 
     def planes_detect(self, planes, upto=STAGE_CLASSIFY):
         """planes: uint8 [P,H,W] (or [H,W]) single-channel images."""

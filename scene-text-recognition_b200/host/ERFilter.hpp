@@ -156,6 +156,15 @@ public:
 		return times;
 	}
 
+	// compute_channels(src, YCrcb, channels)  (src/ER.cpp:114-128): the six planes as one contiguous buffer
+	// (plane k at channels6.data() + k * rows * cols); wrap them in Mat headers as needed.
+	void compute_channels(const Mat &src, std::vector<unsigned char> &channels6)
+	{
+		if (src.empty() || src.channels() != 3) throw std::runtime_error("compute_channels: 8UC3 BGR image expected");
+		channels6.resize((size_t)src.rows * src.cols * 6);
+		if (ert_compute_channels(dev_.ctx(), src.data, src.cols, src.rows, (int)src.step, channels6.data())) throw_last("compute_channels");
+	}
+
 	// ER* er_tree_extract(Mat input)  (src/ER.cpp:240): 8UC1 plane -> heap tree owned by the caller (er_delete).
 	ER *er_tree_extract(const Mat &input)
 	{

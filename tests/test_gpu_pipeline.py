@@ -213,3 +213,41 @@ def test_noise_full_hd_worst_case(ert, port):
         exp = port.plane(ch[k], scores=True, canonical_order=True)
         got = res.planes[k]
         assert (got.nodes == exp["nodes"]).all() and (got.pool == exp["pool"]).all() and (got.label == exp["label"]).all()
+
+
+def test_compute_channels_and_plane_path_equals_bgr_path(ert, port, golden_frames):
+    """compute_channels == OpenCV BGR2YCrCb arithmetic (oracle, pinned against cv2); feeding those six planes through the
+    single-channel entry point gives exactly what the fused BGR entry point gives (full 1080p, no oracle needed)."""
+    from ertext import synth
+    pytest.importorskip("cv2")
+    ch = ert.compute_channels(golden_frames[0])
+    assert (ch == port.channels(golden_frames[0])).all()
+    frame = synth.s_text_frame(4321)
+    planes = ert.compute_channels(frame)
+    a = ert.detect_classify(frame)
+    b = ert.planes_detect(planes)
+    for pa, pb in zip(a.planes, b.planes):
+        assert (pa.nodes == pb.nodes).all() and (pa.pool == pb.pool).all() and (pa.label == pb.label).all()
+        assert (pa.strong_score == pb.strong_score).all()
+
+
+def test_batch_equals_frame_by_frame_and_all_tile_shapes_agree(ert):
+    """Size-independent properties at the benchmark's size: a batch gives what its frames give one at a time, and every
+    tile shape / work-distribution variant of the tile kernel produces identical results."""
+    from ertext import synth
+    pytest.importorskip("cv2")
+    frames = synth.s_text_batch(900, 3)
+    batch = ert.detect_classify(frames)
+    for f in range(3):
+        one = ert.detect_classify(frames[f])
+        for k in range(6):
+            assert (one.planes[k].nodes == batch.planes[f * 6 + k].nodes).all()
+            assert (one.planes[k].pool == batch.planes[f * 6 + k].pool).all()
+    sig = [(p.nodes.tobytes(), p.pool.tobytes(), p.label.tobytes()) for p in batch.planes]
+    try:
+        for cfg in (1, 2, 3, 4):
+            ert.set_tile_config(cfg)
+            r = ert.detect_classify(frames)
+            assert [(p.nodes.tobytes(), p.pool.tobytes(), p.label.tobytes()) for p in r.planes] == sig, cfg
+    finally:
+        ert.set_tile_config(0)
