@@ -213,8 +213,16 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 	}
 	__syncthreads();
 
+	// one 16-byte record per node for the sequential walk (aliases the sort keys, which are dead now):
+	// {parent, first child, x0 | y0 << 16, x1 | y1 << 16} -> one 128-bit load per visited node
+	uint4 *rec = reinterpret_cast<uint4 *>(v.keyA);
+	for (int j = tid; j < n; j += NT)
+		rec[j] = make_uint4((uint32_t)v.parent[j], (uint32_t)v.first[j], (uint32_t)v.bx[4 * j] | ((uint32_t)v.bx[4 * j + 1] << 16),
+		                    (uint32_t)v.bx[4 * j + 2] | ((uint32_t)v.bx[4 * j + 3] << 16));
+	__syncthreads();
+
 	// ---- (4) the reference's sequential walk (src/ER.cpp:426-502) ----
-	__shared__ int stack[72], chain[72];
+	__shared__ int stack[72], chain[72], chain_area[72];
 	if (tid == 0) {
 		int sp = 0, pre = 0, npool = 0;
 		const int T = P.stability_t;
@@ -222,19 +230,27 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 		for (long long guard = 0; guard < 4ll * n + 8; ++guard) {
 			while (cur >= 0) {
 				if (sp >= 72) { atomicOr(status, ERR_NMS_OVERFLOW); cur = -1; break; }
-				stack[sp++] = cur; v.pre[cur] = pre++; cur = v.first[cur];
+				stack[sp++] = cur; v.pre[cur] = pre++; cur = (int)rec[cur].y;
 			}
 			if (sp == 0) break;
 			cur = stack[--sp];
+			const uint4 rc = rec[cur];
 			if (!v.done[cur]) {
 				int len = 0, p = cur;
-				const uint16_t *bc = &v.bx[4 * cur];
-				while (!v.done[p] && overlap_exceeds(bb_inter(bc, &v.bx[4 * p]), bb_area(&v.bx[4 * p]), P.overlap_coef)) {
+				const int cx0 = rc.z & 0xFFFF, cy0 = rc.z >> 16, cx1 = rc.w & 0xFFFF, cy1 = rc.w >> 16;
+				uint4 rp = rc;
+				for (;;) {
+					if (v.done[p]) break;
+					const int px0 = rp.z & 0xFFFF, py0 = rp.z >> 16, px1 = rp.w & 0xFFFF, py1 = rp.w >> 16;
+					const int ix0 = max(cx0, px0), iy0 = max(cy0, py0), ix1 = min(cx1, px1), iy1 = min(cy1, py1);
+					const int inter = (ix1 < ix0 || iy1 < iy0) ? 0 : (ix1 - ix0 + 1) * (iy1 - iy0 + 1);
+					const int parea = (px1 - px0 + 1) * (py1 - py0 + 1);
+					if (!overlap_exceeds(inter, parea, P.overlap_coef)) break;
 					v.done[p] = 1;
-					if (len < 72) chain[len] = p;
+					if (len < 72) { chain[len] = p; chain_area[len] = parea; }
 					len++;
-					const int pp = v.parent[p];
-					p = (pp < 0) ? p : pp;      // root->parent = root (src/ER.cpp:424)
+					const int pp = (int)rp.x;
+					if (pp >= 0) { p = pp; rp = rec[p]; }   // root->parent = root (src/ER.cpp:424): same p, now done
 				}
 				if (len > 72) { atomicOr(status, ERR_NMS_OVERFLOW); len = 72; }
 				if (len >= 1 + T) {
@@ -246,28 +262,28 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 					double best_s = 0.0;
 					const bool small = (long long)P.W * P.H < (1ll << 24);
 					for (int i = 0; i < len - T; i++) {
-						const int ai = bb_area(&v.bx[4 * chain[i]]), aj = bb_area(&v.bx[4 * chain[i + T]]);
+						const int ai = chain_area[i], aj = chain_area[i + T];
 						int cmp;   // sign of (s_i - s_best)
 						if (small) {
 							const long long n_i = ai, d_i = (long long)aj - ai;
 							if (i == 0) cmp = 1;
 							else if (d_i == 0 || bd == 0) cmp = (d_i == 0 && bd == 0) ? 0 : (d_i == 0 ? 1 : -1);
 							else { const long long l = n_i * bd, r = bn * d_i; cmp = (l > r) - (l < r); }
-							if (cmp > 0 || (cmp == 0 && i > 0 && ai < bb_area(&v.bx[4 * chain[best]]))) { best = i; bn = n_i; bd = d_i; }
+							if (cmp > 0 || (cmp == 0 && i > 0 && ai < chain_area[best])) { best = i; bn = n_i; bd = d_i; }
 						} else {
 							const double sdiv = (double)ai / (double)(aj - ai);
 							if (i == 0) { best = 0; best_s = sdiv; }
 							else if (sdiv > best_s) { best = i; best_s = sdiv; }
-							else if (sdiv == best_s && ai < bb_area(&v.bx[4 * chain[best]])) { best = i; best_s = sdiv; }
+							else if (sdiv == best_s && ai < chain_area[best]) { best = i; best_s = sdiv; }
 						}
 					}
 					const int b = chain[best];
-					const uint16_t *bb = &v.bx[4 * b];
-					const int w = bb[2] - bb[0] + 1, h = bb[3] - bb[1] + 1;
+					const uint4 rb = rec[b];
+					const int w = (int)(rb.w & 0xFFFF) - (int)(rb.z & 0xFFFF) + 1, h = (int)(rb.w >> 16) - (int)(rb.z >> 16) + 1;
 					const double ar = (double)w / (double)h;
 					if (ar < 2.0 && ar > 0.10 && v.area[b] < P.max_area && v.area[b] > P.min_area &&
 					    h < P.H * 0.8 && w < P.W * 0.8) {
-						if (npool < P.pool_cap) v.keyB[npool] = (uint32_t)b;   // keyB is free after the sort
+						if (npool < P.pool_cap) v.newpos[npool] = b;   // newpos is free after the build step
 						else atomicOr(status, ERR_POOL_OVERFLOW);
 						npool++;
 					}
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 			}
 			// next sibling: the following sorted position if it has the same parent
 			const int nx = cur + 1;
-			cur = (nx < n && v.parent[nx] == v.parent[cur] && v.parent[cur] >= 0) ? nx : -1;
+			cur = (nx < n && (int)rc.x >= 0 && (int)rec[nx].x == (int)rc.x) ? nx : -1;
 		}
 		s_npool = min(npool, P.pool_cap);
 	}
@@ -295,7 +311,7 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 		outn[v.pre[j]] = o;
 	}
 	const int npool = s_npool;
-	for (int k = tid; k < npool; k += NT) outp[k] = v.pre[v.keyB[k]];
+	for (int k = tid; k < npool; k += NT) outp[k] = v.pre[v.newpos[k]];
 	if (tid == 0) { out_counts[2 * plane] = n; out_counts[2 * plane + 1] = npool; }
 }
 
