@@ -175,10 +175,12 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		__syncwarp();
 		for (int r = lane; r < rows; r += 32) tma_row_g2s(lvl + r * TW, src + (size_t)r * P.pitch, TW, &bar);
 	}
-	mbar_wait(&bar, 0);
+	if (warp == 0) mbar_wait(&bar, 0);   // one warp polls; the others park at the CTA barrier (no issue slots burnt on polling)
+	__syncthreads();
 
 	ERT_PHASE(0);
 	// ---- phase A: quantise, horizontal same-level runs become chains without atomics ----
+	uint32_t wmin = 255u, wmax = 0u;
 	for (int seg = warp; seg < SEGS; seg += NWARP) {
 		const int p = seg * 32 + lane;
 		const int y = p / TW, x = p % TW;
@@ -193,11 +195,13 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		const bool same = local_union && (lane < 31) && (Lr == L) && (L != 255);
 		const uint32_t bmask = __ballot_sync(0xFFFFFFFFu, !same);
 		const int end = lane + __ffs(bmask >> lane) - 1;
-		__syncwarp();
-		lvl[p] = (uint8_t)L;
+		lvl[p] = (uint8_t)L;   // every lane rewrites only the byte it read itself
 		par[p] = (L == 255 || end == lane) ? KEY_NONE : (((uint32_t)L << 16) | (uint32_t)(seg * 32 + end));
-		const uint32_t lmin = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)L);
-		const uint32_t lmax = __reduce_max_sync(0xFFFFFFFFu, (L == 255) ? 0u : (uint32_t)L);
+		wmin = min(wmin, (uint32_t)L);
+		wmax = max(wmax, (L == 255) ? 0u : (uint32_t)L);
+	}
+	{
+		const uint32_t lmin = __reduce_min_sync(0xFFFFFFFFu, wmin), lmax = __reduce_max_sync(0xFFFFFFFFu, wmax);
 		if (lane == 0) { if (lmin < 255u) atomicMin(&s_minlvl, lmin); atomicMax(&s_maxlvl, lmax); }
 	}
 	__syncthreads();
@@ -310,6 +314,10 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	constexpr uint32_t ACC_NODE = 1u << 15, ACC_MASK = 0x7FFFu, ACC_BORDER = 0x80000000u;
 	{
 		volatile uint32_t *vpar = par;
+		static_assert(SEGS / NWARP <= 8, "a warp keeps the root masks of its segments in registers");
+		uint32_t rootmask[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nroot_w = 0;
+		int jseg = 0;
+#pragma unroll
 		for (int seg = warp; seg < SEGS; seg += NWARP) {
 			const int p = seg * 32 + lane;
 			const int y = p / TW, x = p % TW;
@@ -343,10 +351,19 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 				atomicOr(&ymask[r], 1u << y);
 			}
 			const uint32_t rmask = __ballot_sync(0xFFFFFFFFu, isroot);
-			uint32_t wb = 0;
-			if (lane == 0 && rmask) wb = atomicAdd(&s_nroots, (uint32_t)__popc(rmask));
-			wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
-			if (isroot) rootlist[wb + __popc(rmask & ((1u << lane) - 1u))] = (uint16_t)p;
+			if (jseg < 8) { rootmask[jseg] = rmask; }
+			nroot_w += (uint32_t)__popc(rmask);
+			++jseg;
+		}
+		// one reservation in the root list per warp (order inside the list is irrelevant)
+		uint32_t wb = 0;
+		if (lane == 0 && nroot_w) wb = atomicAdd(&s_nroots, nroot_w);
+		wb = __shfl_sync(0xFFFFFFFFu, wb, 0);
+		jseg = 0;
+		for (int seg = warp; seg < SEGS; seg += NWARP, ++jseg) {
+			const uint32_t rmask = rootmask[jseg];
+			if ((rmask >> lane) & 1u) rootlist[wb + __popc(rmask & ((1u << lane) - 1u))] = (uint16_t)(seg * 32 + lane);
+			wb += (uint32_t)__popc(rmask);
 		}
 	}
 	__syncthreads();
