@@ -45,7 +45,7 @@ typedef struct {
 
 enum { ERT_LABEL_NONE = 0, ERT_LABEL_WEAK = 1, ERT_LABEL_STRONG = 2 };
 enum { ERT_CASCADE_STRONG = 0, ERT_CASCADE_WEAK = 1 };
-enum { ERT_STAGE_EXTRACT = 1, ERT_STAGE_NMS = 2, ERT_STAGE_CLASSIFY = 3 };
+enum { ERT_STAGE_EXTRACT = 1, ERT_STAGE_NMS = 2, ERT_STAGE_CLASSIFY = 3, ERT_STAGE_TRACK = 4 };
 
 /* Result of a batch: n_planes = 6 * n_frames for BGR input (plane order of
  * ERFilter::compute_channels, src/ER.cpp:122-127: Y, Cr, Cb, 255-Y, 255-Cr, 255-Cb), or the
@@ -73,6 +73,55 @@ typedef struct {
 	 * [6] the tile-build kernel alone (the dominant kernel; roofline numerator) [7] rest of extract */
 	double stage_ms[8];
 } ert_result;
+
+/* One strong or weak region as ERFilter::er_track leaves it (src/ER.cpp:536-558): the fields of `struct ER`
+ * (inc/ER.h:42-80) that er_track / calc_color set, plus where the region sits in ert_result. */
+typedef struct {
+	int32_t plane;                 /* er->ch: channel 0..5 inside its frame */
+	int32_t pool_index;            /* position inside the plane's pool range of ert_result (-1: caller-supplied region) */
+	int32_t node;                  /* index inside the plane's node range of ert_result (-1: caller-supplied region) */
+	int32_t label;                 /* ERT_LABEL_STRONG or ERT_LABEL_WEAK */
+	int32_t level, area;           /* er->level, er->area */
+	int32_t x, y, w, h;            /* er->bound */
+	int32_t center_x, center_y;    /* er->center = bound.tl + bound.size / 2 */
+	double color1, color2, color3; /* calc_color (src/ER.cpp:1391-1437); NaN when the OTSU mask is empty (0/0 there too) */
+} ert_tracked;
+
+/* Result of er_track for a batch.  Per frame f:
+ *   cand    [cand_offset[f] .. cand_offset[f+1])   every strong region (strong[0..5], pool order) followed by every
+ *                                                  weak region (weak[0..5]); the first n_strong[f] are the strong ones
+ *   tracked [track_offset[f] .. track_offset[f+1]) `ERs &tracked` (all_er) in the reference's order, as indices
+ *                                                  into the frame's candidate range */
+typedef struct {
+	int32_t n_frames;
+	const int32_t *cand_offset;
+	const int32_t *n_strong;
+	const ert_tracked *cand;
+	const int32_t *track_offset;
+	const int32_t *tracked;
+	double track_ms;               /* device time of the er_track kernels (CUDA events) */
+} ert_track_result;
+
+/* One region handed to OCR::chain_run (src/ER.cpp:732: channel[er->ch](er->bound), er->level*THRESH_STEP, text.slope).
+ * The `thresh` argument of chain_run is not carried: THRESH_OTSU ignores it (src/OCR.cpp:72). */
+typedef struct {
+	int32_t frame;          /* frame inside the context's last batch (ert_ocr_chain_run_batch); ignored by the plane form */
+	int32_t plane;          /* er->ch, channel 0..5 of that frame; ignored by the plane form */
+	int32_t x, y, w, h;     /* er->bound */
+	double slope;           /* Text::slope; |slope| <= 0.01 means no rotation (src/OCR.cpp:73) */
+} ert_ocr_region;
+
+/* Result of a chain_run batch; arrays of n entries, valid until the next OCR call on the context. */
+typedef struct {
+	int32_t n, nr_class;
+	const double *value;    /* chain_run's return value: table[label] + prob_estimates[label] (src/OCR.cpp:139);
+	                           the caller splits it as the reference does: letter = (char)floor(v), prob = v - floor(v) */
+	const int32_t *label;   /* svm_predict_probability's label = index into the reference's table[] (src/OCR.cpp:10) */
+	const double *prob_all; /* n x nr_class probability estimates */
+	const uint8_t *feat;    /* n x 1800 feature bytes (svm_node value = byte / 255; zero = absent node; src/OCR.cpp:203-218) */
+	const uint8_t *img;     /* n x 30 x 30: the image extract_feature received (after OTSU, rotate_mat, ARAN) */
+	double ocr_ms;          /* device time, features + SVM (CUDA events) */
+} ert_ocr_result;
 
 ERT_API int ert_abi_version(void);
 ERT_API const char *ert_last_error(void);
@@ -158,6 +207,30 @@ ERT_API int ert_cascade_classify_u8(ert_ctx *ctx, const uint8_t *hist, int n, in
  * (OCR::extract_feature, src/OCR.cpp:203-218). */
 ERT_API int ert_svm_predict_probability_batch(ert_ctx *ctx, const double *x, int n, double *label, double *prob);
 ERT_API int ert_svm_predict_probability_batch_u8(ert_ctx *ctx, const uint8_t *x, int n, double *label, double *prob);
+
+/* ---- after the detect path ------------------------------------------------------------
+ * ERFilter::er_track(strong, weak, tracked, channel, Ycrcb)  (src/ER.cpp:532-609; called at src/ER.cpp:63 and
+ * src/utils.cpp:140): calc_color + center + ch for every strong / weak region, then the strong-seeded greedy
+ * growth of `tracked`.  Runs on the regions of the batch this context processed last (BGR entry points; the
+ * planes and labels are still on the device).  A batch enqueued with upto = ERT_STAGE_TRACK runs it in the
+ * same stream submission and ert_er_track only collects the result. */
+ERT_API int ert_er_track(ert_ctx *ctx, const ert_track_result **out);
+/* The same on caller-supplied regions of ONE host BGR frame: strong / weak = rows of 6 ints
+ * (ch, x, y, w, h, area), channel-major as classify fills strong[ch] / weak[ch]. */
+ERT_API int ert_er_track_regions(ert_ctx *ctx, const uint8_t *bgr, int width, int height, int stride_bytes, const int32_t *strong,
+                                 int n_strong, const int32_t *weak, int n_weak, const ert_track_result **out);
+
+/* OCR::chain_run(src, thresh, slope) for a batch of regions (src/OCR.cpp:67-140; called from ERFilter::er_ocr,
+ * src/ER.cpp:728-735): threshold(255 - src, OTSU) -> rotate_mat when |slope| > 0.01 -> ARAN(30) -> extract_feature
+ * (findContours chain codes, GaussianBlur, normalize, resize) -> svm_predict_probability.  Needs ert_load_svm.
+ * _batch: regions of the BGR batch this context processed last (planes still on the device; only the region records
+ * travel).  _plane: regions of one caller-supplied single-channel image in host memory. */
+ERT_API int ert_ocr_chain_run_batch(ert_ctx *ctx, const ert_ocr_region *regions, int n, const ert_ocr_result **out);
+ERT_API int ert_ocr_chain_run_plane(ert_ctx *ctx, const uint8_t *plane, int width, int height, int stride_bytes,
+                                    const ert_ocr_region *regions, int n, const ert_ocr_result **out);
+/* OCR::extract_feature path only (no SVM model needed): out->value/label/prob_all are NULL. */
+ERT_API int ert_ocr_features_plane(ert_ctx *ctx, const uint8_t *plane, int width, int height, int stride_bytes,
+                                   const ert_ocr_region *regions, int n, const ert_ocr_result **out);
 
 /* ---- plumbing -------------------------------------------------------------------------------- */
 /* use an external CUDA stream (cudaStream_t as integer, e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */

@@ -18,6 +18,15 @@
 #            416-528 non_maximum_supression, classify
 #            789-845 make_LBP_hist, calc_LBP
 #   OCR.cpp  394-430 OCR::ARAN
+# and for the rows that follow the detect path (checked by tests/test_*next*.py):
+#   ER.cpp   532-609   ERFilter::er_track
+#            1391-1437 calc_color
+#   OCR.cpp  4-15      enum category, table[], cat[]
+#            18-21     OCR::OCR(model, img_L, feature_L)
+#            67-140    OCR::chain_run
+#            144-250   OCR::extract_feature
+#            254-360   OCR::rotate_mat
+#            602-622   OCR::chain_code_direction
 set -euo pipefail
 REF="${ERT_REFERENCE_DIR:-/root/reference}"
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -29,11 +38,11 @@ fi
 mkdir -p "$OUT"
 {
 	echo '#include "ER.h"'
-	sed -n '6,10p;14,30p;131,233p;240,413p;416,528p;789,845p' "$REF/src/ER.cpp"
-	sed -n '394,430p' "$REF/src/OCR.cpp"
+	sed -n '6,10p;14,30p;131,233p;240,413p;416,528p;532,609p;789,845p;1391,1437p' "$REF/src/ER.cpp"
+	sed -n '4,15p;18,21p;67,140p;144,250p;254,360p;394,430p;602,622p' "$REF/src/OCR.cpp"
 } > "$OUT/ref_hotpath.cpp"
 g++ -std=c++11 -O2 -fopenmp -fPIC -shared -w \
 	-I "$HERE/cvshim" -I "$REF/inc" \
-	"$OUT/ref_hotpath.cpp" "$REF/src/adaboost.cpp" "$REF/src/svm.cpp" "$HERE/ref_capi.cpp" \
+	"$OUT/ref_hotpath.cpp" "$REF/src/adaboost.cpp" "$REF/src/svm.cpp" "$HERE/ref_capi.cpp" "$HERE/ref_capi_next.cpp" \
 	-o "$OUT/libref_oracle.so"
 echo "built $OUT/libref_oracle.so"

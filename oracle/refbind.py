@@ -72,6 +72,17 @@ class RefOracle:
         L.ref_detect_frames.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _f64p]
         L.ref_channels.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
         L.ref_destroy.argtypes = [C.c_void_p]
+        # rows after the detect path (oracle/ref_capi_next.cpp)
+        L.ref_prim_threshold_otsu.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
+        L.ref_prim_find_contours.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int]
+        L.ref_prim_gaussian7.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
+        L.ref_prim_normalize_minmax.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
+        L.ref_calc_color.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _i32p, C.c_int, _f64p]
+        L.ref_er_track.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _i32p, _f64p, _f64p, _i32p, _i32p]
+        L.ref_chain_run.restype = C.c_double
+        L.ref_chain_run.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.ref_ocr_features.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_double, _u8p, _u8p]
+        L.ref_rotate_mat.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _u8p, C.c_int]
         svm = svm_model_path().encode() if with_svm else None
         self.ctx = L.ref_create(p["thresh_step"], p["min_area"], p["max_area"], p["stability_t"], p["overlap_coef"],
                                 os.path.join(ASSETS, "strong.classifier").encode(),
@@ -154,6 +165,92 @@ class RefOracle:
         label = np.zeros(n, np.float64); prob = np.zeros((n, k), np.float64)
         self.L.ref_svm_predict_probability(self.ctx, _p(x, _f64p), n, d, nthreads, _p(label, _f64p), _p(prob, _f64p))
         return label, prob
+
+    # -- rows after the detect path: er_track / OCR::chain_run ---------------------------------
+    def prim_threshold_otsu(self, img):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        out = np.zeros_like(img)
+        t = self.L.ref_prim_threshold_otsu(_p(img, _u8p), w, h, w, _p(out, _u8p))
+        return t, out
+
+    def prim_find_contours(self, img):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        cap = 8 * h * w + 16
+        pts = np.zeros((cap, 2), np.int32); sizes = np.zeros(h * w + 4, np.int32)
+        n = self.L.ref_prim_find_contours(_p(img, _u8p), w, h, w, _p(pts, _i32p), cap, _p(sizes, _i32p), sizes.size)
+        out, o = [], 0
+        for k in range(n):
+            out.append(pts[o:o + sizes[k]].copy()); o += sizes[k]
+        return out
+
+    def prim_gaussian7(self, img):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        out = np.zeros_like(img)
+        self.L.ref_prim_gaussian7(_p(img, _u8p), w, h, w, _p(out, _u8p))
+        return out
+
+    def prim_normalize_minmax(self, img):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        out = np.zeros_like(img)
+        self.L.ref_prim_normalize_minmax(_p(img, _u8p), w, h, w, _p(out, _u8p))
+        return out
+
+    def calc_color(self, plane, ycrcb, rects):
+        """calc_color (src/ER.cpp:1391-1437): plane [H,W] u8 (the ER's channel), ycrcb [H,W,3], rects [n,4] -> [n,3] f64."""
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        ycrcb = np.ascontiguousarray(ycrcb, dtype=np.uint8)
+        rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+        h, w = plane.shape
+        out = np.zeros((len(rects), 3), np.float64)
+        self.L.ref_calc_color(_p(plane, _u8p), _p(ycrcb, _u8p), w, h, _p(rects, _i32p), len(rects), _p(out, _f64p))
+        return out
+
+    def er_track(self, planes6, ycrcb, strong, weak):
+        """ERFilter::er_track (src/ER.cpp:532-609).  strong / weak = [n,6] rows (ch,x,y,w,h,area), channel-major.
+        Returns dict(tracked [m,2] = (kind 0 strong / 1 weak, row), strong_color, weak_color, strong_center, weak_center)."""
+        planes6 = np.ascontiguousarray(planes6, dtype=np.uint8)
+        ycrcb = np.ascontiguousarray(ycrcb, dtype=np.uint8)
+        strong = np.ascontiguousarray(strong, dtype=np.int32).reshape(-1, 6)
+        weak = np.ascontiguousarray(weak, dtype=np.int32).reshape(-1, 6)
+        _, h, w = planes6.shape
+        ns, nw = len(strong), len(weak)
+        tr = np.zeros((ns + nw + 1, 2), np.int32)
+        sc = np.zeros((ns + 1, 3)); wc = np.zeros((nw + 1, 3))
+        sce = np.zeros((ns + 1, 2), np.int32); wce = np.zeros((nw + 1, 2), np.int32)
+        m = self.L.ref_er_track(self.ctx, _p(planes6, _u8p), _p(ycrcb, _u8p), w, h, _p(strong, _i32p), ns, _p(weak, _i32p), nw,
+                                _p(tr, _i32p), _p(sc, _f64p), _p(wc, _f64p), _p(sce, _i32p), _p(wce, _i32p))
+        return dict(tracked=tr[:m].copy(), strong_color=sc[:ns], weak_color=wc[:nw], strong_center=sce[:ns], weak_center=wce[:nw])
+
+    def chain_run(self, crop, thresh=0, slope=0.0):
+        """OCR::chain_run verbatim (src/OCR.cpp:67-140): returns table[label] + prob[label]."""
+        crop = np.ascontiguousarray(crop, dtype=np.uint8)
+        h, w = crop.shape
+        return self.L.ref_chain_run(self.ctx, _p(crop, _u8p), w, h, w, thresh, slope)
+
+    def ocr_features(self, crop, slope=0.0):
+        """chain_run's pre-processing + extract_feature: (30x30 image, 1800 feature bytes = value*255)."""
+        crop = np.ascontiguousarray(crop, dtype=np.uint8)
+        h, w = crop.shape
+        img = np.zeros((30, 30), np.uint8); feat = np.zeros(1800, np.uint8)
+        n = self.L.ref_ocr_features(self.ctx, _p(crop, _u8p), w, h, w, slope, _p(img, _u8p), _p(feat, _u8p))
+        if n < 0:
+            raise ValueError("empty image after rotation")
+        return img, feat
+
+    def rotate_mat(self, img, rad, crop=True):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        cap = 16 * (h + w + 4) * (h + w + 4)
+        out = np.zeros(cap, np.uint8)
+        r = self.L.ref_rotate_mat(self.ctx, _p(img, _u8p), w, h, w, rad, 1 if crop else 0, _p(out, _u8p), cap)
+        if r < 0:
+            raise ValueError("rotate_mat output too large")
+        rows, cols = r >> 16, r & 0xffff
+        return out[:rows * cols].reshape(rows, cols).copy()
 
     def detect_frames(self, bgr, mode=1, nthreads=1):
         """bgr [F,H,W,3] -> (wall seconds, counts[F,4]=kept,pool,strong,weak, stage seconds[3])."""

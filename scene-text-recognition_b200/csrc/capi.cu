@@ -60,110 +60,11 @@ __global__ void k_compact_results(int n_planes, int node_cap, int pool_cap, cons
 	}
 }
 
-// ---------------------------------------------------------------------------------------------
-// host-side model tables
-// ---------------------------------------------------------------------------------------------
-struct CascadeHost {
-	std::vector<int> stage_len, stage_thr;
-	std::vector<Stump> stumps;
-	bool loaded = false;
-	Stump *d_stumps = nullptr;
-	int *d_len = nullptr, *d_thr = nullptr;
-	CascadeDev dev() const { CascadeDev c; c.stumps = d_stumps; c.stage_len = d_len; c.stage_thr = d_thr; c.n_stages = (int)stage_len.size(); return c; }
-};
-
-struct SvmHost {
-	bool loaded = false;
-	int nr_class = 0, l = 0, dims = 0;
-	double gamma = 0;
-	std::vector<double> rho, probA, probB, coef, sv;
-	std::vector<int> label, nsv, start;
-	double *d_sv = nullptr, *d_coef = nullptr, *d_rho = nullptr, *d_probA = nullptr, *d_probB = nullptr;
-	int *d_label = nullptr, *d_nsv = nullptr, *d_start = nullptr;
-	std::vector<uint8_t> svj; std::vector<int8_t> sve; std::vector<double> ss;
-	uint8_t *d_svj = nullptr; int8_t *d_sve = nullptr; double *d_ss = nullptr;
-	double inv_s255 = 0;
-	bool use_tc = true;
-	SvmDev dev() const
-	{
-		SvmDev m; m.nr_class = nr_class; m.l = l; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef;
-		m.rho = d_rho; m.probA = d_probA; m.probB = d_probB; m.label = d_label; m.nsv = d_nsv; m.start = d_start;
-		m.svj = use_tc ? d_svj : nullptr; m.sve = d_sve; m.ss = d_ss; m.inv_s255 = inv_s255;
-		return m;
-	}
-};
-
-template <typename T>
-static int dev_upload(T **dptr, const std::vector<T> &v)
-{
-	if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
-	if (v.empty()) return 0;
-	ERT_CUDA_CHECK(cudaMalloc((void **)dptr, sizeof(T) * v.size()));
-	ERT_CUDA_CHECK(cudaMemcpy(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
-	return 0;
-}
-
-struct Scratch {
-	void *p = nullptr;
-	size_t cap = 0;
-	int ensure(size_t bytes)
-	{
-		if (bytes <= cap) return 0;
-		if (p) cudaFree(p);
-		p = nullptr; cap = 0;
-		ERT_CUDA_CHECK(cudaMalloc(&p, bytes));
-		cap = bytes;
-		return 0;
-	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
 } // namespace ert
 
+#include "ctx.h"
+
 using namespace ert;
-
-struct ert_ctx {
-	ert_params prm;
-	int device = 0;
-	cudaStream_t stream = nullptr;
-	bool own_stream = true;
-	cudaEvent_t ev[12];
-	int local_union = 1;
-	int tile_cfg = 0;
-	int return_hist = 0;
-	int kept_cap = 16384, pool_cap = 2048;
-	int launches = 0;
-
-	CascadeHost casc[2];
-	SvmHost svm;
-	uint8_t aran_tbl_h[64];
-	uint8_t *d_aran_tbl = nullptr;
-	unsigned long long *d_prof = nullptr;
-
-	// workspace geometry
-	int W = 0, H = 0, pitch = 0, planes_cap = 0, frames_cap = 0;
-	uint8_t *d_bgr = nullptr; size_t bgr_cap = 0;
-	uint8_t *d_ycc = nullptr;          // frames_cap*3 planes (BGR mode) or planes_cap planes (plane mode)
-	size_t ycc_bytes = 0;
-	PlaneSrc *d_planes = nullptr;
-	ExtractWork wk{};
-	uint8_t *d_nms_scratch = nullptr; size_t nms_stride = 0;
-	OutNode *d_out_nodes = nullptr;
-	int32_t *d_out_pool = nullptr, *d_out_counts = nullptr, *d_label = nullptr;
-	double *d_ss = nullptr, *d_ws = nullptr;
-	uint8_t *d_hist = nullptr;
-	// host-mapped result buffers
-	int32_t *h_node_off = nullptr, *h_pool_off = nullptr, *h_pool = nullptr, *h_label = nullptr;
-	OutNode *h_nodes = nullptr;
-	double *h_ss = nullptr, *h_ws = nullptr;
-	uint8_t *h_hist = nullptr;
-	uint32_t *h_status = nullptr;
-	ert_result res{};
-	int pending_planes = 0, pending_upto = 0;
-	bool pending = false;
-
-	Scratch s0, s1, s2, s3, s4;
-};
 
 namespace {
 
@@ -308,6 +209,11 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->wk.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[5], st));
 	c->pending = true; c->pending_planes = n_planes; c->pending_upto = upto;
+	c->track_pending = false;
+	if (upto >= ERT_STAGE_TRACK) {
+		if (c->frames_cap != -1) { set_error("ERT_STAGE_TRACK needs a BGR batch (er_track reads the YCrCb frame)"); return -1; }
+		if (enqueue_track(c, n_planes / 6)) return -1;
+	}
 	return 0;
 }
 
@@ -408,6 +314,7 @@ void ert_destroy(ert_ctx *c)
 	cudaFree(c->svm.d_label); cudaFree(c->svm.d_nsv); cudaFree(c->svm.d_start);
 	cudaFree(c->svm.d_svj); cudaFree(c->svm.d_sve); cudaFree(c->svm.d_ss);
 	c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
+	free_next(c);
 	for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;

@@ -1,6 +1,7 @@
 // kernels.h -- host-side launchers of the sm_100a kernels (internal to libertext.so)
 #pragma once
 #include "common.cuh"
+#include "../../include/ertext.h"
 
 namespace ert {
 
@@ -55,6 +56,38 @@ struct SvmDev {
 	const double *ss;
 	double inv_s255;        // 1 / (255 * S)
 };
+
+// er_track (er_track.cu): per-frame candidate lists (strong then weak), colours, tracked order
+struct TrackWork {
+	ert_tracked *cand;      // [frames][cand_cap]
+	int32_t *n_cand;        // [frames]
+	int32_t *n_strong;      // [frames]
+	int32_t *tracked;       // [frames][cand_cap] indices into the frame's candidates, all_er order
+	int32_t *n_tracked;     // [frames]
+	int cand_cap;
+};
+
+int launch_track_gather(TrackWork &tk, int n_frames, const OutNode *nodes, const int32_t *pool, const int32_t *counts, const int32_t *label,
+                        int node_cap, int pool_cap, cudaStream_t st);
+int launch_calc_color(TrackWork &tk, int n_frames, const uint8_t *d_ycc, size_t plane_bytes, int pitch, cudaStream_t st);
+int launch_track(TrackWork &tk, int n_frames, ert_tracked *h_cand, int32_t *h_cand_off, int32_t *h_nstrong, int32_t *h_track_off,
+                 int32_t *h_tracked, cudaStream_t st);
+
+// OCR::chain_run pre-processing + extract_feature (ocr_feat.cu).  Everything that depends on libm (atan2 / cos / sin /
+// tan / pow) is evaluated by the host with the C library the reference uses and shipped in the job record.
+struct OcrJob {
+	const uint8_t *src;     // channel plane (device), row pitch below
+	int pitch, invert;      // invert: channel value = 255 - src
+	int x0, y0, w, h;       // er->bound inside the plane
+	int rot;                // 0: no rotation (|slope| <= 0.01); 1: OCR::rotate_mat(crop = true); 2: its crop = false fallback
+	double cs, sn;          // cos(rad), sin(rad), rad = atan2(slope, 1)
+	int cx, cy;             // rotate_mat's x0, y0
+	int min_x, min_y, crop_h;
+	int sw, sh;             // size of the image that enters ARAN (the crop, or the rotated image)
+	int dw, dh, offx, offy; // ARAN: resize target and paste offset inside the 30x30 image
+};
+
+int launch_ocr_features(const OcrJob *d_jobs, int n, uint8_t *d_feat1800, uint8_t *d_img30, cudaStream_t st);
 
 int extract_pitch(int W);
 int tile_config_count();

@@ -13,7 +13,7 @@ REPO_ROOT = os.path.dirname(PKG_ROOT)
 LIB_PATH = os.path.join(PKG_ROOT, "libertext.so")
 ASSETS = os.path.join(REPO_ROOT, "assets", "classifier")
 
-STAGE_EXTRACT, STAGE_NMS, STAGE_CLASSIFY = 1, 2, 3
+STAGE_EXTRACT, STAGE_NMS, STAGE_CLASSIFY, STAGE_TRACK = 1, 2, 3, 4
 LABEL_NONE, LABEL_WEAK, LABEL_STRONG = 0, 1, 2
 NEG_DBL_MAX = -1.7976931348623157e308
 
@@ -34,7 +34,55 @@ class ErtResult(C.Structure):
                 ("pool_hist", _u8p), ("status", C.c_uint32), ("stage_ms", C.c_double * 8)]
 
 
+class ErtTracked(C.Structure):
+    _fields_ = [("plane", C.c_int32), ("pool_index", C.c_int32), ("node", C.c_int32), ("label", C.c_int32), ("level", C.c_int32),
+                ("area", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("center_x", C.c_int32), ("center_y", C.c_int32), ("color1", C.c_double), ("color2", C.c_double), ("color3", C.c_double)]
+
+
+TRACKED_DTYPE = np.dtype([("plane", "<i4"), ("pool_index", "<i4"), ("node", "<i4"), ("label", "<i4"), ("level", "<i4"), ("area", "<i4"),
+                          ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("center_x", "<i4"), ("center_y", "<i4"),
+                          ("color1", "<f8"), ("color2", "<f8"), ("color3", "<f8")])
+assert TRACKED_DTYPE.itemsize == C.sizeof(ErtTracked) == 72
+
+
+class ErtTrackResult(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("cand_offset", _i32p), ("n_strong", _i32p), ("cand", C.POINTER(ErtTracked)),
+                ("track_offset", _i32p), ("tracked", _i32p), ("track_ms", C.c_double)]
+
+
+class ErtOcrRegion(C.Structure):
+    _fields_ = [("frame", C.c_int32), ("plane", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("slope", C.c_double)]
+
+
+OCR_REGION_DTYPE = np.dtype([("frame", "<i4"), ("plane", "<i4"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("slope", "<f8")])
+assert OCR_REGION_DTYPE.itemsize == C.sizeof(ErtOcrRegion) == 32
+
+
+class ErtOcrResult(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nr_class", C.c_int32), ("value", _f64p), ("label", _i32p), ("prob_all", _f64p), ("feat", _u8p),
+                ("img", _u8p), ("ocr_ms", C.c_double)]
+
+
+class FrameTrack:
+    """er_track of one frame: cand = structured array (TRACKED_DTYPE) of every strong then every weak region,
+    n_strong, tracked = indices into cand in the reference's all_er order."""
+    __slots__ = ("cand", "n_strong", "tracked")
+
+    def __init__(self, cand, n_strong, tracked):
+        self.cand, self.n_strong, self.tracked = cand, n_strong, tracked
+
+
+class OcrResult:
+    __slots__ = ("value", "label", "prob", "feat", "img", "ocr_ms")
+
+    def __init__(self, value, label, prob, feat, img, ms):
+        self.value, self.label, self.prob, self.feat, self.img, self.ocr_ms = value, label, prob, feat, img, ms
+
+
 EXPORTS = [
+    "ert_er_track", "ert_er_track_regions", "ert_ocr_chain_run_batch", "ert_ocr_chain_run_plane", "ert_ocr_features_plane",
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
     "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
     "ert_load_svm", "ert_svm_nr_class", "ert_set_svm_tensor_cores", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
@@ -90,6 +138,13 @@ def load_library():
     L.ert_last_launch_count.argtypes = [C.c_void_p]
     L.ert_bench_cascade_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _f64p]
     L.ert_bench_svm_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _f64p]
+    TP = C.POINTER(C.POINTER(ErtTrackResult))
+    L.ert_er_track.argtypes = [C.c_void_p, TP]
+    L.ert_er_track_regions.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, TP]
+    OP = C.POINTER(C.POINTER(ErtOcrResult))
+    L.ert_ocr_chain_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, OP]
+    L.ert_ocr_chain_run_plane.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, OP]
+    L.ert_ocr_features_plane.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, OP]
     _lib = L
     return L
 
@@ -322,6 +377,90 @@ class ErText:
             label = np.zeros(n); prob = np.zeros((n, k))
             self._check(self.L.ert_svm_predict_probability_batch(self.ctx, _ptr(x, _f64p), n, _ptr(label, _f64p), _ptr(prob, _f64p)))
         return label, prob
+
+    # ---- after the detect path: er_track, OCR::chain_run ---------------------------------------
+    def _unpack_track(self, tp):
+        r = tp.contents
+        F = r.n_frames
+        coff = np.ctypeslib.as_array(r.cand_offset, (F + 1,)).copy()
+        toff = np.ctypeslib.as_array(r.track_offset, (F + 1,)).copy()
+        ns = np.ctypeslib.as_array(r.n_strong, (F,)).copy()
+        nc, nt = int(coff[-1]), int(toff[-1])
+        if nc:
+            raw = np.ctypeslib.as_array(C.cast(r.cand, _u8p), (nc * 72,)).copy()
+            cand = raw.view(TRACKED_DTYPE)
+        else:
+            cand = np.zeros(0, TRACKED_DTYPE)
+        tracked = np.ctypeslib.as_array(r.tracked, (nt,)).copy() if nt else np.zeros(0, np.int32)
+        out = [FrameTrack(cand[coff[f]:coff[f + 1]], int(ns[f]), tracked[toff[f]:toff[f + 1]]) for f in range(F)]
+        return out, r.track_ms
+
+    def er_track(self):
+        """ERFilter::er_track on the BGR batch this context processed last -> ([FrameTrack per frame], device ms)."""
+        tp = C.POINTER(ErtTrackResult)()
+        self._check(self.L.ert_er_track(self.ctx, C.byref(tp)))
+        return self._unpack_track(tp)
+
+    def er_track_regions(self, bgr, strong, weak):
+        """er_track on caller regions of one BGR frame; strong / weak = [n,6] rows (ch, x, y, w, h, area), channel-major."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        strong = np.ascontiguousarray(strong, dtype=np.int32).reshape(-1, 6)
+        weak = np.ascontiguousarray(weak, dtype=np.int32).reshape(-1, 6)
+        h, w, _ = bgr.shape
+        tp = C.POINTER(ErtTrackResult)()
+        self._check(self.L.ert_er_track_regions(self.ctx, _ptr(bgr, _u8p), w, h, w * 3, _ptr(strong, _i32p), len(strong),
+                                                _ptr(weak, _i32p), len(weak), C.byref(tp)))
+        return self._unpack_track(tp)[0][0]
+
+    @staticmethod
+    def _regions(rects, slopes=None, frames=None, planes=None):
+        rects = np.asarray(rects, dtype=np.int32).reshape(-1, 4)
+        reg = np.zeros(len(rects), OCR_REGION_DTYPE)
+        reg["x"], reg["y"], reg["w"], reg["h"] = rects[:, 0], rects[:, 1], rects[:, 2], rects[:, 3]
+        if slopes is not None:
+            reg["slope"] = slopes
+        if frames is not None:
+            reg["frame"] = frames
+        if planes is not None:
+            reg["plane"] = planes
+        return reg
+
+    def _unpack_ocr(self, op):
+        r = op.contents
+        n, k = r.n, r.nr_class
+        feat = np.ctypeslib.as_array(r.feat, (n * 1800,)).reshape(n, 1800).copy() if n else np.zeros((0, 1800), np.uint8)
+        img = np.ctypeslib.as_array(r.img, (n * 900,)).reshape(n, 30, 30).copy() if n else np.zeros((0, 30, 30), np.uint8)
+        if n and r.value:
+            value = np.ctypeslib.as_array(r.value, (n,)).copy()
+            label = np.ctypeslib.as_array(r.label, (n,)).copy()
+            prob = np.ctypeslib.as_array(r.prob_all, (n * k,)).reshape(n, k).copy()
+        else:
+            value = label = prob = None
+        return OcrResult(value, label, prob, feat, img, r.ocr_ms)
+
+    def ocr_chain_run_plane(self, plane, rects, slopes=None):
+        """OCR::chain_run on regions of one single-channel image: rects [n,4] (x,y,w,h), slopes [n] or None."""
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        h, w = plane.shape
+        reg = self._regions(rects, slopes)
+        op = C.POINTER(ErtOcrResult)()
+        self._check(self.L.ert_ocr_chain_run_plane(self.ctx, _ptr(plane, _u8p), w, h, w, reg.ctypes.data, len(reg), C.byref(op)))
+        return self._unpack_ocr(op)
+
+    def ocr_features_plane(self, plane, rects, slopes=None):
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        h, w = plane.shape
+        reg = self._regions(rects, slopes)
+        op = C.POINTER(ErtOcrResult)()
+        self._check(self.L.ert_ocr_features_plane(self.ctx, _ptr(plane, _u8p), w, h, w, reg.ctypes.data, len(reg), C.byref(op)))
+        return self._unpack_ocr(op)
+
+    def ocr_chain_run_batch(self, frames, planes, rects, slopes=None):
+        """chain_run on regions of the last BGR batch (device-resident planes): frames [n], planes [n] (channel 0..5), rects [n,4]."""
+        reg = self._regions(rects, slopes, frames, planes)
+        op = C.POINTER(ErtOcrResult)()
+        self._check(self.L.ert_ocr_chain_run_batch(self.ctx, reg.ctypes.data, len(reg), C.byref(op)))
+        return self._unpack_ocr(op)
 
     def set_svm_tensor_cores(self, on):
         self._check(self.L.ert_set_svm_tensor_cores(self.ctx, int(on)))

@@ -1,0 +1,165 @@
+"""GPU parity for the rows after the detect path: ERFilter::er_track + calc_color and OCR::chain_run
+(pre-processing, extract_feature, SVM), through the C ABI, against the committed golden vectors (produced by the
+reference's own code) and, where oracle/_ref is present, against that code live."""
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TABLE = "0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz&()"
+
+
+@pytest.fixture(scope="module")
+def golden_next():
+    return np.load(os.path.join(GOLDEN, "ref_next.npz"))
+
+
+def _rows(ft, lo, hi):
+    c = ft.cand[lo:hi]
+    return np.stack([c["plane"], c["x"], c["y"], c["w"], c["h"], c["area"]], axis=1).astype(np.int32).reshape(-1, 6)
+
+
+def _check_track(ft, exp, tag):
+    ns = ft.n_strong
+    S, Wk = _rows(ft, 0, ns), _rows(ft, ns, len(ft.cand))
+    assert (S == exp["strong"]).all() and (Wk == exp["weak"]).all(), tag
+    col = np.stack([ft.cand["color1"], ft.cand["color2"], ft.cand["color3"]], axis=1).reshape(-1, 3)
+    assert np.array_equal(col[:ns], exp["strong_color"], equal_nan=True), tag       # bit-exact doubles
+    assert np.array_equal(col[ns:], exp["weak_color"], equal_nan=True), tag
+    cen = np.stack([ft.cand["center_x"], ft.cand["center_y"]], axis=1).reshape(-1, 2)
+    assert (cen[:ns] == exp["strong_center"]).all() and (cen[ns:] == exp["weak_center"]).all(), tag
+    want = np.array([idx if kind == 0 else ns + idx for kind, idx in exp["tracked"]], np.int32)
+    assert len(ft.tracked) == len(want) and (ft.tracked == want).all(), tag           # same regions, same order
+
+
+def _gold(g, tag):
+    return {k: g["%s_%s" % (tag, k)] for k in ("strong", "weak", "tracked", "strong_color", "weak_color", "strong_center", "weak_center")}
+
+
+def test_er_track_batch_matches_golden(ert, golden_frames, golden_next):
+    """detect_classify on the golden frames, then er_track on the device-resident batch == the reference's er_track."""
+    import ertext
+    res = ert.detect_classify(golden_frames)
+    assert res.status == 0
+    tracks, ms = ert.er_track()
+    assert len(tracks) == 3 and ms > 0
+    for f in range(3):
+        _check_track(tracks[f], _gold(golden_next, "f%d" % f), "f%d" % f)
+        # cand rows point back into the batch result
+        for c in tracks[f].cand:
+            pl = res.planes[f * 6 + c["plane"]]
+            assert pl.pool[c["pool_index"]] == c["node"] and pl.label[c["pool_index"]] == c["label"]
+            assert tuple(pl.nodes[c["node"]][:6]) == (c["level"], c["area"], c["x"], c["y"], c["w"], c["h"])
+    # the same in one stream submission (upto = ERT_STAGE_TRACK)
+    res2 = ert.detect_classify(golden_frames, upto=ertext.STAGE_TRACK)
+    tracks2, _ = ert.er_track()
+    for f in range(3):
+        _check_track(tracks2[f], _gold(golden_next, "f%d" % f), "f%d/fused" % f)
+
+
+def test_er_track_regions_matches_golden(ert, golden_frames, golden_next):
+    for c in range(6):
+        ft = ert.er_track_regions(golden_frames[1], golden_next["s%d_strong" % c], golden_next["s%d_weak" % c])
+        _check_track(ft, _gold(golden_next, "s%d" % c), "s%d" % c)
+
+
+def test_er_track_live_random_and_nan(ert, ref):
+    """seeded frames and region lists (incl. saturated planes whose OTSU mask is empty -> NaN colours) vs the reference live"""
+    rng = np.random.RandomState(5)
+    H, W = 240, 320
+    for t in range(6):
+        if t == 0:
+            bgr = np.full((H, W, 3), 255, np.uint8)          # Y = 255: empty mask on channel 0, full mask on channel 3
+        elif t == 1:
+            bgr = np.zeros((H, W, 3), np.uint8)
+        else:
+            base = rng.randint(0, 256, (H // 8, W // 8, 3)).astype(np.uint8)
+            bgr = np.kron(base, np.ones((8, 8, 1), np.uint8)) + rng.randint(0, 12, (H, W, 3)).astype(np.uint8)
+            bgr = np.ascontiguousarray(bgr.astype(np.uint8))
+        def boxes(n):
+            out = []
+            for _ in range(n):
+                w, h = rng.randint(1, 60), rng.randint(1, 80)
+                out.append((rng.randint(0, 6), rng.randint(0, W - w + 1), rng.randint(0, H - h + 1), w, h, rng.randint(121, 4000)))
+            out.sort(key=lambda r: r[0])
+            return np.array(out, np.int32).reshape(-1, 6)
+        S, Wk = boxes(rng.randint(0, 30)), boxes(rng.randint(0, 90))
+        ch = ref.channels(bgr)
+        exp = ref.er_track(ch, np.stack([ch[0], ch[1], ch[2]], axis=-1), S, Wk)
+        exp.update(strong=S, weak=Wk)
+        _check_track(ert.er_track_regions(bgr, S, Wk), exp, "live%d" % t)
+
+
+def test_ocr_features_match_golden(ert, port, golden_frames, golden_next):
+    g = golden_next
+    chans = [port.channels(golden_frames[f]) for f in range(3)]
+    rows = g["ocr_rows"]
+    for f in range(3):
+        for k in range(6):
+            sel = np.where((rows[:, 0] == f) & (rows[:, 1] == k))[0]
+            if not len(sel):
+                continue
+            r = ert.ocr_features_plane(chans[f][k], rows[sel][:, 2:6], g["ocr_slope"][sel])
+            assert (r.img == g["ocr_img"][sel]).all(), (f, k)
+            assert (r.feat == g["ocr_feat"][sel]).all(), (f, k)        # bit-exact feature bytes
+
+
+def test_ocr_chain_run_matches_golden(ert, port, golden_frames, golden_next):
+    g = golden_next
+    rows = g["ocr_rows"]
+    # device-resident batch form: regions address (frame, channel) of the batch processed last
+    ert.detect_classify(golden_frames)
+    r = ert.ocr_chain_run_batch(rows[:, 0], rows[:, 1], rows[:, 2:6], g["ocr_slope"])
+    assert (r.feat == g["ocr_feat"]).all()
+    v = g["ocr_value"]
+    assert (np.floor(r.value) == np.floor(v)).all()                   # er->letter
+    assert np.allclose(r.value - np.floor(r.value), v - np.floor(v), rtol=1e-4, atol=1e-9)      # er->prob, 1e-4 relative
+    assert [TABLE[l] for l in r.label] == [chr(int(x)) for x in np.floor(v)]
+    assert np.allclose(r.prob.sum(axis=1), 1.0, atol=1e-9)
+    # plane form gives the same numbers
+    chans = port.channels(golden_frames[1])
+    sel = np.where((rows[:, 0] == 1) & (rows[:, 1] == 0))[0]
+    rp = ert.ocr_chain_run_plane(chans[0], rows[sel][:, 2:6], g["ocr_slope"][sel])
+    assert (rp.value == r.value[sel]).all() and (rp.feat == r.feat[sel]).all()
+
+
+def test_ocr_features_live_random(ert, ref):
+    """seeded planes, ragged rectangles (1-pixel sides, exact-2x sizes, full plane) and slopes vs the reference live"""
+    rng = np.random.RandomState(9)
+    H, W = 200, 260
+    base = rng.randint(0, 256, (H // 10, W // 10)).astype(np.uint8)
+    plane = np.kron(base, np.ones((10, 10), np.uint8))
+    plane = np.clip(plane.astype(int) + rng.randint(-10, 10, (H, W)), 0, 255).astype(np.uint8)
+    rects, slopes = [], []
+    for t in range(120):
+        w, h = rng.randint(2, 120), rng.randint(2, 120)
+        if t % 10 == 0:
+            w = h = 2 * rng.randint(8, 31)
+        if t % 17 == 0:
+            w, h = W, H
+        rects.append((rng.randint(0, W - w + 1), rng.randint(0, H - h + 1), w, h))
+        slopes.append(0.0 if t % 3 == 0 else float(rng.uniform(-1.2, 1.2)))
+    keep_r, keep_s, exp_img, exp_feat = [], [], [], []
+    for (x, y, w, h), sl in zip(rects, slopes):
+        try:
+            img, feat = ref.ocr_features(plane[y:y + h, x:x + w], sl)
+        except Exception:
+            continue
+        keep_r.append((x, y, w, h)); keep_s.append(sl); exp_img.append(img); exp_feat.append(feat)
+    assert len(keep_r) > 60
+    r = ert.ocr_features_plane(plane, np.array(keep_r, np.int32), np.array(keep_s))
+    bad = [i for i in range(len(keep_r)) if not ((r.img[i] == exp_img[i]).all() and (r.feat[i] == exp_feat[i]).all())]
+    assert not bad, [(keep_r[i], keep_s[i]) for i in bad[:5]]
+
+
+def test_ocr_rejects_bad_regions(ert, golden_frames, port):
+    import ertext
+    plane = port.channels(golden_frames[0])[0]
+    with pytest.raises(ertext.ErtError):
+        ert.ocr_features_plane(plane, [(630, 470, 20, 20)])           # outside the plane
+    with pytest.raises(ertext.ErtError):
+        ert.ocr_features_plane(plane, [(0, 0, 640, 1)])               # ARAN collapses (cv::resize would throw in the reference)
+    r = ert.ocr_features_plane(plane, np.zeros((0, 4), np.int32))     # empty batch
+    assert r.feat.shape == (0, 1800)
