@@ -240,6 +240,7 @@ int ert_er_track_regions(ert_ctx *c, const uint8_t *bgr, int W, int H, int strid
 			set_error("region %d: channel or rectangle outside the frame", i);
 			return -1;
 		}
+		if (i != 0 && i != ns && r[0] < r[-6]) { set_error("region %d: rows must be channel-major (strong[0..5], weak[0..5])", i); return -1; }
 		ert_tracked &t = hc[i];
 		t.plane = r[0]; t.pool_index = -1; t.node = -1; t.label = i < ns ? ERT_LABEL_STRONG : ERT_LABEL_WEAK; t.level = 0; t.area = r[5];
 		t.x = r[1]; t.y = r[2]; t.w = r[3]; t.h = r[4];

@@ -36,6 +36,9 @@ def frame_lists(ref, ch):
 def synth_lists(rng, case, W, H):
     """Region lists that stress the greedy growth: clusters of similar boxes so that chains of matches form."""
     def boxes(n, cx, cy, s):
+        return sorted(boxes_(n, cx, cy, s), key=lambda r: r[0])       # channel-major like classify's output (stable)
+
+    def boxes_(n, cx, cy, s):
         out = []
         for _ in range(n):
             w = int(np.clip(rng.normal(s, s * 0.25), 4, W // 2)); h = int(np.clip(rng.normal(s * 1.3, s * 0.3), 4, H // 2))
@@ -50,7 +53,6 @@ def synth_lists(rng, case, W, H):
         return np.zeros((0, 6), np.int32), np.zeros((0, 6), np.int32)
     S = boxes(6 + 4 * case, rng.randint(100, 500), rng.randint(100, 380), 14 + 3 * case)
     Wk = boxes(40 + 30 * case, rng.randint(100, 500), rng.randint(100, 380), 14 + 3 * case)
-    S.sort(key=lambda r: r[0]); Wk.sort(key=lambda r: r[0])       # channel-major like classify's output
     return np.array(S, np.int32), np.array(Wk, np.int32)
 
 

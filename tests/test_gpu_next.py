@@ -34,11 +34,41 @@ def _check_track(ft, exp, tag):
     assert len(ft.tracked) == len(want) and (ft.tracked == want).all(), tag           # same regions, same order
 
 
+def _check_track_sets(ft, exp, tag):
+    """Order-free comparison against the golden vectors.  The GPU path visits NMS siblings in the canonical order
+    (DESIGN.md 3), so pool order inside a plane -- hence the order of strong[ch] / weak[ch] and of all_er -- may differ
+    from the reference's while the SETS are equal: per region colours/centres and the set of tracked regions (the
+    growth is a reachability closure from the strong seeds, independent of visiting order)."""
+    ns = ft.n_strong
+    def key(rows):
+        return [tuple(int(v) for v in r) for r in rows]
+    S, Wk = key(_rows(ft, 0, ns)), key(_rows(ft, ns, len(ft.cand)))
+    assert sorted(S) == sorted(key(exp["strong"])) and sorted(Wk) == sorted(key(exp["weak"])), tag
+    col = np.stack([ft.cand["color1"], ft.cand["color2"], ft.cand["color3"]], axis=1).reshape(-1, 3)
+    got = {("s" if i < ns else "w",) + (S + Wk)[i]: tuple(col[i]) for i in range(len(ft.cand))}
+    want = {("s",) + k: tuple(c) for k, c in zip(key(exp["strong"]), exp["strong_color"])}
+    want.update({("w",) + k: tuple(c) for k, c in zip(key(exp["weak"]), exp["weak_color"])})
+    assert got == want, tag
+    got_t = sorted(("s" if i < ns else "w",) + (S + Wk)[i] for i in ft.tracked)
+    want_t = sorted((("s",) + key(exp["strong"])[idx]) if kind == 0 else (("w",) + key(exp["weak"])[idx]) for kind, idx in exp["tracked"])
+    assert got_t == want_t, tag
+
+
+def _live(ref, bgr, ft):
+    """the reference's er_track fed with the GPU's own strong / weak lists (same order) -> exact expectation"""
+    ns = ft.n_strong
+    S, Wk = _rows(ft, 0, ns), _rows(ft, ns, len(ft.cand))
+    ch = ref.channels(bgr)
+    exp = ref.er_track(ch, np.stack([ch[0], ch[1], ch[2]], axis=-1), S, Wk)
+    exp.update(strong=S, weak=Wk)
+    return exp
+
+
 def _gold(g, tag):
     return {k: g["%s_%s" % (tag, k)] for k in ("strong", "weak", "tracked", "strong_color", "weak_color", "strong_center", "weak_center")}
 
 
-def test_er_track_batch_matches_golden(ert, golden_frames, golden_next):
+def test_er_track_batch_matches_golden(ert, ref, golden_frames, golden_next):
     """detect_classify on the golden frames, then er_track on the device-resident batch == the reference's er_track."""
     import ertext
     res = ert.detect_classify(golden_frames)
@@ -46,7 +76,8 @@ def test_er_track_batch_matches_golden(ert, golden_frames, golden_next):
     tracks, ms = ert.er_track()
     assert len(tracks) == 3 and ms > 0
     for f in range(3):
-        _check_track(tracks[f], _gold(golden_next, "f%d" % f), "f%d" % f)
+        _check_track_sets(tracks[f], _gold(golden_next, "f%d" % f), "f%d" % f)
+        _check_track(tracks[f], _live(ref, golden_frames[f], tracks[f]), "f%d/live" % f)     # exact order, exact doubles
         # cand rows point back into the batch result
         for c in tracks[f].cand:
             pl = res.planes[f * 6 + c["plane"]]
@@ -56,7 +87,8 @@ def test_er_track_batch_matches_golden(ert, golden_frames, golden_next):
     res2 = ert.detect_classify(golden_frames, upto=ertext.STAGE_TRACK)
     tracks2, _ = ert.er_track()
     for f in range(3):
-        _check_track(tracks2[f], _gold(golden_next, "f%d" % f), "f%d/fused" % f)
+        _check_track(tracks2[f], _live(ref, golden_frames[f], tracks2[f]), "f%d/fused" % f)
+        assert (tracks2[f].tracked == tracks[f].tracked).all()
 
 
 def test_er_track_regions_matches_golden(ert, golden_frames, golden_next):
@@ -160,6 +192,8 @@ def test_ocr_rejects_bad_regions(ert, golden_frames, port):
     with pytest.raises(ertext.ErtError):
         ert.ocr_features_plane(plane, [(630, 470, 20, 20)])           # outside the plane
     with pytest.raises(ertext.ErtError):
-        ert.ocr_features_plane(plane, [(0, 0, 640, 1)])               # ARAN collapses (cv::resize would throw in the reference)
+        ert.ocr_features_plane(np.zeros((4, 1000), np.uint8), [(0, 0, 1000, 1)])   # ARAN collapses to 30x0 (cv::resize would throw)
+    with pytest.raises(ertext.ErtError):
+        ert.er_track_regions(golden_frames[0], [(3, 0, 0, 5, 5, 130), (1, 0, 0, 5, 5, 130)], np.zeros((0, 6), np.int32))   # not channel-major
     r = ert.ocr_features_plane(plane, np.zeros((0, 4), np.int32))     # empty batch
     assert r.feat.shape == (0, 1800)
