@@ -8,6 +8,8 @@
 //   make_LBP_hist / set_thresh_step / set_min_area                                       inc/ER.h:132-136
 //   CascadeBoost(filename), predict(vector<double>) with -DBL_MAX = rejected             inc/adaboost.h:159-166
 //   struct ER with level/area/bound/parent/child/next/done/stability                     inc/ER.h:42-80
+//   er_track(strong, weak, tracked, ...) incl. calc_color                                 inc/ER.h:129, src/ER.cpp:532-609
+//   OCR(svm_file, img_L, feature_L), chain_run(src, thresh, slope)                        inc/OCR.h:31-35, src/OCR.cpp:67-140
 // Downstream CPU stages of the reference (er_track, er_grouping, er_ocr) consume the ER* trees
 // this facade rebuilds from the device results.  With -DERT_WITH_OPENCV the cv::Mat / cv::Rect types
 // are used directly; otherwise minimal stand-ins with the same member names are provided.
@@ -18,6 +20,7 @@
 #include "../../include/ertext.h"
 
 #include <cfloat>
+#include <cmath>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -115,6 +118,49 @@ private:
 	int which_, n_ = -1;
 };
 
+// OCR(svm_file_name, img_L, feature_L) + chain_run: the SVM model is parsed by the library (libsvm text format).
+class OCR {
+public:
+	OCR(Device &dev, const char *svm_file_name, int img_L = 30, int feature_L = 15) : dev_(dev)
+	{
+		if (img_L != 30 || feature_L != 15) throw std::runtime_error("OCR: only img_L=30, feature_L=15 (the trained model's contract, inc/utils.h:12-13)");
+		loaded_ = ert_load_svm(dev_.ctx(), svm_file_name) == 0;      // svm_load_model returns NULL on failure; so does this, quietly
+	}
+	bool loaded() const { return loaded_; }
+	// double chain_run(Mat src, int thresh, double slope = 0)  (src/OCR.cpp:67): returns table[label] + probability
+	double chain_run(const Mat &src, int thresh, double slope = 0)
+	{
+		(void)thresh;   // THRESH_OTSU ignores it (src/OCR.cpp:72)
+		if (src.empty() || src.channels() != 1) throw std::runtime_error("chain_run: 8UC1 image expected");
+		ert_ocr_region reg; reg.frame = 0; reg.plane = 0; reg.x = 0; reg.y = 0; reg.w = src.cols; reg.h = src.rows; reg.slope = slope;
+		const ert_ocr_result *r = nullptr;
+		if (ert_ocr_chain_run_plane(dev_.ctx(), src.data, src.cols, src.rows, (int)src.step, &reg, 1, &r)) throw_last("chain_run");
+		return r->value[0];
+	}
+	// the batched form er_ocr wants (src/ER.cpp:728-735 loops chain_run over the ERs of a text line):
+	// letter / prob are written into the ERs exactly as er_ocr does (src/ER.cpp:733-734)
+	void chain_run(const Mat &channel, ERs &ers, double slope)
+	{
+		if (ers.empty()) return;
+		std::vector<ert_ocr_region> regs(ers.size());
+		for (size_t i = 0; i < ers.size(); i++) {
+			regs[i].frame = 0; regs[i].plane = 0; regs[i].x = ers[i]->bound.x; regs[i].y = ers[i]->bound.y;
+			regs[i].w = ers[i]->bound.width; regs[i].h = ers[i]->bound.height; regs[i].slope = slope;
+		}
+		const ert_ocr_result *r = nullptr;
+		if (ert_ocr_chain_run_plane(dev_.ctx(), channel.data, channel.cols, channel.rows, (int)channel.step, regs.data(), (int)regs.size(), &r))
+			throw_last("chain_run");
+		for (size_t i = 0; i < ers.size(); i++) {
+			const double result = r->value[i];
+			ers[i]->letter = (char)floor(result);
+			ers[i]->prob = result - floor(result);
+		}
+	}
+private:
+	Device &dev_;
+	bool loaded_ = false;
+};
+
 class ERFilter {
 public:
 	ERFilter(int thresh_step = 2, int min_area = 100, int max_area = 100000, int stability_t = 2, double overlap_coef = 0.7,
@@ -154,6 +200,76 @@ public:
 		times[0] = r->stage_ms[0] * 1e-3; times[1] = r->stage_ms[1] * 1e-3; times[2] = r->stage_ms[2] * 1e-3;
 		times[6] = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
 		return times;
+	}
+
+	// text_detect through er_track (src/ER.cpp:33-63): as above, plus `tracked`; times[3] = er_track seconds.
+	std::vector<double> text_detect(const Mat &src, ERs &root, std::vector<ERs> &all, std::vector<ERs> &pool, std::vector<ERs> &strong,
+	                                std::vector<ERs> &weak, ERs &tracked)
+	{
+		if (src.empty() || src.channels() != 3) throw std::runtime_error("text_detect: 8UC3 BGR image expected");
+		const auto t0 = std::chrono::high_resolution_clock::now();
+		const ert_result *r = nullptr;
+		if (ert_detect_classify(dev_.ctx(), src.data, 1, src.cols, src.rows, (int)src.step, ERT_STAGE_TRACK, &r)) throw_last("text_detect");
+		check_status(r);
+		const ert_track_result *t = nullptr;
+		if (ert_er_track(dev_.ctx(), &t)) throw_last("er_track");
+		root.assign(6, nullptr); all.assign(6, ERs()); pool.assign(6, ERs()); strong.assign(6, ERs()); weak.assign(6, ERs());
+		std::vector<std::vector<ER *> > nodes(6);
+		for (int p = 0; p < 6; p++) {
+			root[p] = build_tree(r, p, nodes[(size_t)p]);
+			for (int k = r->pool_offset[p]; k < r->pool_offset[p + 1]; k++) {
+				ER *e = nodes[(size_t)p][(size_t)r->pool_node[k]];
+				pool[p].push_back(e);
+				if (r->pool_label[k] == ERT_LABEL_STRONG) strong[p].push_back(e);
+				else if (r->pool_label[k] == ERT_LABEL_WEAK) weak[p].push_back(e);
+			}
+		}
+		std::vector<ER *> cand((size_t)(t->cand_offset[1] - t->cand_offset[0]));
+		for (size_t i = 0; i < cand.size(); i++) {
+			const ert_tracked &c = t->cand[i];
+			ER *e = nodes[(size_t)c.plane][(size_t)c.node];
+			e->color1 = c.color1; e->color2 = c.color2; e->color3 = c.color3;
+			e->center.x = c.center_x; e->center.y = c.center_y; e->ch = c.plane;
+			cand[i] = e;
+		}
+		tracked.clear();
+		for (int k = t->track_offset[0]; k < t->track_offset[1]; k++) tracked.push_back(cand[(size_t)t->tracked[k]]);
+		std::vector<double> times(7, 0);
+		times[0] = r->stage_ms[0] * 1e-3; times[1] = r->stage_ms[1] * 1e-3; times[2] = r->stage_ms[2] * 1e-3; times[3] = t->track_ms * 1e-3;
+		times[6] = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+		return times;
+	}
+
+	// er_track(vector<ERs> &strong, vector<ERs> &weak, ERs &all_er, vector<Mat> &channel, Mat Ycrcb)  (src/ER.cpp:532).
+	// The channel planes and the YCrCb frame are derived on the device from the BGR frame, so the facade takes `src`
+	// instead of (channel, Ycrcb).  Sets color1..3, center, ch on every strong / weak ER and appends to all_er.
+	void er_track(std::vector<ERs> &strong, std::vector<ERs> &weak, ERs &all_er, const Mat &src)
+	{
+		if (src.empty() || src.channels() != 3) throw std::runtime_error("er_track: 8UC3 BGR image expected");
+		std::vector<int32_t> rs, rw;
+		std::vector<ER *> es, ew;
+		for (int pass = 0; pass < 2; pass++) {
+			std::vector<ERs> &v = pass ? weak : strong;
+			std::vector<int32_t> &rows = pass ? rw : rs;
+			std::vector<ER *> &flat = pass ? ew : es;
+			for (size_t ch = 0; ch < v.size(); ch++)
+				for (ER *e : v[ch]) {
+					const int32_t row[6] = {(int32_t)ch, e->bound.x, e->bound.y, e->bound.width, e->bound.height, e->area};
+					rows.insert(rows.end(), row, row + 6);
+					flat.push_back(e);
+				}
+		}
+		const ert_track_result *t = nullptr;
+		if (ert_er_track_regions(dev_.ctx(), src.data, src.cols, src.rows, (int)src.step, rs.data(), (int)es.size(), rw.data(), (int)ew.size(), &t))
+			throw_last("er_track");
+		std::vector<ER *> cand(es);
+		cand.insert(cand.end(), ew.begin(), ew.end());
+		for (size_t i = 0; i < cand.size(); i++) {
+			const ert_tracked &c = t->cand[i];
+			cand[i]->color1 = c.color1; cand[i]->color2 = c.color2; cand[i]->color3 = c.color3;
+			cand[i]->center.x = c.center_x; cand[i]->center.y = c.center_y; cand[i]->ch = c.plane;
+		}
+		for (int k = t->track_offset[0]; k < t->track_offset[1]; k++) all_er.push_back(cand[(size_t)t->tracked[k]]);
 	}
 
 	// compute_channels(src, YCrcb, channels)  (src/ER.cpp:114-128): the six planes as one contiguous buffer

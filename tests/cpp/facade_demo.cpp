@@ -1,9 +1,10 @@
 // facade_demo.cpp -- exercises the C++ facade the way the reference's callers use ERFilter
 // (src/utils.cpp:115-140 video_mode: compute_channels, then per channel er_tree_extract ->
 // non_maximum_supression -> classify; src/utils.cpp:49 image_mode: text_detect).
-// usage: facade_demo <bgr.raw> <planes6.raw> <w> <h> <strong.classifier> <weak.classifier>
+// usage: facade_demo <bgr.raw> <planes6.raw> <w> <h> <strong.classifier> <weak.classifier> [OCR.model]
 #include "../../scene-text-recognition_b200/host/ERFilter.hpp"
 #include <cstdio>
+#include <cmath>
 #include <fstream>
 
 using namespace ertx;
@@ -59,6 +60,31 @@ int main(int argc, char **argv)
 				printf("FV %g %g\n", sum, er_filter->stc->predict(fv));
 			}
 			er_filter->er_delete(r);
+		}
+		// er_track the way video_mode calls it after the per-channel loop (src/utils.cpp:140)
+		{
+			ERs tracked;
+			er_filter->er_track(strong, weak, tracked, src);
+			unsigned long long h2 = 1469598103934665603ull;
+			for (ER *e : tracked) { const int v[5] = {e->ch, e->bound.x, e->bound.y, e->center.x, e->center.y}; for (int i = 0; i < 5; i++) { h2 ^= (unsigned long long)(unsigned)v[i]; h2 *= 1099511628211ull; } }
+			printf("TR %zu hash %llu\n", tracked.size(), h2);
+			// text_detect with `tracked` (one submission) must give the same list
+			ERs root2, tracked2; std::vector<ERs> all2, pool2, strong2, weak2;
+			std::vector<double> t2 = er_filter->text_detect(src, root2, all2, pool2, strong2, weak2, tracked2);
+			unsigned long long h3 = 1469598103934665603ull;
+			for (ER *e : tracked2) { const int v[5] = {e->ch, e->bound.x, e->bound.y, e->center.x, e->center.y}; for (int i = 0; i < 5; i++) { h3 ^= (unsigned long long)(unsigned)v[i]; h3 *= 1099511628211ull; } }
+			printf("TD_TR %zu hash %llu t3 %d\n", tracked2.size(), h3, t2[3] > 0 ? 1 : 0);
+			if (argc > 7) {
+				OCR *ocr = new OCR(er_filter->device(), argv[7], 30, 15);                     // src/main.cpp:25
+				for (size_t i = 0; i < tracked2.size() && i < 8; i++) {
+					ER *e = tracked2[i];
+					Mat chn(h, w, 1, planes.data() + (size_t)e->ch * w * h);
+					const double result = ocr->chain_run(chn(e->bound), e->level * 8, 0.0);    // src/ER.cpp:732
+					printf("OCR %c %.6f\n", (char)floor(result), result - floor(result));
+				}
+				delete ocr;
+			}
+			for (int p = 0; p < 6; p++) er_filter->er_delete(root2[(size_t)p]);
 		}
 		for (int p = 0; p < 6; p++) er_filter->er_delete(root[(size_t)p]);
 		printf("times %d\n", (int)times.size());

@@ -158,13 +158,14 @@ def test_cpp_facade_like_the_reference_callers(ert, port, golden_frames, tmp_pat
     exe = str(tmp_path / "facade_demo")
     subprocess.check_call(["g++", "-std=c++11", "-O1", os.path.join(ROOT, "tests", "cpp", "facade_demo.cpp"), "-o", exe,
                            "-L", PKG, "-l:libertext.so", "-Wl,-rpath," + PKG])
-    frame = golden_frames[0]
+    frame = golden_frames[1]
     planes = port.channels(frame)
     (tmp_path / "bgr.raw").write_bytes(frame.tobytes())
     (tmp_path / "planes.raw").write_bytes(planes.tobytes())
     assets = os.path.join(ROOT, "assets", "classifier")
     out = subprocess.run([exe, str(tmp_path / "bgr.raw"), str(tmp_path / "planes.raw"), "640", "480",
-                          os.path.join(assets, "strong.classifier"), os.path.join(assets, "weak.classifier")],
+                          os.path.join(assets, "strong.classifier"), os.path.join(assets, "weak.classifier"),
+                          __import__("ertext").svm_model_path()],
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     lines = out.stdout.strip().splitlines()
@@ -180,6 +181,26 @@ def test_cpp_facade_like_the_reference_callers(ert, port, golden_frames, tmp_pat
     fv = [l for l in lines if l.startswith("FV")][0].split()
     assert float(fv[1]) == 576.0              # 4 blocks x 144
     assert "ASSERT ok" in out.stdout
+    # er_track through the facade (both routes) == the binding's er_track on the same frame
+    tracks, _ = ert.er_track()
+    ft = tracks[0]
+    h = 1469598103934665603
+    for i in ft.tracked:
+        c = ft.cand[i]
+        for v in (c["plane"], c["x"], c["y"], c["center_x"], c["center_y"]):
+            h = ((h ^ (int(v) & 0xffffffff)) * 1099511628211) & 0xffffffffffffffff
+    tr = [l.split() for l in lines if l.startswith("TR")][0]
+    tdtr = [l.split() for l in lines if l.startswith("TD_TR")][0]
+    assert int(tr[1]) == len(ft.tracked) and int(tr[3]) == h
+    assert int(tdtr[1]) == len(ft.tracked) and int(tdtr[3]) == h and tdtr[5] == "1"
+    # OCR::chain_run through the facade == the binding's batch call on the same regions
+    sel = ft.tracked[:8]
+    c = ft.cand[sel]
+    r = ert.ocr_chain_run_batch(np.zeros(len(sel), np.int32), c["plane"], np.stack([c["x"], c["y"], c["w"], c["h"]], axis=1))
+    ocr = [l.split() for l in lines if l.startswith("OCR")]
+    assert len(ocr) == len(sel)
+    for i, l in enumerate(ocr):
+        assert l[1] == chr(int(np.floor(r.value[i]))) and abs(float(l[2]) - (r.value[i] - np.floor(r.value[i]))) < 1e-6
 
 
 def test_4k_three_plane_four_scale_pyramid(ert, port):
