@@ -73,7 +73,7 @@ int main(int argc, char **argv)
 			std::vector<double> t2 = er_filter->text_detect(src, root2, all2, pool2, strong2, weak2, tracked2);
 			unsigned long long h3 = 1469598103934665603ull;
 			for (ER *e : tracked2) { const int v[5] = {e->ch, e->bound.x, e->bound.y, e->center.x, e->center.y}; for (int i = 0; i < 5; i++) { h3 ^= (unsigned long long)(unsigned)v[i]; h3 *= 1099511628211ull; } }
-			printf("TD_TR %zu hash %llu t3 %d\n", tracked2.size(), h3, t2[3] > 0 ? 1 : 0);
+			printf("XTR %zu hash %llu t3 %d\n", tracked2.size(), h3, t2[3] > 0 ? 1 : 0);
 			if (argc > 7) {
 				OCR *ocr = new OCR(er_filter->device(), argv[7], 30, 15);                     // src/main.cpp:25
 				for (size_t i = 0; i < tracked2.size() && i < 8; i++) {

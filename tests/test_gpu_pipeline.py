@@ -190,7 +190,7 @@ def test_cpp_facade_like_the_reference_callers(ert, port, golden_frames, tmp_pat
         for v in (c["plane"], c["x"], c["y"], c["center_x"], c["center_y"]):
             h = ((h ^ (int(v) & 0xffffffff)) * 1099511628211) & 0xffffffffffffffff
     tr = [l.split() for l in lines if l.startswith("TR")][0]
-    tdtr = [l.split() for l in lines if l.startswith("TD_TR")][0]
+    tdtr = [l.split() for l in lines if l.startswith("XTR")][0]
     assert int(tr[1]) == len(ft.tracked) and int(tr[3]) == h
     assert int(tdtr[1]) == len(ft.tracked) and int(tdtr[3]) == h and tdtr[5] == "1"
     # OCR::chain_run through the facade == the binding's batch call on the same regions
