@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--input-batches", type=int, default=4, help="distinct input batches rotated through (defeats L2 reuse)")
     ap.add_argument("--cpu-sample-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the er_track / chain_run leg (SURVEY 8f rows, outside the timed region)")
     ap.add_argument("--contexts", type=int, default=3, help="contexts / streams used round-robin (copy/compute overlap)")
     return ap.parse_args()
 
@@ -335,11 +336,40 @@ def run_ours(a, rank, local_rank, world):
         "regions_per_frame": res_stats["regions"] / max(res_stats["steps"] * fpg, 1),
         "kept_nodes_per_frame": res_stats["kept"] / max(res_stats["steps"] * fpg, 1),
     }
+    if world == 1 and not a.no_next_rows:
+        line["next_rows"] = next_rows(a, ctxs[0], dev_batches, fpg, W, H)
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, host_batches)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def next_rows(a, ctx, dev_batches, fpg, W, H):
+    """The two steps after the path, measured OUTSIDE the timed region on one context, device events:
+    the same batch with er_track fused into the submission (upto = ERT_STAGE_TRACK), then OCR::chain_run
+    (feature kernel + SVM) on every tracked region of the batch, planes still resident."""
+    import ertext
+    try:
+        ctx.load_svm(ertext.svm_model_path())
+        tr_ms, ocr_ms, tot_ms, n_tr = [], [], [], 0
+        for i in range(5):
+            ctx.enqueue_device(dev_batches[i % len(dev_batches)].data_ptr(), fpg, W, H, W * 3, upto=ertext.STAGE_TRACK)
+            r = ctx.fetch()
+            tracks, ms = ctx.er_track()
+            fr, pl, rc = [], [], []
+            for f, t in enumerate(tracks):
+                c = t.cand[t.tracked]
+                fr += [f] * len(c); pl += c["plane"].tolist(); rc += list(zip(c["x"].tolist(), c["y"].tolist(), c["w"].tolist(), c["h"].tolist()))
+            o = ctx.ocr_chain_run_batch(np.array(fr, np.int32), np.array(pl, np.int32), np.array(rc, np.int32).reshape(-1, 4))
+            if i:
+                tr_ms.append(ms); ocr_ms.append(o.ocr_ms); tot_ms.append(r.stage_ms[5] + ms + o.ocr_ms); n_tr = len(fr)
+        return {"er_track_ms_per_batch": float(np.median(tr_ms)), "chain_run_ms_per_batch": float(np.median(ocr_ms)),
+                "tracked_regions_per_batch": n_tr, "serial_ms_per_batch_detect_to_letters": float(np.median(tot_ms)),
+                "frames_per_s_detect_to_letters_one_context": fpg / (float(np.median(tot_ms)) * 1e-3),
+                "note": "device time, one context, no overlap; er_grouping (CPU, between the two) not included, slope 0"}
+    except Exception as ex:    # never lose the headline line to the extra leg
+        return {"error": str(ex)}
 
 
 def cpu_baseline(a, host_batches):

@@ -197,3 +197,33 @@ def test_ocr_rejects_bad_regions(ert, golden_frames, port):
         ert.er_track_regions(golden_frames[0], [(3, 0, 0, 5, 5, 130), (1, 0, 0, 5, 5, 130)], np.zeros((0, 6), np.int32))   # not channel-major
     r = ert.ocr_features_plane(plane, np.zeros((0, 4), np.int32))     # empty batch
     assert r.feat.shape == (0, 1800)
+
+
+def test_er_track_and_ocr_at_bench_size(ert, ref):
+    """BASELINE's full frame size: two synthetic 1080p S-text frames through detect -> er_track (fused submission) ->
+    chain_run on every tracked region, each checked against the reference's own code on the same inputs."""
+    import ertext
+    from ertext import synth
+    frames = synth.s_text_batch(4321, 2, 1920, 1080)
+    res = ert.detect_classify(frames, upto=ertext.STAGE_TRACK)
+    assert res.status == 0
+    tracks, _ = ert.er_track()
+    fr, pl, rc, exp_feat, exp_val = [], [], [], [], []
+    for f in range(2):
+        ft = tracks[f]
+        assert len(ft.cand) > 20 and len(ft.tracked) >= ft.n_strong
+        _check_track(ft, _live(ref, frames[f], ft), "1080p/%d" % f)
+        ch = ref.channels(frames[f])
+        for j, i in enumerate(ft.tracked[:40]):
+            c = ft.cand[i]
+            k, x, y, w, h = int(c["plane"]), int(c["x"]), int(c["y"]), int(c["w"]), int(c["h"])
+            sl = [0.0, 0.07, -0.2][j % 3]
+            crop = ch[k][y:y + h, x:x + w]
+            fr.append(f); pl.append(k); rc.append((x, y, w, h))
+            exp_feat.append(ref.ocr_features(crop, sl)[1]); exp_val.append(ref.chain_run(crop, 0, sl))
+    sl = np.array([[0.0, 0.07, -0.2][j % 3] for f in range(2) for j in range(min(40, len(tracks[f].tracked)))])
+    o = ert.ocr_chain_run_batch(np.array(fr, np.int32), np.array(pl, np.int32), np.array(rc, np.int32), sl)
+    assert (o.feat == np.stack(exp_feat)).all()
+    ev = np.array(exp_val)
+    assert (np.floor(o.value) == np.floor(ev)).all()
+    assert np.allclose(o.value - np.floor(o.value), ev - np.floor(ev), rtol=1e-4, atol=1e-9)
