@@ -8,7 +8,8 @@ A "step" is one pass of the hot path (compute_channels -> er_tree_extract -> non
 classify, 6 planes per frame) over one batch of `--frames-per-gpu` synthetic 1080p S-text frames per GPU.
   value : frames/s with the BGR frames already resident in HBM (device-timed with CUDA events)
   e2e   : frames/s through the host-buffer C-ABI call (pinned host frames -> H2D -> kernels -> result D2H
-          inside the timed region), two contexts used alternately so copies overlap compute
+          inside the timed region), several contexts (streams) used round-robin so copies and the narrow
+          kernels of one batch overlap the tile kernel of another
 Weak scaling: every rank processes its own `frames-per-gpu` frames per step (frames are independent units,
 no collective on the compute path); for N > 1 the per-step region records are all-gathered over NCCL.
 """
@@ -53,7 +54,8 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the er_track / chain_run leg (SURVEY 8f rows, outside the timed region)")
-    ap.add_argument("--contexts", type=int, default=3, help="contexts / streams used round-robin (copy/compute overlap)")
+    ap.add_argument("--no-tile-fifo", action="store_true", help="A/B: do not chain the tile kernels of the contexts in submission order")
+    ap.add_argument("--contexts", type=int, default=5, help="contexts / streams used round-robin (copy/compute overlap)")
     return ap.parse_args()
 
 
@@ -214,6 +216,8 @@ def run_ours(a, rank, local_rank, world):
     streams = [torch.cuda.Stream(device=dev) for _ in range(NC)]
     for c, s in zip(ctxs, streams):
         c.set_stream(s.cuda_stream)
+        if a.no_tile_fifo:
+            c.set_tile_fifo(False)
 
     gatherer = edist.RegionGatherer(dev) if world > 1 else None
     stats = {"tile_ms": [], "extract_ms": [], "nms_ms": [], "classify_ms": [], "launches": 0, "d2h": 0, "regions": 0, "kept": 0, "steps": 0}
@@ -254,7 +258,8 @@ def run_ours(a, rank, local_rank, world):
                 stats["gathered_rows"] = stats.get("gathered_rows", 0) + int(sum(len(g) for g in gathered))
 
     def timed(resident):
-        run_loop(a.warmup, resident, False)
+        # every context allocates its workspace on first use: W warm-up steps, but at least one per context
+        run_loop(max(a.warmup, NC), resident, False)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

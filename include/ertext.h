@@ -137,6 +137,9 @@ ERT_API int ert_set_min_area(ert_ctx *ctx, int min_area);
 ERT_API int ert_set_return_hist(ert_ctx *ctx, int on);
 /* option (debug / A-B): 0 = skip the shared-memory tile pass and link every edge in global memory */
 ERT_API int ert_set_tile_local_union(ert_ctx *ctx, int on);
+/* scheduling: 1 (default) = the tile-build kernels of all contexts on a device run in submission order (an event
+ * chain); keeps the oldest batch in flight from being starved when several contexts are used round-robin */
+ERT_API int ert_set_tile_fifo(ert_ctx *ctx, int on);
 /* tuning: tile shape / CTA size of the tile-build kernel (0 = default 64x32 pixels, 256 threads) */
 ERT_API int ert_set_tile_config(ert_ctx *ctx, int id);
 /* debug: per-phase cycle sums (clock64, thread 0 of every CTA) of the tile-build kernel since the last call */

@@ -74,6 +74,7 @@ struct ert_ctx {
 	bool own_stream = true;
 	cudaEvent_t ev[12];
 	int local_union = 1;
+	int tile_fifo = 1;       // chain the tile kernels of all contexts on the device in submission order
 	int tile_cfg = 0;
 	int return_hist = 0;
 	int kept_cap = 16384, pool_cap = 2048;
