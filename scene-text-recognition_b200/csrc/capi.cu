@@ -84,6 +84,8 @@ void free_workspace(ert_ctx *c)
 	c->h_node_off = c->h_pool_off = c->h_pool = c->h_label = nullptr; c->h_nodes = nullptr; c->h_ss = c->h_ws = nullptr;
 	c->h_hist = nullptr; c->h_status = nullptr;
 	c->planes_cap = 0; c->frames_cap = 0; c->W = c->H = 0;
+	c->cap_np = c->cap_ycc = c->cap_ring = 0;
+	c->table_planes = 0; c->table_W = c->table_H = 0;
 }
 
 template <typename T>
@@ -99,26 +101,34 @@ int dmalloc(T **p, size_t n)
 	return 0;
 }
 
-// (re)allocate everything that depends on (n_planes, W, H)
+// Workspace by CAPACITY: buffers grow to the largest (planes x pixels) seen and are reused for anything smaller, so
+// alternating plane sizes (the scales of a pyramid, BASELINE config 4) costs no allocation after the first pass.
+// Nothing in the workspace needs clearing between batches (sparse slots are initialised by the kernel that creates them).
 int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 {
-	if (W == c->W && H == c->H && n_planes <= c->planes_cap) return 0;
 	if (W < 1 || H < 1 || (long long)W * H > (1ll << KEY_IDX_BITS) || W > 8191 || H > 8191) {
 		set_error("unsupported plane size %dx%d (max 8191 per side, %d pixels)", W, H, 1 << KEY_IDX_BITS);
 		return -1;
 	}
-	const int keep_planes = std::max(n_planes, (W == c->W && H == c->H) ? c->planes_cap : 0);
-	free_workspace(c);
-	ERT_CUDA_CHECK(cudaSetDevice(c->device));
-	c->W = W; c->H = H; c->pitch = extract_pitch(W);
-	const int P = keep_planes;
+	const int pitch = extract_pitch(W);
 	const size_t N = (size_t)W * H;
-	c->ycc_bytes = (size_t)c->pitch * H;
-	if (dmalloc(&c->d_ycc, c->ycc_bytes * P + 256)) return -1;
-	ERT_CUDA_CHECK(cudaMemset(c->d_ycc, 0, c->ycc_bytes * P + 256));
+	const size_t need_np = N * n_planes, need_ycc = (size_t)pitch * H * n_planes, need_ring = ring_words_per_plane(W, H) * n_planes;
+	if (n_planes <= c->planes_cap && need_np <= c->cap_np && need_ycc <= c->cap_ycc && need_ring <= c->cap_ring) {
+		c->W = W; c->H = H; c->pitch = pitch; c->ycc_bytes = (size_t)pitch * H;
+		return 0;
+	}
+	const int P = std::max(n_planes, c->planes_cap);
+	const size_t cap_np = std::max(need_np, c->cap_np), cap_ycc = std::max(need_ycc, c->cap_ycc), cap_ring = std::max(need_ring, c->cap_ring);
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	free_workspace(c);
+	c->W = W; c->H = H; c->pitch = pitch;
+	c->ycc_bytes = (size_t)pitch * H;
+	if (dmalloc(&c->d_ycc, cap_ycc + 256)) return -1;
+	ERT_CUDA_CHECK(cudaMemset(c->d_ycc, 0, cap_ycc + 256));
 	if (dmalloc(&c->d_planes, (size_t)P)) return -1;
-	if (dmalloc(&c->wk.par, N * P) || dmalloc(&c->wk.attr, N * P) || dmalloc(&c->wk.node_list, N * P)) return -1;
-	if (dmalloc(&c->wk.ring_rec, ring_words_per_plane(W, H) * P)) return -1;
+	if (dmalloc(&c->wk.par, cap_np) || dmalloc(&c->wk.attr, cap_np) || dmalloc(&c->wk.node_list, cap_np)) return -1;
+	if (dmalloc(&c->wk.ring_rec, cap_ring)) return -1;
 	if (dmalloc(&c->wk.node_count, (size_t)P) || dmalloc(&c->wk.reach_root, (size_t)P) || dmalloc(&c->wk.lone_level, (size_t)P)) return -1;
 	if (dmalloc(&c->wk.kept, (size_t)P * c->kept_cap) || dmalloc(&c->wk.kept_count, (size_t)P) || dmalloc(&c->wk.status, 1)) return -1;
 	ERT_CUDA_CHECK(cudaMemset(c->wk.status, 0, sizeof(uint32_t)));
@@ -135,7 +145,7 @@ int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 	if (hmalloc(&c->h_nodes, (size_t)P * c->kept_cap) || hmalloc(&c->h_pool, (size_t)P * c->pool_cap)) return -1;
 	if (hmalloc(&c->h_label, (size_t)P * c->pool_cap) || hmalloc(&c->h_ss, (size_t)P * c->pool_cap) || hmalloc(&c->h_ws, (size_t)P * c->pool_cap)) return -1;
 	if (hmalloc(&c->h_hist, (size_t)P * c->pool_cap * 1024) || hmalloc(&c->h_status, 1)) return -1;
-	c->planes_cap = P;
+	c->planes_cap = P; c->cap_np = cap_np; c->cap_ycc = cap_ycc; c->cap_ring = cap_ring;
 	return 0;
 }
 
@@ -553,9 +563,12 @@ static int detect_common(ert_ctx *c, const uint8_t *bgr, bool on_device, int n_f
 	if (stride < 3 * W) { set_error("stride %d < 3*width", stride); return -1; }
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
 	const int n_planes = 6 * n_frames;
-	const bool fresh = !(W == c->W && H == c->H && n_planes <= c->planes_cap);
 	if (ensure_workspace(c, n_planes, W, H)) return -1;
-	if (fresh || c->frames_cap != -1) { if (set_plane_table(c, c->planes_cap, true)) return -1; c->frames_cap = -1; }
+	// the plane table (plane -> source pointer, invert flag) depends on the layout, the plane pitch and the plane count
+	if (c->frames_cap != -1 || c->table_W != W || c->table_H != H || n_planes > c->table_planes) {
+		if (set_plane_table(c, n_planes, true)) return -1;
+		c->frames_cap = -1; c->table_W = W; c->table_H = H; c->table_planes = n_planes;
+	}
 	c->launches = 0;
 	cudaStream_t st = c->stream;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[0], st));
@@ -616,7 +629,7 @@ int ert_planes_detect(ert_ctx *c, const uint8_t *planes, int n_planes, int W, in
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
 	if (ensure_workspace(c, n_planes, W, H)) return -1;
 	if (set_plane_table(c, n_planes, false)) return -1;
-	c->frames_cap = 0;   // plane table no longer in BGR layout
+	c->frames_cap = 0; c->table_planes = 0;   // plane table no longer in BGR layout
 	c->launches = 0;
 	cudaStream_t st = c->stream;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[0], st));

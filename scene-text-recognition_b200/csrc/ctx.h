@@ -88,6 +88,8 @@ struct ert_ctx {
 
 	// workspace geometry
 	int W = 0, H = 0, pitch = 0, planes_cap = 0, frames_cap = 0;
+	size_t cap_np = 0, cap_ycc = 0, cap_ring = 0;   // capacities: planes x pixels, plane bytes, seam-record words
+	int table_planes = 0, table_W = 0, table_H = 0; // what the BGR-layout plane table on the device was built for
 	uint8_t *d_bgr = nullptr; size_t bgr_cap = 0;
 	uint8_t *d_ycc = nullptr;          // frames_cap*3 planes (BGR mode) or planes_cap planes (plane mode)
 	size_t ycc_bytes = 0;
