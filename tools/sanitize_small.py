@@ -20,5 +20,20 @@ print(e.nms_nodes(r.planes[0].nodes, 70, 40))
 x = np.load(os.path.join(ROOT, "tests", "golden", "ref_svm.npz"))["x_u8"][:3]
 print(e.svm_predict_probability(x)[0], e.svm_predict_probability(x.astype(np.float64) / 255.0)[0])
 print(e.cascade_predict(0, np.zeros((2, 1024)))[:2], e.compute_channels(g[0, :50, :60]).shape)
+# rows after the path: er_track (fused, stand-alone, caller regions) and OCR::chain_run (batch / plane, with rotation)
+r = e.detect_classify(g[1:2, :240, :400], upto=ertext.STAGE_TRACK)
+tr, _ = e.er_track()
+print("track", len(tr[0].cand), len(tr[0].tracked))
+r = e.detect_classify(g[1:2, :240, :400]); tr, _ = e.er_track()
+c = tr[0].cand
+if len(c):
+    o = e.ocr_chain_run_batch(np.zeros(len(c), np.int32), c["plane"], np.stack([c["x"], c["y"], c["w"], c["h"]], axis=1),
+                              np.where(np.arange(len(c)) % 2 == 0, 0.0, 0.3))
+    print("ocr batch", o.label[:4], o.feat.sum())
+ft = e.er_track_regions(g[1, :200, :300], [(0, 10, 10, 30, 40, 500), (3, 50, 60, 20, 25, 300)], [(1, 12, 14, 28, 38, 450), (4, 100, 20, 1, 1, 130)])
+print("track regions", ft.tracked)
+o = e.ocr_chain_run_plane(pl, [(0, 0, 120, 90), (5, 5, 60, 60), (7, 9, 3, 40), (20, 20, 40, 30)], [0.0, 0.0, 0.0, -0.5])
+print("ocr plane", o.label, o.img.sum())
+print(e.ocr_features_plane(pl, [(1, 1, 2, 2)]).feat.sum())
 e.close()
 print("done")
