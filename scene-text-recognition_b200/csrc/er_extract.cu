@@ -133,7 +133,7 @@ __device__ __forceinline__ void tma_row_g2s(void *dst_smem, const void *src_gmem
 // ---------------------------------------------------------------------------------------------
 // k_tile_build
 // ---------------------------------------------------------------------------------------------
-template <int TW, int TH, int NT, int RF, bool CHUNK, bool KRUSKAL = false>
+template <int TW, int TH, int NT, int RF, bool CHUNK>
 __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneSrc *__restrict__ planes,
                                                    uint32_t *__restrict__ par_g, NodeAttr *__restrict__ attr_g,
                                                    uint32_t *__restrict__ node_list, uint32_t *__restrict__ node_count,
@@ -155,7 +155,6 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	uint16_t *rootlist = reinterpret_cast<uint16_t *>(ymask + TPX);
 	__shared__ __align__(8) uint64_t bar;
 	__shared__ uint32_t s_nroots, s_base, s_cursor, s_nlinks, s_nemit, s_minlvl, s_maxlvl;
-	__shared__ uint32_t s_lcnt[36];                          // KRUSKAL: edges per level, then bucket bases (exclusive prefix)
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int plane = blockIdx.y;
@@ -170,7 +169,6 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 
 	// ---- stage the tile through TMA (one bulk copy per row, all completing on one mbarrier) ----
 	if (tid == 0) { mbar_init(&bar, 1); s_nroots = 0; s_cursor = 0; s_nlinks = 0; s_nemit = 0; s_minlvl = 255; s_maxlvl = 0; }
-	if (KRUSKAL && tid < 36) s_lcnt[tid] = 0;
 	__syncthreads();
 	if (warp == 0) {
 		if (lane == 0) mbar_expect_tx(&bar, (uint32_t)(rows * TW));
@@ -199,7 +197,6 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 		const int end = lane + __ffs(bmask >> lane) - 1;
 		lvl[p] = (uint8_t)L;   // every lane rewrites only the byte it read itself
 		par[p] = (L == 255 || end == lane) ? KEY_NONE : (((uint32_t)L << 16) | (uint32_t)(seg * 32 + end));
-		if (KRUSKAL) cnt[p] = (uint32_t)(seg * 32 + end);   // zpar: connectivity forest, starts as the same-level runs
 		wmin = min(wmin, (uint32_t)L);
 		wmax = max(wmax, (L == 255) ? 0u : (uint32_t)L);
 	}
@@ -215,95 +212,7 @@ __global__ void __launch_bounds__(NT) k_tile_build(ExtractParams P, const PlaneS
 	// every lane owns one edge at a time, all lanes advance one hop per iteration (no divergent inner
 	// loops), idle lanes refill from the list -- so a long chain stalls one lane, not the CTA. ----
 	uint32_t *links = cnt;   // up to 2*TPX packed (p << 16 | q)
-	if constexpr (KRUSKAL) { if (local_union) {
-		// ---- phase B, level-ordered variant (Kruskal / Najman-Couprie style).  Two forests: zpar (aliases cnt) is a
-		// plain union-find over CONNECTIVITY with free path halving; par is the component tree and is written once per
-		// merge.  Edges are bucketed by level = max(level p, level q) and the buckets processed in ascending order, one
-		// CTA barrier per non-empty level: when bucket l runs, every component is complete below l, so one of the two
-		// tops of an edge is a level-l root and the other one loses -- as a same-level merge (larger index wins, so the
-		// surviving root of a node is its highest pixel, as in the keyed variant) or as a child link.  No re-linking. ----
-		volatile uint32_t *zpar = cnt;
-		uint16_t *sorted = reinterpret_cast<uint16_t *>(xmn);       // up to 2*TPX edges: p | dir << 11
-		static_assert(TPX <= 2048, "edge record packs the pixel index in 11 bits");
-		constexpr int EPL = 2 * ((SEGS + NWARP - 1) / NWARP);       // edges a lane can own
-		uint32_t erec[EPL];                                          // p | dir << 11 | level << 12 | rank << 17 ; ~0 = none
-		int je = 0;
-#pragma unroll
-		for (int seg = warp; seg < SEGS; seg += NWARP) {
-			const int p = seg * 32 + lane;
-			const int y = p / TW, x = p % TW;
-			const uint32_t L = lvl[p];
-			const uint32_t Lb = (y + 1 < TH) ? (uint32_t)lvl[p + TW] : 255u;
-			uint32_t Lrt = __shfl_down_sync(0xFFFFFFFFu, L, 1), Llf = __shfl_up_sync(0xFFFFFFFFu, L, 1), Lbl = __shfl_up_sync(0xFFFFFFFFu, Lb, 1);
-			if (lane == 31) Lrt = (x + 1 < TW) ? (uint32_t)lvl[p + 1] : 255u;
-			if (lane == 0) { Llf = (x > 0) ? (uint32_t)lvl[p - 1] : 255u; Lbl = (x > 0 && y + 1 < TH) ? (uint32_t)lvl[p + TW - 1] : 255u; }
-			bool eh = false, ev = false;
-			if (L != 255) {
-				eh = (Lrt != 255) && (Lrt != L || lane == 31);
-				if (Lb != 255) ev = !((x > 0) && (Llf == L) && (Lbl == Lb));
-			}
-#pragma unroll
-			for (int d = 0; d < 2; d++) {
-				const bool on = d ? ev : eh;
-				const uint32_t lev = max(L, d ? Lb : Lrt);
-				const uint32_t m = __ballot_sync(0xFFFFFFFFu, on);
-				uint32_t rec = 0xFFFFFFFFu;
-				if (on) {
-					// one shared-memory ticket per distinct level per warp (levels cluster: a handful per 32 edges)
-					const uint32_t peers = __match_any_sync(m, lev);
-					const int leader = __ffs(peers) - 1;
-					uint32_t t = 0;
-					if (lane == leader) t = atomicAdd(&s_lcnt[lev], (uint32_t)__popc(peers));
-					t = __shfl_sync(peers, t, leader);
-					rec = (uint32_t)p | ((uint32_t)d << 11) | (lev << 12) | ((t + (uint32_t)__popc(peers & ((1u << lane) - 1u))) << 17);
-				}
-				erec[je++] = rec;
-			}
-		}
-		__syncthreads();
-		if (warp == 0) {   // exclusive prefix over the (at most 33) level counters
-			const uint32_t c0 = s_lcnt[lane], c1 = (lane < 4) ? s_lcnt[32 + lane] : 0u;
-			uint32_t v = c0;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += t; }
-			const uint32_t tot32 = __shfl_sync(0xFFFFFFFFu, v, 31);
-			__syncwarp();
-			s_lcnt[lane] = v - c0;
-			if (lane == 0) { s_lcnt[32] = tot32; s_lcnt[33] = tot32 + c1; }
-		}
-		__syncthreads();
-		ERT_PHASE(2);
-#pragma unroll
-		for (int k = 0; k < EPL; k++) {
-			const uint32_t rec = erec[k];
-			if (rec != 0xFFFFFFFFu) sorted[s_lcnt[(rec >> 12) & 31u] + (rec >> 17)] = (uint16_t)(rec & 0xFFFu);
-		}
-		__syncthreads();
-		{
-			const int lo = (int)s_minlvl, hi_l = (int)s_maxlvl;
-			for (int l = lo; l <= hi_l; ++l) {
-				const uint32_t b0 = s_lcnt[l], n_l = s_lcnt[l + 1] - b0;
-				if (n_l == 0) continue;                               // uniform: every thread reads the same counters
-				for (uint32_t i = tid; i < n_l; i += NT) {
-					const uint32_t e = sorted[b0 + i];
-					uint32_t a = e & 2047u, b = a + ((e >> 11) ? (uint32_t)TW : 1u);
-					for (int guard = 0; guard < (1 << 16); ++guard) {
-						// find with path halving on the connectivity forest
-						for (;;) { const uint32_t p1 = zpar[a]; if (p1 == a) break; const uint32_t g = zpar[p1]; if (g == p1) { a = p1; break; } zpar[a] = g; a = g; }
-						for (;;) { const uint32_t p1 = zpar[b]; if (p1 == b) break; const uint32_t g = zpar[p1]; if (g == p1) { b = p1; break; } zpar[b] = g; b = g; }
-						if (a == b) break;
-						const uint32_t la = lvl[a], lb = lvl[b];
-						uint32_t w, sdn;
-						if (la > lb || (la == lb && a > b)) { w = a; sdn = b; } else { w = b; sdn = a; }
-						if (atomicCAS(const_cast<uint32_t *>(&zpar[sdn]), sdn, w) == sdn) { par[sdn] = ((uint32_t)lvl[w] << 16) | w; break; }
-					}
-				}
-				__syncthreads();
-			}
-		}
-		ERT_PHASE(3);
-	} }
-	if (!KRUSKAL && local_union) {
+	if (local_union) {
 		for (int seg = warp; seg < SEGS; seg += NWARP) {
 			const int p = seg * 32 + lane;
 			const int y = p / TW, x = p % TW;
@@ -903,7 +812,7 @@ int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 
 // tile configurations (selectable at run time for tuning; id 0 is the default)
 struct TileCfg { int tw, th, nt; };
-static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {128, 32, 512}, {32, 32, 256}, {64, 32, 512}, {64, 32, 512}, {64, 32, 256}};
+static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {128, 32, 512}, {32, 32, 256}, {64, 32, 512}};
 int tile_config_count() { return (int)(sizeof(g_tile_cfgs) / sizeof(g_tile_cfgs[0])); }
 size_t ring_words_per_plane(int W, int H)
 {
@@ -915,14 +824,14 @@ size_t ring_words_per_plane(int W, int H)
 	return m;
 }
 
-template <int TW, int TH, int NT, int RF, bool CHUNK, bool KRUSKAL = false>
+template <int TW, int TH, int NT, int RF, bool CHUNK>
 static int launch_tile(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st)
 {
 	const size_t smem = (size_t)TW * TH * (1 + 5 * 4 + 2);
-	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TW, TH, NT, RF, CHUNK, KRUSKAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build<TW, TH, NT, RF, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const int tiles_x = (P.W + TW - 1) / TW, tiles_y = (P.H + TH - 1) / TH;
 	dim3 grid(tiles_x * tiles_y, P.n_planes);
-	k_tile_build<TW, TH, NT, RF, CHUNK, KRUSKAL><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union, wk.prof,
+	k_tile_build<TW, TH, NT, RF, CHUNK><<<grid, NT, smem, st>>>(P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, local_union, wk.prof,
 	                                                 local_union ? wk.ring_rec : nullptr);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
@@ -971,8 +880,6 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	case 2: rc = launch_tile<128, 32, 512, 8, true>(P, d_planes, wk, local_union, st); break;
 	case 3: rc = launch_tile<32, 32, 256, 8, true>(P, d_planes, wk, local_union, st); break;
 	case 4: rc = launch_tile<64, 32, 512, 12, false>(P, d_planes, wk, local_union, st); break;   // shared work queue instead of per-warp shares
-	case 5: rc = launch_tile<64, 32, 512, 8, true, true>(P, d_planes, wk, local_union, st); break;   // level-ordered (Kruskal) union phase
-	case 6: rc = launch_tile<64, 32, 256, 8, true, true>(P, d_planes, wk, local_union, st); break;
 	default: rc = launch_tile<64, 32, 512, 8, true>(P, d_planes, wk, local_union, st); break;
 	}
 	if (rc) return rc;

@@ -9,7 +9,7 @@ from ertext import synth
 frames = synth.s_text_batch(1234, 8)
 e = ertext.ErText()
 ref = None
-names = ["64x32x512", "64x32x256", "128x32x512", "32x32x256", "64x32x512-queue", "64x32x512-kruskal", "64x32x256-kruskal"]
+names = ["64x32x512", "64x32x256", "128x32x512", "32x32x256", "64x32x512-queue"]
 only = [int(a) for a in sys.argv[1:]] or list(range(len(names)))
 e.phase_cycles(True)
 for cfg in only:
