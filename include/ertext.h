@@ -171,6 +171,9 @@ ERT_API int ert_enqueue_host(ert_ctx *ctx, const uint8_t *bgr, int n_frames, int
  * fetched (one stream sync + small D2H) by ert_fetch_result. */
 ERT_API int ert_detect_classify_device(ert_ctx *ctx, const void *d_bgr, int n_frames, int width, int height, int stride_bytes, int upto);
 ERT_API int ert_fetch_result(ert_ctx *ctx, const ert_result **out);
+/* non-blocking: 1 = the batch enqueued last on this context has finished (ert_fetch_result will not wait),
+ * 0 = still running, -1 = nothing in flight */
+ERT_API int ert_batch_done(ert_ctx *ctx);
 
 /* ERFilter::compute_channels(src, YCrCb, channels)  (src/ER.cpp:114-128): BGR -> the six 8-bit planes
  * Y, Cr, Cb, 255-Y, 255-Cr, 255-Cb (OpenCV's 8-bit BGR2YCrCb arithmetic), written to planes6 as six
@@ -239,6 +242,9 @@ ERT_API int ert_ocr_features_plane(ert_ctx *ctx, const uint8_t *plane, int width
 /* use an external CUDA stream (cudaStream_t as integer, e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */
 ERT_API int ert_set_stream(ert_ctx *ctx, uint64_t cuda_stream);
 ERT_API uint64_t ert_get_stream(ert_ctx *ctx);
+/* page-locked host memory for frame staging: ert_enqueue_host copies asynchronously only from pinned memory */
+ERT_API void *ert_host_alloc(size_t bytes);
+ERT_API void ert_host_free(void *p);
 /* number of kernel launches issued by the last batch call (bench's gpu_launches) */
 ERT_API int ert_last_launch_count(ert_ctx *ctx);
 /* device-side benchmark helpers for the classifier sweeps (inputs generated/resident on device):

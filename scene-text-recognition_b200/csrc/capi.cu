@@ -607,6 +607,16 @@ int ert_detect_classify_device(ert_ctx *c, const void *d_bgr, int n_frames, int 
 
 int ert_fetch_result(ert_ctx *c, const ert_result **out) { return finish_result(c, out); }
 
+int ert_batch_done(ert_ctx *c)
+{
+	if (!c || !c->pending) return -1;
+	const cudaError_t e = cudaEventQuery(c->track_pending ? c->ev[11] : c->ev[5]);
+	if (e == cudaSuccess) return 1;
+	if (e == cudaErrorNotReady) return 0;
+	set_error("cudaEventQuery: %s", cudaGetErrorString(e));
+	return -1;
+}
+
 int ert_compute_channels(ert_ctx *c, const uint8_t *bgr, int W, int H, int stride, uint8_t *planes6)
 {
 	if (!c || !bgr || !planes6 || W < 1 || H < 1 || stride < 3 * W) { set_error("bad arguments"); return -1; }

@@ -214,6 +214,14 @@ void free_next(ert_ctx *c)
 
 extern "C" {
 
+void *ert_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+	return p;
+}
+void ert_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 int ert_er_track(ert_ctx *c, const ert_track_result **out)
 {
 	if (!c) { set_error("bad arguments"); return -1; }

@@ -82,7 +82,7 @@ class OcrResult:
 
 
 EXPORTS = [
-    "ert_set_tile_fifo", "ert_er_track", "ert_er_track_regions", "ert_ocr_chain_run_batch", "ert_ocr_chain_run_plane", "ert_ocr_features_plane",
+    "ert_set_tile_fifo", "ert_host_alloc", "ert_host_free", "ert_batch_done", "ert_er_track", "ert_er_track_regions", "ert_ocr_chain_run_batch", "ert_ocr_chain_run_plane", "ert_ocr_features_plane",
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
     "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
     "ert_load_svm", "ert_svm_nr_class", "ert_set_svm_tensor_cores", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
@@ -138,6 +138,10 @@ def load_library():
     L.ert_last_launch_count.argtypes = [C.c_void_p]
     L.ert_bench_cascade_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _f64p]
     L.ert_bench_svm_u8.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _f64p]
+    L.ert_batch_done.argtypes = [C.c_void_p]
+    L.ert_host_alloc.restype = C.c_void_p
+    L.ert_host_alloc.argtypes = [C.c_size_t]
+    L.ert_host_free.argtypes = [C.c_void_p]
     TP = C.POINTER(C.POINTER(ErtTrackResult))
     L.ert_er_track.argtypes = [C.c_void_p, TP]
     L.ert_er_track_regions.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, TP]

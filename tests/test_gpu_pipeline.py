@@ -272,3 +272,39 @@ def test_batch_equals_frame_by_frame_and_all_tile_shapes_agree(ert):
             assert [(p.nodes.tobytes(), p.pool.tobytes(), p.label.tobytes()) for p in r.planes] == sig, cfg
     finally:
         ert.set_tile_config(0)
+
+
+def test_cpp_frame_pipeline_streams_frames_in_order(ert, golden_frames, tmp_path):
+    """host/FramePipeline.hpp (the C++ streaming runtime: pinned staging, batches, several contexts round-robin) returns
+    per-frame regions in push order, identical to one-shot calls through the binding -- incl. a partial last batch."""
+    import subprocess, os
+    import ertext
+    from conftest import ROOT, PKG
+    exe = str(tmp_path / "stream_demo")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", os.path.join(ROOT, "tests", "cpp", "stream_demo.cpp"), "-o", exe,
+                           "-L", PKG, "-l:libertext.so", "-Wl,-rpath," + PKG])
+    (tmp_path / "frames.raw").write_bytes(golden_frames.tobytes())
+    assets = os.path.join(ROOT, "assets", "classifier")
+    out = subprocess.run([exe, str(tmp_path / "frames.raw"), "3", "640", "480", "22", "4", "3",
+                          os.path.join(assets, "strong.classifier"), os.path.join(assets, "weak.classifier")],
+                         capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.strip().splitlines()]
+    fl = [l for l in lines if l[0] == "F"]
+    assert [int(l[1]) for l in fl] == list(range(22))                 # every frame once, in push order
+    res = ert.detect_classify(golden_frames, upto=ertext.STAGE_TRACK)
+    tracks, _ = ert.er_track()
+    exp = []
+    for f in range(3):
+        pls = res.planes[6 * f: 6 * f + 6]
+        h = 1469598103934665603
+        for i in tracks[f].tracked:
+            c = tracks[f].cand[i]
+            for v in (c["plane"], c["x"], c["y"], c["center_x"], c["center_y"]):
+                h = ((h ^ (int(v) & 0xffffffff)) * 1099511628211) & 0xffffffffffffffff
+        exp.append([str(sum(len(p.pool) for p in pls)), str(sum(int((p.label == 2).sum()) for p in pls)),
+                    str(sum(int((p.label == 1).sum()) for p in pls)), str(len(tracks[f].tracked)), str(h)])
+    for l in fl:
+        assert [l[3], l[5], l[7], l[9], l[11]] == exp[int(l[1]) % 3], l
+    done = [l for l in lines if l[0] == "DONE"][0]
+    assert int(done[2]) == 22
