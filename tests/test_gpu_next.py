@@ -227,3 +227,49 @@ def test_er_track_and_ocr_at_bench_size(ert, ref):
     ev = np.array(exp_val)
     assert (np.floor(o.value) == np.floor(ev)).all()
     assert np.allclose(o.value - np.floor(o.value), ev - np.floor(ev), rtol=1e-4, atol=1e-9)
+
+
+def test_next_rows_properties_at_full_size(ert):
+    """Size-independent properties on 1080p frames (no oracle needed): results do not depend on where a frame sits in the
+    batch, on the order / composition of an OCR batch, on presenting a crop alone or inside its plane; the tracked SET is
+    the closure from the strong seeds, so it is invariant under any reordering of the weak list."""
+    import ertext
+    from ertext import synth
+    frames = synth.s_text_batch(777, 3, 1920, 1080)
+    ert.detect_classify(frames, upto=ertext.STAGE_TRACK)
+    tr_a, _ = ert.er_track()
+    perm = [2, 0, 1]
+    ert.detect_classify(frames[perm], upto=ertext.STAGE_TRACK)
+    tr_b, _ = ert.er_track()
+    for i, f in enumerate(perm):                                      # frame position in the batch is irrelevant
+        assert tr_b[i].cand.tobytes() == tr_a[f].cand.tobytes() and (tr_b[i].tracked == tr_a[f].tracked).all()
+    # er_track on caller lists: shuffle the weak rows inside each channel -> same tracked set, same colours per region
+    ft = tr_a[0]
+    ns = ft.n_strong
+    rows = np.stack([ft.cand["plane"], ft.cand["x"], ft.cand["y"], ft.cand["w"], ft.cand["h"], ft.cand["area"]], axis=1).astype(np.int32)
+    S, Wk = rows[:ns], rows[ns:]
+    rng = np.random.RandomState(1)
+    order = np.lexsort((rng.rand(len(Wk)), Wk[:, 0]))                 # random inside a channel, channel-major overall
+    ft2 = ert.er_track_regions(frames[0], S, Wk[order])
+    key = lambda c: (int(c["plane"]), int(c["x"]), int(c["y"]), int(c["w"]), int(c["h"]), int(c["area"]), int(c["label"]))
+    assert sorted(key(ft.cand[i]) for i in ft.tracked) == sorted(key(ft2.cand[i]) for i in ft2.tracked)
+    col = lambda t: {key(c): (c["color1"], c["color2"], c["color3"]) for c in t.cand}
+    assert col(ft) == col(ft2)
+    # OCR: batch order / composition, and crop-alone vs crop-in-plane
+    ert.detect_classify(frames)
+    c = ft.cand[ft.tracked][:48]
+    fr = np.zeros(len(c), np.int32)
+    rc = np.stack([c["x"], c["y"], c["w"], c["h"]], axis=1).astype(np.int32)
+    sl = np.where(np.arange(len(c)) % 3 == 1, 0.12, 0.0)
+    o1 = ert.ocr_chain_run_batch(fr, c["plane"], rc, sl)
+    p2 = rng.permutation(len(c))
+    o2 = ert.ocr_chain_run_batch(fr[p2], c["plane"][p2], rc[p2], sl[p2])
+    assert (o2.feat == o1.feat[p2]).all() and (o2.value == o1.value[p2]).all()
+    o3 = ert.ocr_chain_run_batch(fr[:5], c["plane"][:5], rc[:5], sl[:5])
+    assert (o3.feat == o1.feat[:5]).all() and np.allclose(o3.value, o1.value[:5], rtol=1e-12, atol=0)
+    planes = ert.compute_channels(frames[0])
+    for i in range(6):
+        k, (x, y, w, h) = int(c["plane"][i]), rc[i]
+        alone = np.ascontiguousarray(planes[k][y:y + h, x:x + w])
+        oa = ert.ocr_features_plane(alone, [(0, 0, w, h)], [sl[i]])
+        assert (oa.feat[0] == o1.feat[i]).all() and (oa.img[0] == o1.img[i]).all()
