@@ -21,6 +21,11 @@
 # and for the rows that follow the detect path (checked by tests/test_*next*.py):
 #   ER.cpp   532-609   ERFilter::er_track
 #            1391-1437 calc_color
+#            612-692   ERFilter::er_grouping
+#            893-964   ERFilter::inner_suppression, overlap_suppression
+#            1361-1389 fitline_avgslope
+#            702-724   the duplicate-removal loop body of ERFilter::er_ocr (emitted as an include fragment, ref_er_ocr_dedupe.inc,
+#                      which ref_capi_next.cpp wraps in the loop header of src/ER.cpp:700-701)
 #   OCR.cpp  4-15      enum category, table[], cat[]
 #            18-21     OCR::OCR(model, img_L, feature_L)
 #            67-140    OCR::chain_run
@@ -38,10 +43,11 @@ fi
 mkdir -p "$OUT"
 {
 	echo '#include "ER.h"'
-	sed -n '6,10p;14,30p;131,233p;240,413p;416,528p;532,609p;789,845p;1391,1437p' "$REF/src/ER.cpp"
+	sed -n '6,10p;14,30p;131,233p;240,413p;416,528p;532,609p;612,692p;789,845p;893,964p;1361,1389p;1391,1437p' "$REF/src/ER.cpp"
 	sed -n '4,15p;18,21p;67,140p;144,250p;254,360p;394,430p;602,622p' "$REF/src/OCR.cpp"
 } > "$OUT/ref_hotpath.cpp"
-g++ -std=c++11 -O2 -fopenmp -fPIC -shared -w \
+sed -n '702,724p' "$REF/src/ER.cpp" > "$OUT/ref_er_ocr_dedupe.inc"
+g++ -std=c++11 -O2 -fopenmp -fPIC -shared -w -I "$OUT" \
 	-I "$HERE/cvshim" -I "$REF/inc" \
 	"$OUT/ref_hotpath.cpp" "$REF/src/adaboost.cpp" "$REF/src/svm.cpp" "$HERE/ref_capi.cpp" "$HERE/ref_capi_next.cpp" \
 	-o "$OUT/libref_oracle.so"

@@ -60,6 +60,19 @@ inline Rect operator&(const Rect &a, const Rect &b)
 	return Rect(x1, y1, x2 - x1, y2 - y1);
 }
 
+// cv::Rect | cv::Rect: bounding box of both; an empty operand is ignored (OpenCV's operator|=)
+inline Rect operator|(const Rect &a, const Rect &b)
+{
+	if (a.width <= 0 || a.height <= 0) return b;
+	if (b.width <= 0 || b.height <= 0) return a;
+	const int x1 = std::min(a.x, b.x), y1 = std::min(a.y, b.y);
+	const int x2 = std::max(a.x + a.width, b.x + b.width), y2 = std::max(a.y + a.height, b.y + b.height);
+	return Rect(x1, y1, x2 - x1, y2 - y1);
+}
+inline Rect &operator|=(Rect &a, const Rect &b) { a = a | b; return a; }
+inline Point operator-(const Point &a, const Point &b) { return Point(a.x - b.x, a.y - b.y); }
+inline double norm(const Point &p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y); }
+
 namespace flann { struct Index { Index() {} }; }
 
 class Mat {

@@ -148,6 +148,50 @@ int ref_er_track(void *ctx, const uchar *planes6, const uchar *ycrcb, int w, int
 	return (int)all_er.size();
 }
 
+// ---- ERFilter::er_grouping (src/ER.cpp:612-692) + the duplicate removal at the head of er_ocr (src/ER.cpp:702-724) ---
+// in:  all_er as rows of 11 doubles: ch, x, y, w, h, area, center_x, center_y, color1, color2, color3 (what er_track left)
+// out: n_after / after[] = all_er after the call (indices into the input; inner_suppression erases),
+//      bounds[] = every input ER's bound and centre afterwards (x, y, w, h, cx, cy; overlap_suppression edits them in place),
+//      text_off[] / text_ers[] / text_slope[] = the Text groups (members as input indices, in the group's final order).
+// dedupe != 0 additionally runs the reference's per-text duplicate removal (er_ocr's first step) on every group.
+int ref_er_grouping(void *ctx, const double *rows, int n, int overlap_sup, int inner_sup, int dedupe, int *n_after, int *after, int *bounds,
+                    int *text_off, int *text_ers, int text_ers_cap, double *text_slope, int text_cap)
+{
+	RefCtxView *c = (RefCtxView *)ctx;
+	std::vector<ER> E((size_t)n);
+	ERs all_er;
+	for (int i = 0; i < n; i++) {
+		const double *r = rows + 11 * i;
+		E[i] = ER(0, 0, 0, 0);
+		E[i].ch = (int)r[0]; E[i].bound = cv::Rect((int)r[1], (int)r[2], (int)r[3], (int)r[4]); E[i].area = (int)r[5];
+		E[i].center = cv::Point((int)r[6], (int)r[7]); E[i].color1 = r[8]; E[i].color2 = r[9]; E[i].color3 = r[10];
+		all_er.push_back(&E[i]);
+	}
+	vector<Text> text;
+	c->erf->er_grouping(all_er, text, overlap_sup != 0, inner_sup != 0);
+	if (dedupe) {
+		for (int i = (int)text.size() - 1; i >= 0; i--)          // the loop header of src/ER.cpp:700-701
+		{
+#include "ref_er_ocr_dedupe.inc"
+		}
+	}
+	*n_after = (int)all_er.size();
+	for (size_t i = 0; i < all_er.size(); i++) after[i] = (int)(all_er[i] - &E[0]);
+	for (int i = 0; i < n; i++) {
+		int *b = bounds + 6 * i;
+		b[0] = E[i].bound.x; b[1] = E[i].bound.y; b[2] = E[i].bound.width; b[3] = E[i].bound.height; b[4] = E[i].center.x; b[5] = E[i].center.y;
+	}
+	int k = 0;
+	if ((int)text.size() > text_cap) return -1;
+	for (size_t t = 0; t < text.size(); t++) {
+		text_off[t] = k;
+		text_slope[t] = text[t].slope;
+		for (size_t j = 0; j < text[t].ers.size(); j++) { if (k >= text_ers_cap) return -1; text_ers[k++] = (int)(text[t].ers[j] - &E[0]); }
+	}
+	text_off[text.size()] = k;
+	return (int)text.size();
+}
+
 // ---- OCR::chain_run (src/OCR.cpp:67-140) -------------------------------------------------------------
 // the verbatim call: returns table[label] + prob[label]
 double ref_chain_run(void *ctx, const uchar *crop, int w, int h, int stride, int thresh, double slope)

@@ -79,6 +79,7 @@ class RefOracle:
         L.ref_prim_normalize_minmax.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
         L.ref_calc_color.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _i32p, C.c_int, _f64p]
         L.ref_er_track.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _i32p, _f64p, _f64p, _i32p, _i32p]
+        L.ref_er_grouping.argtypes = [C.c_void_p, _f64p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, C.c_int, _f64p, C.c_int]
         L.ref_chain_run.restype = C.c_double
         L.ref_chain_run.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
         L.ref_ocr_features.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_double, _u8p, _u8p]
@@ -224,6 +225,23 @@ class RefOracle:
         m = self.L.ref_er_track(self.ctx, _p(planes6, _u8p), _p(ycrcb, _u8p), w, h, _p(strong, _i32p), ns, _p(weak, _i32p), nw,
                                 _p(tr, _i32p), _p(sc, _f64p), _p(wc, _f64p), _p(sce, _i32p), _p(wce, _i32p))
         return dict(tracked=tr[:m].copy(), strong_color=sc[:ns], weak_color=wc[:nw], strong_center=sce[:ns], weak_center=wce[:nw])
+
+    def er_grouping(self, rows, overlap_sup=False, inner_sup=True, dedupe=False):
+        """ERFilter::er_grouping (src/ER.cpp:612-692) [+ er_ocr's duplicate removal, src/ER.cpp:702-724].  rows [n,11] =
+        ch, x, y, w, h, area, cx, cy, color1..3.  Returns dict(after = all_er afterwards (input indices), bounds [n,6] =
+        x, y, w, h, cx, cy afterwards, texts = [(slope, [input indices])])."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 11)
+        n = len(rows)
+        n_after = C.c_int32(0)
+        after = np.zeros(n + 1, np.int32); bounds = np.zeros((n + 1, 6), np.int32)
+        tcap, ecap = 4 * n + 4, 64 * n + 64
+        toff = np.zeros(tcap + 1, np.int32); ters = np.zeros(ecap, np.int32); tsl = np.zeros(tcap, np.float64)
+        nt = self.L.ref_er_grouping(self.ctx, _p(rows, _f64p), n, int(overlap_sup), int(inner_sup), int(dedupe), C.byref(n_after), _p(after, _i32p),
+                                    _p(bounds, _i32p), _p(toff, _i32p), _p(ters, _i32p), ecap, _p(tsl, _f64p), tcap)
+        if nt < 0:
+            raise ValueError("er_grouping output capacity exceeded")
+        texts = [(float(tsl[t]), ters[toff[t]:toff[t + 1]].tolist()) for t in range(nt)]
+        return dict(after=after[:n_after.value].tolist(), bounds=bounds[:n].copy(), texts=texts)
 
     def chain_run(self, crop, thresh=0, slope=0.0):
         """OCR::chain_run verbatim (src/OCR.cpp:67-140): returns table[label] + prob[label]."""

@@ -201,6 +201,35 @@ def test_cpp_facade_like_the_reference_callers(ert, port, golden_frames, tmp_pat
     assert len(ocr) == len(sel)
     for i, l in enumerate(ocr):
         assert l[1] == chr(int(np.floor(r.value[i]))) and abs(float(l[2]) - (r.value[i] - np.floor(r.value[i]))) < 1e-6
+    # text_detect -> er_grouping -> er_ocr letters through the facade == the same chain on the reference's own code
+    try:
+        from oracle.refbind import RefOracle
+        ref = RefOracle(with_svm=True)
+    except (FileNotFoundError, OSError):
+        return
+    cand = ft.cand[ft.tracked]
+    rows = np.stack([cand[k].astype(np.float64) for k in ("plane", "x", "y", "w", "h", "area", "center_x", "center_y", "color1", "color2", "color3")], axis=1)
+    g = ref.er_grouping(rows, False, True, dedupe=True)
+    exp = []
+    for slope, members in g["texts"]:
+        ers = []
+        for m in members:
+            ch = int(rows[m, 0]); x, y, w, h = [int(v) for v in g["bounds"][m, :4]]
+            v = ref.chain_run(planes[ch][y:y + h, x:x + w], 0, slope)
+            if v - np.floor(v) >= 0.15:
+                ers.append((ch, x, y, w, h, chr(int(np.floor(v))), v - np.floor(v)))
+        if len(ers) >= 2:
+            exp.append((slope, ers))
+    got = []
+    for l in lines:
+        if l.startswith("TXT"):
+            t = l.split()
+            got.append((float(t[1]), [tuple(e.split(":")) for e in t[2:]]))
+    assert len(got) == len(exp) and len(exp) >= 1
+    for (s1, e1), (s2, e2) in zip(got, exp):
+        assert s1 == s2 and len(e1) == len(e2)
+        for a, b in zip(e1, e2):
+            assert tuple(int(v) for v in a[:5]) == b[:5] and a[5] == b[5] and abs(float(a[6]) - b[6]) <= 1e-4 * b[6] + 1e-6
 
 
 def test_4k_three_plane_four_scale_pyramid(ert, port):
