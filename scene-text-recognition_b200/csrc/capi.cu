@@ -144,7 +144,8 @@ int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 	if (hmalloc(&c->h_node_off, (size_t)P + 1) || hmalloc(&c->h_pool_off, (size_t)P + 1)) return -1;
 	if (hmalloc(&c->h_nodes, (size_t)P * c->kept_cap) || hmalloc(&c->h_pool, (size_t)P * c->pool_cap)) return -1;
 	if (hmalloc(&c->h_label, (size_t)P * c->pool_cap) || hmalloc(&c->h_ss, (size_t)P * c->pool_cap) || hmalloc(&c->h_ws, (size_t)P * c->pool_cap)) return -1;
-	if (hmalloc(&c->h_hist, (size_t)P * c->pool_cap * 1024) || hmalloc(&c->h_status, 1)) return -1;
+	// the pooled-region histograms travel to the host only on request: 1 KB per region, 100 MB of pinned memory at the defaults
+	if (hmalloc(&c->h_hist, c->return_hist ? (size_t)P * c->pool_cap * 1024 : 1) || hmalloc(&c->h_status, 1)) return -1;
 	c->planes_cap = P; c->cap_np = cap_np; c->cap_ycc = cap_ycc; c->cap_ring = cap_ring;
 	return 0;
 }
@@ -359,7 +360,12 @@ int ert_set_thresh_step(ert_ctx *c, int step)
 	c->prm.thresh_step = step; return 0;
 }
 int ert_set_min_area(ert_ctx *c, int m) { c->prm.min_area = m; return 0; }
-int ert_set_return_hist(ert_ctx *c, int on) { c->return_hist = on; return 0; }
+int ert_set_return_hist(ert_ctx *c, int on)
+{
+	if (on && !c->return_hist && c->planes_cap) { cudaStreamSynchronize(c->stream); free_workspace(c); }   // re-allocate with the host histogram buffer
+	c->return_hist = on;
+	return 0;
+}
 int ert_set_tile_fifo(ert_ctx *c, int on) { c->tile_fifo = on ? 1 : 0; return 0; }
 int ert_set_tile_local_union(ert_ctx *c, int on) { c->local_union = on ? 1 : 0; return 0; }
 int ert_debug_phase_cycles(ert_ctx *c, int enable, unsigned long long *out16)
