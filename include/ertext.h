@@ -137,6 +137,9 @@ ERT_API int ert_set_min_area(ert_ctx *ctx, int min_area);
 ERT_API int ert_set_return_hist(ert_ctx *ctx, int on);
 /* option (debug / A-B): 0 = skip the shared-memory tile pass and link every edge in global memory */
 ERT_API int ert_set_tile_local_union(ert_ctx *ctx, int on);
+/* audit / A-B: 1 = non_maximum_supression's walk on ONE thread per plane, literally as the reference orders it;
+ * 0 (default) = the level-parallel statement of the same result (er_nms.cu).  Pools are identical either way. */
+ERT_API int ert_set_nms_sequential(ert_ctx *ctx, int on);
 /* scheduling: 1 (default) = the tile-build kernels of all contexts on a device run in submission order (an event
  * chain); keeps the oldest batch in flight from being starved when several contexts are used round-robin */
 ERT_API int ert_set_tile_fifo(ert_ctx *ctx, int on);

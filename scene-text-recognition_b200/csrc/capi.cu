@@ -187,6 +187,7 @@ NmsParams make_nms_params(const ert_ctx *c, int W, int H)
 	P.kept_cap = c->kept_cap; P.pool_cap = c->pool_cap;
 	P.min_area = c->prm.min_area; P.max_area = c->prm.max_area; P.stability_t = c->prm.stability_t;
 	P.overlap_coef = c->prm.overlap_coef;
+	P.sequential_walk = c->nms_sequential;
 	return P;
 }
 
@@ -366,6 +367,7 @@ int ert_set_return_hist(ert_ctx *c, int on)
 	c->return_hist = on;
 	return 0;
 }
+int ert_set_nms_sequential(ert_ctx *c, int on) { c->nms_sequential = on ? 1 : 0; return 0; }
 int ert_set_tile_fifo(ert_ctx *c, int on) { c->tile_fifo = on ? 1 : 0; return 0; }
 int ert_set_tile_local_union(ert_ctx *c, int on) { c->local_union = on ? 1 : 0; return 0; }
 int ert_debug_phase_cycles(ert_ctx *c, int enable, unsigned long long *out16)

@@ -74,6 +74,7 @@ struct ert_ctx {
 	bool own_stream = true;
 	cudaEvent_t ev[12];
 	int local_union = 1;
+	int nms_sequential = 0;  // 1: run the reference's walk on one thread per plane (audit / A-B) instead of the level-parallel form
 	int tile_fifo = 1;       // chain the tile kernels of all contexts on the device in submission order
 	int tile_cfg = 0;
 	int return_hist = 0;

@@ -12,10 +12,24 @@
 // that order is used verbatim.
 //
 // Steps: (1) load the kept list, resolve parent positions; (2) bitonic sort by (parent, sibling
-// key) so every child list is contiguous and ordered; (3) one thread runs the reference's
-// sequential post-order walk out of shared memory (arithmetic in IEEE double exactly as the
-// reference: overlap = area(bbox∩)/area(parent bbox) > coef, stability = a_i / (a_{i+T} - a_i));
-// (4) all threads scatter nodes into DFS pre-order (the oracle's dump order) and the pool.
+// key) so every child list is contiguous and ordered; (3) the reference's post-order walk with its
+// `done` chains (arithmetic in IEEE double exactly as the reference: overlap = area(bbox∩) /
+// area(parent bbox) > coef, stability = a_i / (a_{i+T} - a_i)); (4) all threads scatter nodes into
+// DFS pre-order (the oracle's dump order) and the pool.
+//
+// Step (3) exists twice.  The reference's walk is sequential, but its RESULT has a parallel statement:
+// every node ends up in exactly one chain (the one that marked it done); a chain is a contiguous piece
+// of a root path that starts at the node D visited first; the chain that owns a child c is the only one
+// that can continue into its parent p, it does so when D is visited (long before p), and if several
+// children's chains qualify the one visited first wins.  Hence
+//     owner(p) = owner(c*)  with c* = the FIRST child in visiting order whose owner passes the overlap
+//                test against p,            owner(p) = p if there is none,
+// a bottom-up recurrence over the tree levels (a parent's level is strictly higher than its children's).
+// Chains are then evaluated independently (one thread per chain start), and the pool order -- the order
+// in which the walk meets the chain starts -- is the post-order index of the start, which follows from
+// subtree sizes and a prefix sum.  The one-thread walk is kept for trees whose levels do not increase
+// towards the root (caller-supplied nodes), for overlap_coef >= 1, and as an audit path
+// (ert_set_nms_sequential); tests run both and require identical pools.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -74,6 +88,36 @@ __device__ __forceinline__ bool overlap_exceeds(int inter, int parea, double coe
 	return a / (double)parea > coef;
 }
 
+// exclusive prefix sum of a[0..n) in place; returns the total.  Every thread of the CTA must call it.
+template <int NT>
+__device__ int block_exclusive_scan(int32_t *a, int n, int32_t *s_warp /* [NT/32 + 1] shared */)
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int C = (n + NT - 1) / NT;
+	const int b = min(n, tid * C), e = min(n, b + C);
+	int sum = 0;
+	for (int i = b; i < e; i++) sum += a[i];
+	int inc = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		const int w = (lane < NT / 32) ? s_warp[lane] : 0;
+		int winc = w;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, winc, o); if (lane >= o) winc += t; }
+		if (lane < NT / 32) s_warp[lane] = winc - w;
+		if (lane == NT / 32 - 1) s_warp[NT / 32] = winc;
+	}
+	__syncthreads();
+	int run = s_warp[warp] + inc - sum;
+	for (int i = b; i < e; i++) { const int t = a[i]; a[i] = run; run += t; }
+	const int total = s_warp[NT / 32];
+	__syncthreads();
+	return total;
+}
+
 // in:  either the extract stage's kept list (kept != nullptr; parents given as root-pixel indices,
 //      resolved through attr[].arr) or caller nodes (in_nodes: DFS pre-order with explicit order).
 template <int NT>
@@ -86,7 +130,8 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
                                             int32_t *__restrict__ out_counts /* per plane: n_nodes, n_pool */, uint32_t *status)
 {
 	extern __shared__ __align__(16) uint8_t nms_smem[];
-	__shared__ int s_npool;
+	__shared__ int s_npool, s_lmin, s_lmax, s_bad;
+	__shared__ int32_t s_scan[NT / 32 + 1];
 	const int tid = threadIdx.x;
 	const int plane = blockIdx.x;
 	const bool from_kept = (kept != nullptr);
@@ -207,12 +252,105 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 		v.done[j] = 0;
 	}
 	__syncthreads();
+	if (tid == 0) { s_lmin = 255; s_lmax = 0; s_bad = 0; }
+	__syncthreads();
 	for (int j = tid; j < n; j += NT) {
 		const int p = v.parent[j];
 		if (p >= 0 && (j == 0 || v.parent[j - 1] != p)) v.first[p] = j;
+		const int lj = v.level[j];
+		atomicMin(&s_lmin, lj); atomicMax(&s_lmax, lj);
+		if ((p >= 0 && v.level[p] <= lj) || (p < 0 && j != 0)) s_bad = 1;   // not a level-ordered single tree: use the walk
 	}
 	__syncthreads();
+	const bool parallel_walk = !P.sequential_walk && !s_bad && P.overlap_coef < 1.0;
 
+	if (parallel_walk) {
+		// ---- (4p) level-parallel statement of the walk's result (see the header) ----
+		int32_t *owner = reinterpret_cast<int32_t *>(v.keyA);     // chain start that owns the node   (sort keys are dead now)
+		int32_t *size = owner + n2;                               // subtree size
+		int32_t *fpass = reinterpret_cast<int32_t *>(v.keyB);     // first child whose chain continues into this node; later: pool marks
+		int32_t *S = reinterpret_cast<int32_t *>(v.ord);          // prefix sums
+		int32_t *depth = v.newpos;
+		const int T = P.stability_t;
+		const int lmin = s_lmin, lmax = s_lmax;
+		for (int j = tid; j < n; j += NT) { size[j] = 1; fpass[j] = 0x7FFFFFFF; }
+		__syncthreads();
+		for (int L = lmin; L <= lmax; ++L) {                      // bottom-up: children (lower levels) are final
+			for (int j = tid; j < n; j += NT) {
+				if (v.level[j] != L) continue;
+				const int fp = fpass[j];
+				const int o = (fp != 0x7FFFFFFF) ? owner[fp] : j;
+				owner[j] = o;
+				const int p = v.parent[j];
+				if (p >= 0) {
+					atomicAdd(&size[p], size[j]);
+					// the test the walk makes when the chain started at o, having taken j, looks at p (src/ER.cpp:457)
+					if (overlap_exceeds(bb_inter(&v.bx[4 * o], &v.bx[4 * p]), bb_area(&v.bx[4 * p]), P.overlap_coef)) atomicMin(&fpass[p], j);
+				}
+			}
+			__syncthreads();
+		}
+		// DFS pre-order index and depth, top-down: pre(child) = pre(parent) + 1 + sizes of the siblings before it
+		for (int j = tid; j < n; j += NT) S[j] = size[j];
+		__syncthreads();
+		block_exclusive_scan<NT>(S, n, s_scan);
+		for (int L = lmax; L >= lmin; --L) {
+			for (int j = tid; j < n; j += NT) {
+				if (v.level[j] != L) continue;
+				const int p = v.parent[j];
+				if (p < 0) { v.pre[j] = 0; depth[j] = 0; }
+				else { v.pre[j] = v.pre[p] + 1 + (S[j] - S[v.first[p]]); depth[j] = depth[p] + 1; }
+			}
+			__syncthreads();
+		}
+		// chains: one thread per chain start; an accepted chain marks its start's POST-order slot with the chosen node
+		for (int j = tid; j < n; j += NT) fpass[j] = 0;
+		__syncthreads();
+		for (int j = tid; j < n; j += NT) {
+			if (owner[j] != j) continue;
+			int len = 0, hi = j;
+			for (int p = j; p >= 0 && owner[p] == j; p = v.parent[p]) { if (len == T) hi = p; len++; }   // hi = T-th element of the chain
+			if (len > 72) { atomicOr(status, ERR_NMS_OVERFLOW); len = 72; }
+			if (len < 1 + T) continue;
+			// stability_i = a_i / (a_{i+T} - a_i), arg-max with ties to the smaller area then the earlier element (src/ER.cpp:470-484)
+			int best = j, best_area = 0, lo = j;
+			long long bn = 0, bd = 1;
+			double best_s = 0.0;
+			const bool small = (long long)P.W * P.H < (1ll << 24);
+			for (int i = 0; i < len - T; i++) {
+				const int ai = bb_area(&v.bx[4 * lo]), aj = bb_area(&v.bx[4 * hi]);
+				if (small) {
+					const long long n_i = ai, d_i = (long long)aj - ai;
+					int cmp;
+					if (i == 0) cmp = 1;
+					else if (d_i == 0 || bd == 0) cmp = (d_i == 0 && bd == 0) ? 0 : (d_i == 0 ? 1 : -1);
+					else { const long long l = n_i * bd, r = bn * d_i; cmp = (l > r) - (l < r); }
+					if (cmp > 0 || (cmp == 0 && i > 0 && ai < best_area)) { best = lo; best_area = ai; bn = n_i; bd = d_i; }
+				} else {
+					const double sdiv = (double)ai / (double)(aj - ai);
+					if (i == 0 || sdiv > best_s || (sdiv == best_s && ai < best_area)) { best = lo; best_area = ai; best_s = sdiv; }
+				}
+				lo = v.parent[lo]; hi = v.parent[hi];
+			}
+			const int w = (int)v.bx[4 * best + 2] - (int)v.bx[4 * best] + 1, h = (int)v.bx[4 * best + 3] - (int)v.bx[4 * best + 1] + 1;
+			const double ar = (double)w / (double)h;
+			if (ar < 2.0 && ar > 0.10 && v.area[best] < P.max_area && v.area[best] > P.min_area && h < P.H * 0.8 && w < P.W * 0.8)
+				fpass[v.pre[j] - depth[j] + size[j] - 1] = best + 1;      // post-order index of the chain start
+		}
+		__syncthreads();
+		for (int j = tid; j < n; j += NT) S[j] = fpass[j] != 0;
+		__syncthreads();
+		const int total = block_exclusive_scan<NT>(S, n, s_scan);
+		for (int j = tid; j < n; j += NT) {
+			const int b = fpass[j];
+			if (b != 0 && S[j] < P.pool_cap) outp[S[j]] = v.pre[b - 1];
+		}
+		if (tid == 0) {
+			if (total > P.pool_cap) atomicOr(status, ERR_POOL_OVERFLOW);
+			s_npool = min(total, P.pool_cap);
+		}
+		__syncthreads();
+	} else {
 	// one 16-byte record per node for the sequential walk (aliases the sort keys, which are dead now):
 	// {parent, first child, x0 | y0 << 16, x1 | y1 << 16} -> one 128-bit load per visited node
 	uint4 *rec = reinterpret_cast<uint4 *>(v.keyA);
@@ -296,6 +434,7 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 		s_npool = min(npool, P.pool_cap);
 	}
 	__syncthreads();
+	}
 
 	// ---- (5) scatter into DFS pre-order ----
 	for (int j = tid; j < n; j += NT) {
@@ -311,7 +450,7 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 		outn[v.pre[j]] = o;
 	}
 	const int npool = s_npool;
-	for (int k = tid; k < npool; k += NT) outp[k] = v.pre[v.newpos[k]];
+	if (!parallel_walk) for (int k = tid; k < npool; k += NT) outp[k] = v.pre[v.newpos[k]];
 	if (tid == 0) { out_counts[2 * plane] = n; out_counts[2 * plane + 1] = npool; }
 }
 

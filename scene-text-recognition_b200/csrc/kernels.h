@@ -27,6 +27,7 @@ struct NmsParams {
 	int kept_cap, pool_cap;
 	int min_area, max_area, stability_t;
 	double overlap_coef;
+	int sequential_walk;    // 1: the one-thread walk (audit / A-B); 0: the level-parallel formulation of the same result
 };
 
 struct ClassifyParams {

@@ -82,7 +82,7 @@ class OcrResult:
 
 
 EXPORTS = [
-    "ert_set_tile_fifo", "ert_host_alloc", "ert_host_free", "ert_batch_done", "ert_er_track", "ert_er_track_regions", "ert_ocr_chain_run_batch", "ert_ocr_chain_run_plane", "ert_ocr_features_plane",
+    "ert_set_tile_fifo", "ert_set_nms_sequential", "ert_host_alloc", "ert_host_free", "ert_batch_done", "ert_er_track", "ert_er_track_regions", "ert_ocr_chain_run_batch", "ert_ocr_chain_run_plane", "ert_ocr_features_plane",
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
     "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
     "ert_load_svm", "ert_svm_nr_class", "ert_set_svm_tensor_cores", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
@@ -109,7 +109,7 @@ def load_library():
     L.ert_create.restype = C.c_void_p
     L.ert_create.argtypes = [C.POINTER(ErtParams), C.c_int]
     L.ert_destroy.argtypes = [C.c_void_p]
-    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_set_tile_fifo"):
+    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_set_tile_fifo", "ert_set_nms_sequential"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_int]
     L.ert_set_capacity.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ert_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
@@ -235,6 +235,9 @@ class ErText:
 
     def set_tile_local_union(self, on):
         self._check(self.L.ert_set_tile_local_union(self.ctx, int(on)))
+
+    def set_nms_sequential(self, on):
+        self._check(self.L.ert_set_nms_sequential(self.ctx, int(on)))
 
     def set_tile_fifo(self, on):
         self._check(self.L.ert_set_tile_fifo(self.ctx, int(on)))

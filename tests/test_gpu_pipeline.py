@@ -337,3 +337,29 @@ def test_cpp_frame_pipeline_streams_frames_in_order(ert, golden_frames, tmp_path
         assert [l[3], l[5], l[7], l[9], l[11]] == exp[int(l[1]) % 3], l
     done = [l for l in lines if l[0] == "DONE"][0]
     assert int(done[2]) == 22
+
+
+def test_nms_level_parallel_equals_the_sequential_walk(golden_frames):
+    """k_nms has two forms of the reference's walk (er_nms.cu): one thread per plane literally as the reference orders it,
+    and the level-parallel statement of its result.  Same nodes, same pool, same order -- on real frames, on the edge-case
+    planes (deep chains, thousands of siblings, lone nodes), at several MIN_AREA / stability / overlap settings."""
+    import ertext
+    from ertext import synth
+    from conftest import make_plane
+    cases = [("golden", None, golden_frames), ("1080p", None, synth.s_text_batch(99, 2, 1920, 1080))]
+    for kind in ("noise", "smooth", "blobs", "walls", "allwall", "flat", "checker", "ramp"):
+        for (h, w) in ((64, 96), (200, 333)):
+            cases.append((kind, np.stack([make_plane(5, h, w, kind), make_plane(6, h, w, kind)]), None))
+    for params in (dict(), dict(min_area=20), dict(min_area=3, stability_t=1), dict(overlap_coef=0.4, stability_t=3), dict(overlap_coef=0.95)):
+        a = ertext.ErText(**params)
+        b = ertext.ErText(**params)
+        b.set_nms_sequential(True)
+        a.set_capacity(65536, 4096); b.set_capacity(65536, 4096)
+        for name, planes, frames in cases:
+            ra = a.planes_detect(planes) if planes is not None else a.detect_classify(frames)
+            rb = b.planes_detect(planes) if planes is not None else b.detect_classify(frames)
+            assert ra.status == rb.status == 0, (name, params, ra.status, rb.status)
+            for pa, pb in zip(ra.planes, rb.planes):
+                assert pa.nodes.tobytes() == pb.nodes.tobytes(), (name, params)
+                assert pa.pool.tobytes() == pb.pool.tobytes() and pa.label.tobytes() == pb.label.tobytes(), (name, params)
+        a.close(); b.close()
