@@ -2,7 +2,7 @@
 // (reference src/ER.cpp:532-609, 1391-1437), on the device, for every frame of a batch at once.
 //
 //   k_track_gather  strong[0..5] then weak[0..5] of a frame, each in pool order -> one candidate list per frame
-//   k_calc_color    per candidate: histogram of 255 - channel over the bound, OpenCV's OTSU threshold (the FP64
+//   k_calc_color    per candidate: per-warp histograms of 255 - channel over the bound, OpenCV's OTSU threshold (the FP64
 //                   recurrence of getThreshVal_Otsu_8u evaluated in the same order, no FMA contraction), then the
 //                   mean YCrCb over the mask -- read at (row, col) counted from the IMAGE origin, not the bound's,
 //                   because that is what the reference does (color_img.ptr(i), src/ER.cpp:1404)
@@ -108,12 +108,9 @@ __global__ void __launch_bounds__(CC_THREADS) k_calc_color(TrackWork tk, const u
 				const bool in = x < w;
 				int u = 0;
 				if (in) { const int v = row[x]; u = inv ? v : 255 - v; }
-				// text crops are near-bimodal: aggregate equal values inside the warp before touching shared memory
-				const unsigned act = __ballot_sync(0xffffffffu, in);
-				if (in) {
-					const unsigned peers = __match_any_sync(act, u);
-					if (lane == __ffs(peers) - 1) atomicAdd(&hist[warp][u], __popc(peers));
-				}
+				// per-warp histogram; same-bin lanes serialise in the shared-memory atomic unit (measured faster than aggregating
+				// equal values with __match_any_sync first: 0.265 -> 0.224 ms per 8-frame batch)
+				if (in) atomicAdd(&hist[warp][u], 1);
 			}
 		}
 		__syncthreads();

@@ -108,11 +108,7 @@ __global__ void __launch_bounds__(OCR_THREADS) k_ocr_features(const OcrJob *__re
 			const bool in = x < J.w;
 			int u = 0;
 			if (in) { const int v = row[x]; u = J.invert ? v : 255 - v; }
-			const unsigned act = __ballot_sync(0xffffffffu, in);
-			if (in) {
-				const unsigned peers = __match_any_sync(act, u);
-				if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[warp][u], __popc(peers));
-			}
+			if (in) atomicAdd(&s_hist[warp][u], 1);
 		}
 	}
 	__syncthreads();
