@@ -115,3 +115,89 @@ def test_reference_reproduces_golden_ocr(ref, golden_frames, golden_next):
         # chain_run == svm_predict_probability on the visible feature vector
         lab, prob = ref.svm_predict_probability(feat[None].astype(np.float64) / 255.0)
         assert ord(TABLE[int(lab[0])]) + prob[0, int(lab[0])] == v, i
+
+
+def _cv2_chain_run_features(cv2, crop):
+    """OCR::chain_run's pre-processing + extract_feature (src/OCR.cpp:72-84, 144-218, slope 0) written with the REAL OpenCV
+    functions of python cv2 -- an end-to-end check of the reference-backed oracle (reference code + oracle/cvshim)."""
+    import math
+    _t, img = cv2.threshold(255 - crop, 128, 255, cv2.THRESH_OTSU)
+    rows, cols = img.shape
+    L = 30
+    R1 = rows / cols if cols > rows else cols / rows
+    minor = int(L * math.pow(R1, 0.5))
+    size = (L, minor) if cols > rows else (minor, L)            # cv::Size(width, height)
+    tmp = cv2.resize(img, size)
+    dst = np.zeros((L, L), np.uint8)
+    if tmp.shape[1] > tmp.shape[0]:
+        off = int(round((L - tmp.shape[0]) // 2))
+        dst[off:off + tmp.shape[0], :tmp.shape[1]] = tmp
+    else:
+        off = int(round((L - tmp.shape[1]) // 2))
+        dst[:tmp.shape[0], off:off + tmp.shape[1]] = tmp
+    f = [np.zeros((L, L), np.uint8) for _ in range(8)]
+    contours, _h = cv2.findContours(dst.copy(), cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+
+    def direction(p1, p2):                                       # OCR::chain_code_direction(next, current), src/OCR.cpp:602-622
+        if p1[0] < p2[0] and p1[1] == p2[1]: return 0
+        if p1[0] < p2[0] and p1[1] < p2[1]: return 1
+        if p1[0] == p2[0] and p1[1] < p2[1]: return 2
+        if p1[0] > p2[0] and p1[1] < p2[1]: return 3
+        if p1[0] > p2[0] and p1[1] == p2[1]: return 4
+        if p1[0] > p2[0] and p1[1] > p2[1]: return 5
+        if p1[0] == p2[0] and p1[1] > p2[1]: return 6
+        return 7
+    for c in contours:
+        pts = [tuple(p) for p in c.reshape(-1, 2)]
+        if len(pts) == 1:
+            continue
+        pts.append(pts[0])
+        for j in range(len(pts) - 1):
+            f[direction(pts[j + 1], pts[j])][pts[j][1], pts[j][0]] = 255
+    feat = []
+    for k in range(8):
+        g = cv2.GaussianBlur(f[k], (7, 7), 0)
+        cv2.normalize(g, g, 0, 255, cv2.NORM_MINMAX, cv2.CV_8U)
+        feat.append(cv2.resize(g, (15, 15)).ravel())
+    return dst, np.concatenate(feat)
+
+
+def test_ocr_oracle_matches_a_cv2_pipeline_end_to_end(ref, golden_frames):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(12)
+    ch = ref.channels(golden_frames[1])
+    n = 0
+    for t in range(220):
+        k = rng.randint(0, 6)
+        w, h = rng.randint(4, 160), rng.randint(4, 160)
+        if t % 9 == 0:
+            w = h = 2 * rng.randint(6, 31)                       # hits the exact-2x INTER_AREA switch when it reaches 60
+        x, y = rng.randint(0, 640 - w), rng.randint(0, 480 - h)
+        crop = np.ascontiguousarray(ch[k][y:y + h, x:x + w])
+        if int(30 * (min(w, h) / max(w, h)) ** 0.5) < 1:
+            continue
+        img, feat = ref.ocr_features(crop, 0.0)
+        eimg, efeat = _cv2_chain_run_features(cv2, crop)
+        assert (img == eimg).all(), (t, w, h)
+        assert (feat == efeat).all(), (t, w, h)
+        n += 1
+    assert n > 200
+
+
+def test_calc_color_oracle_matches_a_cv2_pipeline(ref, golden_frames):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(13)
+    ch = ref.channels(golden_frames[2])
+    ycc = cv2.cvtColor(golden_frames[2], cv2.COLOR_BGR2YCrCb)
+    for t in range(200):
+        k = rng.randint(0, 6)
+        w, h = rng.randint(1, 200), rng.randint(1, 200)
+        x, y = rng.randint(0, 640 - w), rng.randint(0, 480 - h)
+        _t, mask = cv2.threshold(255 - ch[k][y:y + h, x:x + w], 128, 255, cv2.THRESH_OTSU)
+        m = mask != 0
+        got = ref.calc_color(ch[k], ycc, [(x, y, w, h)])[0]
+        if m.sum() == 0:
+            assert np.isnan(got).all()
+        else:
+            exp = [ycc[:h, :w, c][m].astype(np.float64).sum() / m.sum() for c in range(3)]      # rows / cols from the image origin
+            assert (got == np.array(exp)).all(), (t, x, y, w, h)
