@@ -555,11 +555,27 @@ __device__ __forceinline__ uint32_t find_g(const uint32_t *par, uint32_t k)
 	}
 }
 
+// find with path halving for the seam kernel: chains of tile roots of one big same-level region (background) grow with
+// the number of tiles it spans.  par[k] = same-level grandparent is a relaxed store; the argument of climb_s carries
+// over: whatever a concurrent atomicMin puts below a same-level parent is itself a same-level pixel of the node and is
+// re-linked above by the thread that displaced it, so per-level connectivity never changes.
+__device__ __forceinline__ uint32_t find_halve_g(uint32_t *par, uint32_t k)
+{
+	for (;;) {
+		const uint32_t p = ld_relaxed(par + key_idx(k));
+		if (p == KEY_NONE || key_level(p) != key_level(k)) return k;
+		const uint32_t g = ld_relaxed(par + key_idx(p));
+		if (g == KEY_NONE || key_level(g) != key_level(k)) return p;
+		asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(par + key_idx(k)), "r"(g) : "memory");
+		k = g;
+	}
+}
+
 __device__ __forceinline__ void link_g(uint32_t *par, uint32_t a, uint32_t b, uint32_t *status)
 {
 	for (int guard = 0; guard < (1 << 22); ++guard) {
-		a = find_g(par, a);
-		b = find_g(par, b);
+		a = find_halve_g(par, a);
+		b = find_halve_g(par, b);
 		if (a == b) return;
 		if (a > b) { const uint32_t t = a; a = b; b = t; }
 		const uint32_t old = atomicMin(&par[key_idx(a)], b);
