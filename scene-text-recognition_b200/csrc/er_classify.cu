@@ -162,44 +162,36 @@ __global__ void k_cascade(const T *__restrict__ fv, size_t row_stride, int n_row
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_cascade_warp : one WARP per region for u8 histograms.  Stump tables live in shared memory in a compact
+// Warp-cooperative stage evaluation for u8 histograms.  Stump tables live in shared memory in a compact
 // form (dim, integer threshold, cp, cn: for integer counts h < thr <=> h < ceil(thr)); 32 lanes gather and select
 // 32 stumps at once, then the stage sum is accumulated in FILE ORDER by broadcasting the 32 selected values one
 // after the other (every lane performs the same non-fused double adds) -- bit-identical stage sums, ~20x less
 // latency than one thread walking the table.
 // ---------------------------------------------------------------------------------------------
 struct StumpC { double cp, cn; uint16_t dim, ithr; uint32_t pad; };
-constexpr int CW_WARPS = 8;
 
-__device__ __forceinline__ double cascade_eval_warp(const StumpC *__restrict__ st, const int *__restrict__ stage_len, const int *__restrict__ stage_thr,
-                                                    int n_stages, const uint8_t *__restrict__ hist, int lane)
-{
-	double score = 0.0;
-	int off = 0;
-	for (int s = 0; s < n_stages; s++) {
-		score = 0.0;
-		const int len = stage_len[s];
-		for (int c0 = 0; c0 < len; c0 += 32) {
-			const int j = c0 + lane;
-			double v = 0.0;
-			if (j < len) { const StumpC t = st[off + j]; v = ((int)hist[t.dim] < (int)t.ithr) ? t.cp : t.cn; }
-			const int m = min(32, len - c0);
-			for (int i = 0; i < m; i++) score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, v, i));
-		}
-		if (score < (double)stage_thr[s]) return ERT_NEG_DBL_MAX;
-		off += len;
-	}
-	return score;
-}
+// ---------------------------------------------------------------------------------------------
+// k_cascade_stage : one CTA per region, one WARP per cascade STAGE.  A stage's sum starts from zero
+// (src/adaboost.cpp:528-529), so the stages of both cascades are independent computations: each warp evaluates one
+// stage as described above (32 stumps gathered at once, added in FILE ORDER with non-fused double adds),
+// and one thread then applies the stage thresholds in order.  Same bits as walking the stages one after the other,
+// but the latency is the longest stage (1210 stumps) instead of the sum of the stages a region survives (up to 4014).
+// Persistent CTAs: the stump tables are loaded into shared memory once per CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int CS_WARPS = 12;
 
-__global__ void __launch_bounds__(CW_WARPS * 32) k_cascade_warp(const uint8_t *__restrict__ hist, int n_rows, const int32_t *__restrict__ counts,
-                                                                int pool_cap, CascadeDev strong, CascadeDev weak, int n_strong, int n_weak,
-                                                                int32_t *__restrict__ label, double *__restrict__ sscore, double *__restrict__ wscore)
+__global__ void __launch_bounds__(CS_WARPS * 32) k_cascade_stage(const uint8_t *__restrict__ hist, int n_rows, const int32_t *__restrict__ counts,
+                                                                 int n_planes, int pool_cap, CascadeDev strong, CascadeDev weak, int n_strong,
+                                                                 int n_weak, int32_t *__restrict__ label, double *__restrict__ sscore,
+                                                                 double *__restrict__ wscore)
 {
 	extern __shared__ __align__(16) uint8_t csm[];
 	StumpC *st = reinterpret_cast<StumpC *>(csm);                 // strong stumps, then weak stumps
-	int *meta = reinterpret_cast<int *>(st + n_strong + n_weak);  // stage_len/thr of both cascades
-	uint8_t *hs = reinterpret_cast<uint8_t *>(meta + 64);         // CW_WARPS x 1024 histogram bytes
+	double *s_score = reinterpret_cast<double *>(st + n_strong + n_weak);   // [32] stage sums of the current region
+	int *meta = reinterpret_cast<int *>(s_score + 32);            // [0..15] strong len, [16..31] strong thr, [32..47] weak len, [48..63] weak thr
+	int *stage_off = meta + 64;                                   // [32] first stump of stage s (strong stages, then weak stages)
+	uint8_t *hs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(stage_off + 32) + 15) & ~(uintptr_t)15);   // 1024 histogram bytes (uint4 copies)
+	int *pref = reinterpret_cast<int *>(hs + 1024);               // [n_planes + 1] first region of each plane (pipeline flavour)
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	for (int i = tid; i < n_strong + n_weak; i += blockDim.x) {
 		const Stump s0 = (i < n_strong) ? strong.stumps[i] : weak.stumps[i - n_strong];
@@ -217,23 +209,51 @@ __global__ void __launch_bounds__(CW_WARPS * 32) k_cascade_warp(const uint8_t *_
 		meta[48 + tid] = (tid < weak.n_stages) ? weak.stage_thr[tid] : 0;
 	}
 	__syncthreads();
-	uint8_t *myh = hs + warp * 1024;
-	for (long long idx = (long long)blockIdx.x * CW_WARPS + warp; idx < n_rows; idx += (long long)gridDim.x * CW_WARPS) {
+	const int ns = strong.n_stages, nw = weak.n_stages, nst = ns + nw;
+	if (tid == 0) {
+		int o = 0;
+		for (int s2 = 0; s2 < ns; s2++) { stage_off[s2] = o; o += meta[s2]; }
+		o = n_strong;
+		for (int s2 = 0; s2 < nw; s2++) { stage_off[ns + s2] = o; o += meta[32 + s2]; }
 		if (counts) {
-			const int plane = (int)(idx / pool_cap), k = (int)(idx % pool_cap);
-			if (k >= min(counts[2 * plane + 1], pool_cap)) continue;
+			int acc = 0;
+			for (int p = 0; p < n_planes; p++) { pref[p] = acc; acc += min(counts[2 * p + 1], pool_cap); }
+			pref[n_planes] = acc;
 		}
-		const uint4 *src = reinterpret_cast<const uint4 *>(hist + (size_t)idx * 1024);
-		__syncwarp();
-		reinterpret_cast<uint4 *>(myh)[lane] = src[lane];
-		reinterpret_cast<uint4 *>(myh)[lane + 32] = src[lane + 32];
-		__syncwarp();
-		const double s = cascade_eval_warp(st, meta, meta + 16, strong.n_stages, myh, lane);
-		const double w = cascade_eval_warp(st + n_strong, meta + 32, meta + 48, weak.n_stages, myh, lane);
-		if (lane == 0) {
-			label[idx] = (s > ERT_NEG_DBL_MAX) ? 2 : ((w > ERT_NEG_DBL_MAX) ? 1 : 0);
-			if (sscore) sscore[idx] = s;
-			if (wscore) wscore[idx] = w;
+	}
+	__syncthreads();
+	const int total = counts ? pref[n_planes] : n_rows;
+	for (int r = blockIdx.x; r < total; r += gridDim.x) {
+		size_t idx = (size_t)r;
+		if (counts) {
+			int lo = 0, hi = n_planes - 1;                             // largest plane with pref[plane] <= r
+			while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pref[mid] <= r) lo = mid; else hi = mid - 1; }
+			idx = (size_t)lo * pool_cap + (size_t)(r - pref[lo]);
+		}
+		__syncthreads();                                               // the previous region's readers are done with hs / s_score
+		if (tid < 64) reinterpret_cast<uint4 *>(hs)[tid] = reinterpret_cast<const uint4 *>(hist + idx * 1024)[tid];
+		__syncthreads();
+		for (int s2 = warp; s2 < nst; s2 += CS_WARPS) {
+			const StumpC *tbl = st + stage_off[s2];
+			const int len = (s2 < ns) ? meta[s2] : meta[32 + s2 - ns];
+			double score = 0.0;
+			for (int c0 = 0; c0 < len; c0 += 32) {
+				const int j = c0 + lane;
+				double v = 0.0;
+				if (j < len) { const StumpC t = tbl[j]; v = ((int)hs[t.dim] < (int)t.ithr) ? t.cp : t.cn; }
+				const int m = min(32, len - c0);
+				for (int i = 0; i < m; i++) score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, v, i));
+			}
+			if (lane == 0) s_score[s2] = score;
+		}
+		__syncthreads();
+		if (tid == 0) {
+			double sres = 0.0, wres = 0.0;                              // CascadeBoost::predict: the last stage's sum, -DBL_MAX on the first failing stage
+			for (int s2 = 0; s2 < ns; s2++) { sres = s_score[s2]; if (sres < (double)meta[16 + s2]) { sres = ERT_NEG_DBL_MAX; break; } }
+			for (int s2 = 0; s2 < nw; s2++) { wres = s_score[ns + s2]; if (wres < (double)meta[48 + s2]) { wres = ERT_NEG_DBL_MAX; break; } }
+			label[idx] = (sres > ERT_NEG_DBL_MAX) ? 2 : ((wres > ERT_NEG_DBL_MAX) ? 1 : 0);
+			if (sscore) sscore[idx] = sres;
+			if (wscore) wscore[idx] = wres;
 		}
 	}
 }
@@ -251,15 +271,15 @@ int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const 
                       const CascadeDev &weak, int n_strong, int n_weak, int32_t *label, double *sscore, double *wscore, cudaStream_t st)
 {
 	if (n_rows <= 0) return 0;
-	const size_t smem = (size_t)(n_strong + n_weak) * sizeof(StumpC) + 64 * sizeof(int) + (size_t)CW_WARPS * 1024;
-	// few regions (the pipeline: tens per plane): one warp per region hides the sequential sum's latency;
-	// very many regions (candidate sweeps): one thread per region keeps 32 independent sums per warp in flight
+	const int n_planes = counts ? n_rows / pool_cap : 0;
+	const size_t smem = (size_t)(n_strong + n_weak) * sizeof(StumpC) + 32 * sizeof(double) + 96 * sizeof(int) + 16 + 1024 + (size_t)(n_planes + 1) * sizeof(int);
+	// few regions (the pipeline: tens per plane): one CTA per region, one warp per cascade stage -- the latency is the
+	// longest stage; very many regions (candidate sweeps): one thread per region keeps 32 independent sums per warp in flight
 	const bool few = (counts != nullptr) || n_rows < 32768;
 	if (few && row_stride == 1024 && strong.n_stages <= 16 && weak.n_stages <= 16 && smem <= 200 * 1024) {
-		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_cascade_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		const long long want = ((long long)n_rows + CW_WARPS - 1) / CW_WARPS;
-		const int grid = (int)std::min<long long>(want, 148 * 2);
-		k_cascade_warp<<<grid, CW_WARPS * 32, smem, st>>>(hist, n_rows, counts, pool_cap, strong, weak, n_strong, n_weak, label, sscore, wscore);
+		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_cascade_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const int grid = counts ? 148 * 2 : (int)std::min<long long>(n_rows, 148 * 2);
+		k_cascade_stage<<<grid, CS_WARPS * 32, smem, st>>>(hist, n_rows, counts, n_planes, pool_cap, strong, weak, n_strong, n_weak, label, sscore, wscore);
 	} else {
 		k_cascade<uint8_t><<<(n_rows + 127) / 128, 128, 0, st>>>(hist, row_stride, n_rows, counts, pool_cap, strong, weak, label, sscore, wscore);
 	}
