@@ -189,6 +189,10 @@ ERT_API int ert_compute_channels(ert_ctx *ctx, const uint8_t *bgr, int width, in
  * size, plane k at planes + k*plane_stride_bytes, rows stride_bytes apart, host memory. */
 ERT_API int ert_planes_detect(ert_ctx *ctx, const uint8_t *planes, int n_planes, int width, int height, int stride_bytes,
                               size_t plane_stride_bytes, int upto, const ert_result **out);
+/* Asynchronous form (collect with ert_fetch_result; the host planes must stay valid until then unless pinned copies were
+ * enqueued).  One context per scale runs the levels of a pyramid concurrently (BASELINE config 4). */
+ERT_API int ert_enqueue_planes(ert_ctx *ctx, const uint8_t *planes, int n_planes, int width, int height, int stride_bytes,
+                               size_t plane_stride_bytes, int upto);
 
 /* ERFilter::non_maximum_supression(ER *root, ..., pool, input) on a caller tree (src/ER.cpp:416):
  * nodes in DFS pre-order with the caller's child order (as ert_result delivers them, or as

@@ -641,9 +641,10 @@ int ert_compute_channels(ert_ctx *c, const uint8_t *bgr, int W, int H, int strid
 	return 0;
 }
 
-int ert_planes_detect(ert_ctx *c, const uint8_t *planes, int n_planes, int W, int H, int stride, size_t plane_stride, int upto, const ert_result **out)
+int ert_enqueue_planes(ert_ctx *c, const uint8_t *planes, int n_planes, int W, int H, int stride, size_t plane_stride, int upto)
 {
 	if (!c || !planes || n_planes < 1 || stride < W) { set_error("bad arguments"); return -1; }
+	if (upto >= ERT_STAGE_TRACK) { set_error("ERT_STAGE_TRACK needs a BGR batch (er_track reads the YCrCb frame)"); return -1; }
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
 	if (ensure_workspace(c, n_planes, W, H)) return -1;
 	if (set_plane_table(c, n_planes, false)) return -1;
@@ -655,7 +656,12 @@ int ert_planes_detect(ert_ctx *c, const uint8_t *planes, int n_planes, int W, in
 		ERT_CUDA_CHECK(cudaMemcpy2DAsync(c->d_ycc + (size_t)p * c->ycc_bytes, (size_t)c->pitch, planes + (size_t)p * plane_stride, (size_t)stride,
 		                                 (size_t)W, (size_t)H, cudaMemcpyHostToDevice, st));
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
-	if (enqueue_pipeline(c, n_planes, upto)) return -1;
+	return enqueue_pipeline(c, n_planes, upto);
+}
+
+int ert_planes_detect(ert_ctx *c, const uint8_t *planes, int n_planes, int W, int H, int stride, size_t plane_stride, int upto, const ert_result **out)
+{
+	if (ert_enqueue_planes(c, planes, n_planes, W, H, stride, plane_stride, upto)) return -1;
 	return finish_result(c, out);
 }
 

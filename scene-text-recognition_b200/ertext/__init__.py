@@ -86,7 +86,7 @@ EXPORTS = [
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
     "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
     "ert_load_svm", "ert_svm_nr_class", "ert_set_svm_tensor_cores", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
-    "ert_fetch_result", "ert_compute_channels", "ert_planes_detect", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
+    "ert_fetch_result", "ert_compute_channels", "ert_planes_detect", "ert_enqueue_planes", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
     "ert_cascade_predict_batch", "ert_cascade_classify_u8", "ert_svm_predict_probability_batch",
     "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
     "ert_bench_cascade_u8", "ert_bench_svm_u8",
@@ -125,6 +125,7 @@ def load_library():
     L.ert_fetch_result.argtypes = [C.c_void_p, RP]
     L.ert_compute_channels.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
     L.ert_planes_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, RP]
+    L.ert_enqueue_planes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int]
     L.ert_nms_nodes.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int)]
     L.ert_classify_regions.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, _f64p, _f64p, _u8p]
     L.ert_lbp_hist.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f64p]
@@ -328,6 +329,12 @@ class ErText:
         rp = C.POINTER(ErtResult)()
         self._check(self.L.ert_planes_detect(self.ctx, planes.ctypes.data, p, w, h, w, w * h, upto, C.byref(rp)))
         return self._unpack(rp)
+
+    def enqueue_planes(self, planes, upto=STAGE_CLASSIFY):
+        """asynchronous planes_detect: returns at once, collect with fetch(); `planes` must stay alive until then"""
+        assert planes.dtype == np.uint8 and planes.flags["C_CONTIGUOUS"] and planes.ndim == 3
+        p, h, w = planes.shape
+        self._check(self.L.ert_enqueue_planes(self.ctx, planes.ctypes.data, p, w, h, w, w * h, upto))
 
     # ---- stage entry points --------------------------------------------------------------------
     def nms_nodes(self, nodes, w, h):

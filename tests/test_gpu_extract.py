@@ -85,3 +85,21 @@ def test_kept_capacity_overflow_is_reported(ert):
         assert res.status & 2
     finally:
         ert.set_capacity(16384, 2048); ert.set_min_area(120)
+
+
+@pytest.mark.gpu
+def test_enqueue_planes_matches_planes_detect_and_overlaps_scales(ert):
+    """asynchronous plane entry point: two contexts, two plane sizes in flight at once == the synchronous calls"""
+    import ertext
+    from conftest import make_plane
+    a = np.stack([make_plane(3, 120, 200, "blobs"), make_plane(4, 120, 200, "smooth")])
+    b = np.stack([make_plane(5, 60, 100, "blobs")])
+    ra, rb = ert.planes_detect(a), ert.planes_detect(b)
+    c1, c2 = ertext.ErText(), ertext.ErText()
+    c1.enqueue_planes(a); c2.enqueue_planes(b)
+    qa, qb = c1.fetch(), c2.fetch()
+    for x, y in ((ra, qa), (rb, qb)):
+        assert x.status == y.status == 0
+        for p, q in zip(x.planes, y.planes):
+            assert p.nodes.tobytes() == q.nodes.tobytes() and p.pool.tobytes() == q.pool.tobytes() and p.label.tobytes() == q.label.tobytes()
+    c1.close(); c2.close()

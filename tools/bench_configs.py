@@ -57,6 +57,16 @@ ms = timeit(run4, n=5, warm=2)
 rs = run4()
 out = {"config": 4, "what": "3840x2160 S-text, 3 planes x scales 1,1/2,1/4,1/8 (11.0 MP per plane pyramid), host planes in", "gpu_ms": ms,
        "device_ms_per_scale": [x.stage_ms[5] for x in rs], "kept_nodes": [sum(len(p.nodes) for p in x.planes) for x in rs]}
+# the same with one context per scale, enqueued asynchronously: the four levels overlap on the device
+ctxs = [ertext.ErText() for _ in levels]
+def run4_async():
+    for c_, l in zip(ctxs, levels):
+        c_.enqueue_planes(l)
+    return [c_.fetch() for c_ in ctxs]
+ms_async = timeit(run4_async, n=5, warm=2)
+ra = run4_async()
+assert all((a.planes[k].nodes == b.planes[k].nodes).all() and (a.planes[k].pool == b.planes[k].pool).all() for a, b in zip(ra, rs) for k in range(3))
+out["gpu_ms_async_one_context_per_scale"] = ms_async
 if ref:
     t = time.perf_counter()
     for l in levels:
