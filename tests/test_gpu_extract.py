@@ -103,3 +103,25 @@ def test_enqueue_planes_matches_planes_detect_and_overlaps_scales(ert):
         for p, q in zip(x.planes, y.planes):
             assert p.nodes.tobytes() == q.nodes.tobytes() and p.pool.tobytes() == q.pool.tobytes() and p.label.tobytes() == q.label.tobytes()
     c1.close(); c2.close()
+
+
+@pytest.mark.gpu
+def test_maximum_plane_size_matches_oracle(port):
+    """the largest plane the key layout supports: 8191 x 8191 (67 092 481 pixels < 2^26), with a wall band and a wall start pixel;
+    one pixel more per side is refused"""
+    import ertext
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(3)
+    big = cv2.resize(rng.randint(0, 256, (64, 64)).astype(np.uint8), (8191, 8191), interpolation=cv2.INTER_CUBIC)
+    big[4000:4100, 100:8000] = 255
+    big[0, 0] = 255
+    e = ertext.ErText()
+    res = e.planes_detect(big, upto=ertext.STAGE_NMS)
+    assert res.status == 0
+    exp = port.plane(big, classify=False, canonical_order=True)
+    got = res.planes[0]
+    assert got.nodes.shape == exp["nodes"].shape and (got.nodes == exp["nodes"]).all()
+    assert (got.pool == exp["pool"]).all()
+    with pytest.raises(ertext.ErtError):
+        e.planes_detect(np.zeros((8, 8192), np.uint8))
+    e.close()
