@@ -71,3 +71,9 @@ for i in range(24):
 label, prob = ref.svm_predict_probability(x)
 np.savez_compressed(os.path.join(HERE, "ref_svm.npz"), x_u8=np.rint(x * 255).astype(np.uint8), label=label, prob=prob)
 print("golden fixtures written:", [f for f in os.listdir(HERE) if f.endswith(".npz")])
+
+# larger real frames for the GPU parity tests, kept as their JPEG bytes (inputs only: the expectation is computed live by the C
+# restatement on whatever cv2 decodes, and that restatement is itself pinned to the reference above):
+# ICDAR img_123 (1280x960), img_1 (960x1280 portrait), img_100 (827x959, odd size)
+big = {k: np.frombuffer(open(os.path.join(REF_IMG, n), "rb").read(), np.uint8) for k, n in (("landscape", "img_123.jpg"), ("portrait", "img_1.jpg"), ("odd", "img_100.jpg"))}
+np.savez(os.path.join(HERE, "frames_large.npz"), names=np.array(["img_123.jpg", "img_1.jpg", "img_100.jpg"]), **big)

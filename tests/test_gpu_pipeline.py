@@ -363,3 +363,24 @@ def test_nms_level_parallel_equals_the_sequential_walk(golden_frames):
                 assert pa.nodes.tobytes() == pb.nodes.tobytes(), (name, params)
                 assert pa.pool.tobytes() == pb.pool.tobytes() and pa.label.tobytes() == pb.label.tobytes(), (name, params)
         a.close(); b.close()
+
+
+def test_larger_real_frames_full_pipeline_parity(ert, port):
+    """real ICDAR frames at 1280x960, 960x1280 (portrait) and 827x959 (widths / heights that are no multiple of the tile):
+    nodes, pool, labels and scores identical to the oracle on every plane"""
+    from conftest import GOLDEN
+    import os
+    cv2 = pytest.importorskip("cv2")
+    g = np.load(os.path.join(GOLDEN, "frames_large.npz"))
+    for key, shape in (("landscape", (960, 1280, 3)), ("portrait", (1280, 960, 3)), ("odd", (959, 827, 3))):
+        frame = cv2.imdecode(g[key], cv2.IMREAD_COLOR)
+        assert frame.shape == shape
+        res = ert.detect_classify(frame)
+        assert res.status == 0, key
+        ch = port.channels(frame)
+        for k in range(6):
+            exp = port.plane(ch[k], scores=True, canonical_order=True)
+            got = res.planes[k]
+            assert got.nodes.shape == exp["nodes"].shape and (got.nodes == exp["nodes"]).all(), (key, k)
+            assert (got.pool == exp["pool"]).all() and (got.label == exp["label"]).all(), (key, k)
+            assert (got.strong_score == exp["strong_score"]).all() and (got.weak_score == exp["weak_score"]).all(), (key, k)
