@@ -918,3 +918,253 @@ PORT_API int port_canonical_nodes(const uint8_t *plane, int w, int h, int stride
 	free(bx0); free(bx1); free(by0); free(by1); free(stamp); free(act);
 	return nout;
 }
+
+/* ==========================================================================================
+ * Rows AFTER the detect path: er_track + calc_color, OCR::chain_run's feature path.
+ * Restated from the reference's behaviour; the OpenCV primitives it calls (threshold OTSU, findContours,
+ * GaussianBlur, normalize, resize) are restated from OpenCV 4.x and pinned against cv2 in tests/test_oracle_next.py
+ * through the reference-backed oracle, against which every function below is checked (tests/test_port_next.py).
+ * ========================================================================================== */
+
+/* cv::threshold(..., THRESH_OTSU) -> getThreshVal_Otsu_8u: running-mean recurrence in double, strict '>' */
+static int otsu_from_hist(const int *h, int total)
+{
+	double mu = 0, scale = 1. / total;
+	for (int i = 0; i < 256; i++) mu += i * (double)h[i];
+	mu *= scale;
+	double mu1 = 0, q1 = 0, max_sigma = 0;
+	int max_val = 0;
+	for (int i = 0; i < 256; i++) {
+		const double p_i = h[i] * scale;
+		mu1 *= q1;
+		q1 += p_i;
+		const double q2 = 1. - q1;
+		if (fmin(q1, q2) < FLT_EPSILON || fmax(q1, q2) > 1. - FLT_EPSILON) continue;
+		mu1 = (mu1 + i * p_i) / q1;
+		const double mu2 = (mu - q1 * mu1) / q2;
+		const double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+		if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+	}
+	return max_val;
+}
+
+/* OTSU threshold of (255 - crop), the image both calc_color (src/ER.cpp:1395) and chain_run (src/OCR.cpp:72) binarise */
+static int otsu_of_inverted(const uint8_t *crop, int w, int h, int stride)
+{
+	int hist[256];
+	memset(hist, 0, sizeof hist);
+	for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) hist[255 - crop[(size_t)y * stride + x]]++;
+	return otsu_from_hist(hist, w * h);
+}
+
+/* calc_color (src/ER.cpp:1391-1437): mean YCrCb under the OTSU mask of 255 - channel(bound).  The colour rows and
+ * columns are counted from the IMAGE origin, not from the bound (color_img.ptr(i), src/ER.cpp:1404).  0/0 -> NaN. */
+PORT_API void port_calc_color(const uint8_t *plane, const uint8_t *ycrcb, int W, int H, const int32_t *rects, int n, double *color3)
+{
+	(void)H;
+	for (int i = 0; i < n; i++) {
+		const int x0 = rects[4 * i], y0 = rects[4 * i + 1], w = rects[4 * i + 2], h = rects[4 * i + 3];
+		const uint8_t *crop = plane + (size_t)y0 * W + x0;
+		const int thr = otsu_of_inverted(crop, w, h, W);
+		int count = 0;
+		double c1 = 0, c2 = 0, c3 = 0;
+		for (int r = 0; r < h; r++) {
+			const uint8_t *cp = ycrcb + (size_t)r * W * 3;
+			for (int j = 0; j < w; j++)
+				if (255 - crop[(size_t)r * W + j] > thr) { ++count; c1 += cp[3 * j]; c2 += cp[3 * j + 1]; c3 += cp[3 * j + 2]; }
+		}
+		color3[3 * i] = c1 / count; color3[3 * i + 1] = c2 / count; color3[3 * i + 2] = c3 / count;
+	}
+}
+
+/* ERFilter::er_track (src/ER.cpp:532-609).  strong / weak: rows (ch, x, y, w, h, area), channel-major.  all_er starts as
+ * the strong rows; every entry, in order, pulls in the not-yet-tracked weak rows that pass the geometry / colour / area
+ * test (src/ER.cpp:579-590), in (channel, index) order.  tracked_out: (kind 0 strong / 1 weak, row).  Returns its length. */
+PORT_API int port_er_track(const uint8_t *planes6, const uint8_t *ycrcb, int W, int H, const int32_t *strong, int ns, const int32_t *weak, int nw,
+                           int32_t *tracked_out, double *strong_color, double *weak_color, int32_t *strong_center, int32_t *weak_center)
+{
+	const size_t np = (size_t)W * H;
+	for (int pass = 0; pass < 2; pass++) {
+		const int32_t *rows = pass ? weak : strong;
+		const int n = pass ? nw : ns;
+		double *col = pass ? weak_color : strong_color;
+		int32_t *cen = pass ? weak_center : strong_center;
+		for (int i = 0; i < n; i++) {
+			const int32_t *r = rows + 6 * i;
+			port_calc_color(planes6 + (size_t)r[0] * np, ycrcb, W, H, r + 1, 1, col + 3 * i);
+			cen[2 * i] = r[1] + r[3] / 2; cen[2 * i + 1] = r[2] + r[4] / 2;          /* src/ER.cpp:545 */
+		}
+	}
+	int len = 0;
+	for (int i = 0; i < ns; i++) { tracked_out[2 * len] = 0; tracked_out[2 * len + 1] = i; len++; }
+	uint8_t *taken = (uint8_t *)calloc((size_t)(nw > 0 ? nw : 1), 1);
+	for (int i = 0; i < len; i++) {
+		const int kind = tracked_out[2 * i], idx = tracked_out[2 * i + 1];
+		const int32_t *s = (kind ? weak : strong) + 6 * idx;
+		const double *sc = (kind ? weak_color : strong_color) + 3 * idx;
+		const int32_t *scen = (kind ? weak_center : strong_center) + 2 * idx;
+		for (int n = 0; n < nw; n++) {       /* rows are channel-major: this IS the (m, n) loop order of the reference */
+			if (taken[n]) continue;
+			const int32_t *w = weak + 6 * n;
+			const double *wc = weak_color + 3 * n;
+			const int32_t *wcen = weak_center + 2 * n;
+			const int sw = s[3], sh = s[4], ww = w[3], wh = w[4];
+			if (abs(scen[0] - wcen[0]) + abs(scen[1] - wcen[1]) < ((sw > sh ? sw : sh) << 1) &&
+			    abs(sh - wh) < (sh < wh ? sh : wh) &&
+			    abs(sw - ww) < ((sw + ww) >> 1) &&
+			    fabs(sc[0] - wc[0]) < 25 && fabs(sc[1] - wc[1]) < 25 && fabs(sc[2] - wc[2]) < 25 &&
+			    abs(s[5] - w[5]) < (s[5] < w[5] ? s[5] : w[5]) * 3) {
+				taken[n] = 1;
+				tracked_out[2 * len] = 1; tracked_out[2 * len + 1] = n; len++;
+			}
+		}
+	}
+	free(taken);
+	return len;
+}
+
+/* OCR::rotate_mat(src, dst, rad, crop) (src/OCR.cpp:254-360) on a contiguous image; returns a malloc'ed image */
+static uint8_t *rotate_image(const uint8_t *src, int cols, int rows, double rad, int crop, int *out_w, int *out_h)
+{
+	const int x0 = (int)((cols - 1) / 2.0), y0 = (int)((rows - 1) / 2.0);
+	const int cx[4] = { 0 - x0, (cols - 1) - x0, (cols - 1) - x0, 0 - x0 };
+	const int cy[4] = { 0 - y0, 0 - y0, (rows - 1) - y0, (rows - 1) - y0 };
+	int nx[4], ny[4];
+	for (int k = 0; k < 4; k++) {
+		nx[k] = (int)round(cx[k] * cos(rad) - cy[k] * sin(rad));
+		ny[k] = (int)round(cx[k] * sin(rad) + cy[k] * cos(rad));
+	}
+	int max_x = nx[0], max_y = ny[0], min_x = nx[0], min_y = ny[0];
+	for (int k = 1; k < 4; k++) {
+		if (nx[k] > max_x) max_x = nx[k]; if (nx[k] < min_x) min_x = nx[k];
+		if (ny[k] > max_y) max_y = ny[k]; if (ny[k] < min_y) min_y = ny[k];
+	}
+	int crop_h = 0;
+	if (crop) {
+		crop_h = (int)((nx[1] - nx[0]) * tan(rad) * 0.5);
+		if (max_y - min_y + 1 - 2 * crop_h <= 0) { crop = 0; crop_h = 0; }          /* falls back to the un-cropped form */
+	}
+	const int ow = max_x - min_x + 1, oh = max_y - min_y + 1 - 2 * crop_h;
+	uint8_t *out = (uint8_t *)calloc((size_t)(ow > 0 && oh > 0 ? ow * oh : 1), 1);
+	*out_w = ow; *out_h = oh;
+	if (ow <= 0 || oh <= 0) return out;
+	for (int i = min_y + crop_h; i < max_y - crop_h; i++) {
+		uint8_t *t = out + (size_t)(i - min_y - crop_h) * ow;
+		for (int j = min_x; j < max_x; j++) {
+			const double ii = (double)(i - crop_h);                                    /* crop_h is 0 in the un-cropped form */
+			const double new_j = cos(rad) * j - sin(rad) * ii + x0;
+			const double new_i = sin(rad) * j + cos(rad) * ii + y0;
+			if (!(new_i > 0 && new_j > 0 && new_i < rows - 1 && new_j < cols - 1)) continue;
+			if (crop && !(i > min_y + crop_h)) continue;                               /* first row stays empty in the cropped form */
+			const uint8_t *s = src + (size_t)(int)new_i * cols + (int)new_j;
+			if (new_i == floor(new_i) && new_j == floor(new_j)) t[j - min_x] = s[0];
+			else {
+				const double alpha = new_i - floor(new_i), beta = new_j - floor(new_j);
+				const uint8_t A = s[0], B = s[1], C = s[cols], D = s[cols + 1];
+				t[j - min_x] = (uint8_t)round((1 - alpha) * (1 - beta) * A + (1 - alpha) * beta * B + alpha * (1 - beta) * C + alpha * beta * D);
+			}
+		}
+	}
+	return out;
+}
+
+/* the eight chain-code bitmaps of OCR::extract_feature (src/OCR.cpp:153-169): every step (pixel -> next pixel) of every
+ * border that cv::findContours(RETR_LIST, CHAIN_APPROX_NONE) traces sets the pixel in the bitmap of its direction
+ * (chain_code_direction(next, current), src/OCR.cpp:602-622 = (4 - s) & 7 for OpenCV's step code s).  Border following is
+ * Suzuki-Abe as OpenCV runs it, on a zero-framed copy: 1 untouched, 2 visited, 2|-128 visited with the border to its east. */
+static void chain_code_bitmaps(const uint8_t *img, int L, uint8_t *f /* 8 x L x L */)
+{
+	const int W = L + 2;
+	signed char *b = (signed char *)calloc((size_t)W * W, 1);
+	for (int y = 0; y < L; y++) for (int x = 0; x < L; x++) b[(y + 1) * W + x + 1] = img[y * L + x] ? 1 : 0;
+	const int dx[8] = { 1, 1, 0, -1, -1, -1, 0, 1 }, dy[8] = { 0, -1, -1, -1, 0, 1, 1, 1 };
+	int delta[16];
+	for (int k = 0; k < 16; k++) delta[k] = dy[k & 7] * W + dx[k & 7];
+	memset(f, 0, (size_t)8 * L * L);
+	for (int y = 1; y <= L; y++) {
+		int prev = 0;
+		for (int x = 1; x <= L + 1; x++) {
+			int p = b[y * W + x];
+			if (p == prev) continue;
+			int hole = 0, start = 0;
+			if (prev == 0 && p == 1) start = 1;
+			else if (p == 0 && prev >= 1) { start = 1; hole = 1; }
+			if (start) {
+				const int i0 = y * W + x - hole;
+				int s_end = hole ? 0 : 4, s = s_end, i1;
+				do { s = (s - 1) & 7; i1 = i0 + delta[s]; } while (b[i1] == 0 && s != s_end);
+				if (s == s_end) b[i0] = (signed char)(2 | -128);                  /* isolated pixel: a 1-point contour, skipped (src/OCR.cpp:159) */
+				else {
+					int i3 = i0, i4 = i0;
+					for (;;) {
+						s_end = s;
+						while (s < 15) { i4 = i3 + delta[++s]; if (b[i4] != 0) break; }
+						s &= 7;
+						if ((unsigned)(s - 1) < (unsigned)s_end) b[i3] = (signed char)(2 | -128);
+						else if (b[i3] == 1) b[i3] = 2;
+						f[((4 - s) & 7) * L * L + (i3 / W - 1) * L + (i3 % W - 1)] = 255;
+						if (i4 == i0 && i3 == i1) break;
+						i3 = i4;
+						s = (s + 4) & 7;
+					}
+				}
+				p = b[y * W + x];
+			}
+			prev = p;
+		}
+	}
+	free(b);
+}
+
+/* chain_run's pre-processing (src/OCR.cpp:72-79) + extract_feature (src/OCR.cpp:144-218): returns -1 where the reference's
+ * cv::resize would throw (empty target).  img30: the 30x30 image extract_feature receives; feat1800: value * 255. */
+PORT_API int port_ocr_features(const uint8_t *crop, int w, int h, int stride, double slope, uint8_t *img30, uint8_t *feat1800)
+{
+	const int L = 30, FL = 15;
+	const int thr = otsu_of_inverted(crop, w, h, stride);
+	uint8_t *bin = (uint8_t *)malloc((size_t)w * h);
+	for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) bin[(size_t)y * w + x] = (255 - crop[(size_t)y * stride + x] > thr) ? 255 : 0;
+	int iw = w, ih = h;
+	if (fabs(slope) > 0.01) {
+		uint8_t *rot = rotate_image(bin, w, h, atan2(slope, 1), 1, &iw, &ih);
+		free(bin);
+		bin = rot;
+	}
+	if (iw < 1 || ih < 1 || port_aran_minor(iw, ih, L) < 1) { free(bin); return -1; }
+	port_aran(bin, iw, ih, iw, L, img30);
+	free(bin);
+	uint8_t f[8 * 30 * 30];
+	chain_code_bitmaps(img30, L, f);
+	static const int K[7] = { 8, 28, 56, 72, 56, 28, 8 };      /* GaussianBlur(7x7, sigma 0) on 8U: fixed point, reflect-101 */
+	int nnz = 0;
+	for (int c = 0; c < 8; c++) {
+		const uint8_t *s = f + c * L * L;
+		int hp[30 * 30];
+		uint8_t g[30 * 30];
+		for (int y = 0; y < L; y++) for (int x = 0; x < L; x++) {
+			int a = 0;
+			for (int k = 0; k < 7; k++) { int xi = x + k - 3; if (xi < 0) xi = -xi; if (xi >= L) xi = 2 * L - 2 - xi; a += K[k] * s[y * L + xi]; }
+			hp[y * L + x] = a;
+		}
+		int mn = 255, mx = 0;
+		for (int y = 0; y < L; y++) for (int x = 0; x < L; x++) {
+			int a = 0;
+			for (int k = 0; k < 7; k++) { int yi = y + k - 3; if (yi < 0) yi = -yi; if (yi >= L) yi = 2 * L - 2 - yi; a += K[k] * hp[yi * L + x]; }
+			const int v = (a + 32768) >> 16;
+			g[y * L + x] = (uint8_t)v;
+			if (v < mn) mn = v; if (v > mx) mx = v;
+		}
+		/* normalize(0, 255, NORM_MINMAX, CV_8U): double scale / shift, cast to float, ONE fused multiply-add, round half even */
+		const double scale = 255.0 * ((double)(mx - mn) > DBL_EPSILON ? 1. / (double)(mx - mn) : 0);
+		const double shift = 0.0 - mn * scale;
+		const float fa = (float)scale, fb = (float)shift;
+		for (int i = 0; i < L * L; i++) { long v = lrintf(fmaf((float)g[i], fa, fb)); g[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+		for (int y = 0; y < FL; y++) for (int x = 0; x < FL; x++) {            /* resize 30 -> 15: the exact-2x box */
+			const uint8_t *a = g + (2 * y) * L + 2 * x;
+			const uint8_t v = (uint8_t)((a[0] + a[1] + a[L] + a[L + 1] + 2) >> 2);
+			feat1800[c * FL * FL + y * FL + x] = v;
+			nnz += v != 0;
+		}
+	}
+	return nnz;
+}

@@ -318,6 +318,9 @@ class PortOracle:
         L.port_svm_free.argtypes = [C.c_void_p]
         L.port_canonical_nodes.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int]
         L.port_sort_children.argtypes = [C.c_void_p, C.c_int]
+        L.port_calc_color.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _i32p, C.c_int, _f64p]
+        L.port_er_track.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _i32p, _f64p, _f64p, _i32p, _i32p]
+        L.port_ocr_features.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_double, _u8p, _u8p]
         self.casc = [L.port_cascade_load(os.path.join(ASSETS, "strong.classifier").encode()),
                      L.port_cascade_load(os.path.join(ASSETS, "weak.classifier").encode())]
         self.svm = L.port_svm_load(svm_model_path().encode()) if with_svm else None
@@ -353,6 +356,39 @@ class PortOracle:
             out.update(label=label, strong_score=ss, weak_score=ws)
         self.L.port_tree_free(t)
         return out
+
+    # -- rows after the detect path (same call surface as RefOracle) ----------------------------
+    def calc_color(self, plane, ycrcb, rects):
+        plane = np.ascontiguousarray(plane, dtype=np.uint8)
+        ycrcb = np.ascontiguousarray(ycrcb, dtype=np.uint8)
+        rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+        h, w = plane.shape
+        out = np.zeros((len(rects), 3), np.float64)
+        self.L.port_calc_color(_p(plane, _u8p), _p(ycrcb, _u8p), w, h, _p(rects, _i32p), len(rects), _p(out, _f64p))
+        return out
+
+    def er_track(self, planes6, ycrcb, strong, weak):
+        planes6 = np.ascontiguousarray(planes6, dtype=np.uint8)
+        ycrcb = np.ascontiguousarray(ycrcb, dtype=np.uint8)
+        strong = np.ascontiguousarray(strong, dtype=np.int32).reshape(-1, 6)
+        weak = np.ascontiguousarray(weak, dtype=np.int32).reshape(-1, 6)
+        _, h, w = planes6.shape
+        ns, nw = len(strong), len(weak)
+        tr = np.zeros((ns + nw + 1, 2), np.int32)
+        sc = np.zeros((ns + 1, 3)); wc = np.zeros((nw + 1, 3))
+        sce = np.zeros((ns + 1, 2), np.int32); wce = np.zeros((nw + 1, 2), np.int32)
+        m = self.L.port_er_track(_p(planes6, _u8p), _p(ycrcb, _u8p), w, h, _p(strong, _i32p), ns, _p(weak, _i32p), nw,
+                                 _p(tr, _i32p), _p(sc, _f64p), _p(wc, _f64p), _p(sce, _i32p), _p(wce, _i32p))
+        return dict(tracked=tr[:m].copy(), strong_color=sc[:ns], weak_color=wc[:nw], strong_center=sce[:ns], weak_center=wce[:nw])
+
+    def ocr_features(self, crop, slope=0.0):
+        crop = np.ascontiguousarray(crop, dtype=np.uint8)
+        h, w = crop.shape
+        img = np.zeros((30, 30), np.uint8); feat = np.zeros(1800, np.uint8)
+        n = self.L.port_ocr_features(_p(crop, _u8p), w, h, w, slope, _p(img, _u8p), _p(feat, _u8p))
+        if n < 0:
+            raise ValueError("empty image after rotation / ARAN")
+        return img, feat
 
     def canonical_nodes(self, plane, min_area=None):
         plane = np.ascontiguousarray(plane, dtype=np.uint8)
