@@ -48,7 +48,86 @@ def _link(par, x, y):
             x, y = y, old
 
 
-def tiled_nodes(levels, min_area, TH=32, TW=64, hi=32, seam_aware=True, stats=None):
+def _supertile_merge(lv, W, H, TH, TW, SY, SX, min_area, gpar, attr, recs, stats):
+    """Round-2 design, validated here first: unite the BORDER graphs of SY x SX tiles before the global kernels see them.
+    Per super-tile: the keyed union on its INTERIOR seams, aliases folded into their final node, the seam-aware BORDER rule
+    re-evaluated against the super-tile's OUTER ring only (in the merged forest), everything that became interior folded
+    bottom-up into its parent and dropped (or kept as a complete node if the reference keeps it)."""
+    SH_, SW_ = SY * TH, SX * TW
+    level_of = lambda k: k >> SH
+    for Y0 in range(0, H, SH_):
+        for X0 in range(0, W, SW_):
+            Y1, X1 = min(H, Y0 + SH_), min(W, X0 + SW_)
+            inside = lambda k: Y0 <= (k & MASK) // W < Y1 and X0 <= (k & MASK) % W < X1
+            # 1. interior seams
+            for (y, x, side), ra in list(recs.items()):
+                if not (Y0 <= y < Y1 and X0 <= x < X1) or ra is None:
+                    continue
+                if side == "R" and x + 1 < X1:
+                    rb = recs.get((y, x + 1, "L"))
+                elif side == "B" and y + 1 < Y1:
+                    rb = recs.get((y + 1, x, "T"))
+                else:
+                    continue
+                if rb is not None:
+                    _link(gpar, ra, rb)
+            # 2. aliases hand their totals to the final node of their level and disappear
+            members = [g for g in attr if inside(g) and not attr[g][6]]
+            for g in members:
+                f = _find(gpar, g)
+                if f != g:
+                    a, b = attr.pop(g), attr[f]
+                    b[0] += a[0]; b[1] += a[1] - 1
+                    b[2] = min(b[2], a[2]); b[3] = min(b[3], a[3]); b[4] = max(b[4], a[4]); b[5] = max(b[5], a[5])
+            members = [g for g in members if g in attr]
+            parent = {}
+            for g in members:
+                pk = gpar.get(g & MASK, INF)
+                parent[g] = None if pk == INF else _find(gpar, pk)
+                if parent[g] is not None:
+                    gpar[g & MASK] = parent[g]
+            # 3. BORDER against the outer ring, in the merged forest
+            border = set()
+
+            def mark(r):
+                while r is not None and r not in border:
+                    border.add(r); r = parent[r]
+
+            for (y, x, side), r in list(recs.items()):
+                if not (Y0 <= y < Y1 and X0 <= x < X1) or r is None:
+                    continue
+                dy, dx = {"T": (-1, 0), "B": (1, 0), "L": (0, -1), "R": (0, 1)}[side]
+                qy, qx = y + dy, x + dx
+                if Y0 <= qy < Y1 and X0 <= qx < X1:
+                    recs[(y, x, side)] = None                    # interior seam: done
+                    continue
+                M = max(int(lv[y, x]), int(lv[qy, qx]))
+                a = _find(gpar, r)
+                while parent[a] is not None and level_of(parent[a]) <= M:
+                    a = parent[a]
+                recs[(y, x, side)] = a
+                mark(a)
+            for (gy, gx) in ((0, 0), (0, 1), (1, 0)):
+                if Y0 <= gy < Y1 and X0 <= gx < X1 and gx < W and gy < H and lv[gy, gx] != WALL:
+                    mark(_find(gpar, _find(gpar, (int(lv[gy, gx]) << SH) | (gy * W + gx))))
+            # 4. what became interior folds into its parent, bottom-up, and leaves the global forest unless the reference keeps it
+            for g in sorted(members):
+                if g in border:
+                    continue
+                a = attr[g]
+                if parent[g] is not None:
+                    b = attr[parent[g]]
+                    b[0] += a[0]; b[1] += a[1]
+                    b[2] = min(b[2], a[2]); b[3] = min(b[3], a[3]); b[4] = max(b[4], a[4]); b[5] = max(b[5], a[5])
+                if a[0] + a[1] > min_area:
+                    a[6] = True
+                else:
+                    del attr[g]
+    if stats is not None:
+        stats["global_nodes_after_supertile"] = sum(1 for a in attr.values() if not a[6])
+
+
+def tiled_nodes(levels, min_area, TH=32, TW=64, hi=32, seam_aware=True, stats=None, supertile=None):
     """levels: int array [H, W] of quantised levels (>= hi = wall).  Returns the kept nodes as tuples
     (level, area, x, y, w, h), the same columns as the oracle's canonical dump."""
     H, W = levels.shape
@@ -146,6 +225,10 @@ def tiled_nodes(levels, min_area, TH=32, TW=64, hi=32, seam_aware=True, stats=No
                         gpar[gy * W + gx] = r
     if stats is not None:
         stats["local_nodes"] = n_local; stats["global_nodes"] = n_global
+        stats["global_border_nodes"] = sum(1 for a in attr.values() if not a[6])
+    if supertile is not None:
+        assert seam_aware
+        _supertile_merge(lv, W, H, TH, TW, supertile[0], supertile[1], min_area, gpar, attr, recs, stats)
 
     # ---- k_seam_link_rec: unite the records across every seam ----
     for (y, x, side), ra in list(recs.items()):

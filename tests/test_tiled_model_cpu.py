@@ -31,3 +31,17 @@ def test_seam_aware_rule_sends_fewer_nodes_global(port):
     nb = sorted(tiled_nodes(lev, 120, TH=32, TW=64, seam_aware=False, stats=b))
     assert na == nb == sorted(map(tuple, port.canonical_nodes(img, 120)))
     assert a["local_nodes"] == b["local_nodes"] and a["global_nodes"] < b["global_nodes"]
+
+
+@pytest.mark.parametrize("kind", ["noise", "smooth", "blobs", "walls", "wall0", "allwall", "checker", "ramp"])
+def test_supertile_merge_model_matches_oracle(port, kind):
+    """the round-2 design (unite the BORDER graphs of a group of tiles before the global kernels) leaves the result unchanged"""
+    for seed, (h, w), (th, tw), sup in [(0, (40, 70), (8, 16), (2, 2)), (1, (50, 45), (7, 11), (4, 2)), (2, (64, 96), (16, 16), (2, 3))]:
+        img = make_plane(60 + seed, h, w, kind)
+        lev = port.quantize(img, 8).reshape(img.shape)
+        for ma in (0, 5, 120):
+            exp = sorted(map(tuple, port.canonical_nodes(img, ma)))
+            st = {}
+            got = sorted(tiled_nodes(lev, ma, TH=th, TW=tw, supertile=sup, stats=st))
+            assert got == exp, (kind, h, w, th, tw, sup, ma)
+            assert st["global_nodes_after_supertile"] <= st["global_border_nodes"]
