@@ -133,6 +133,8 @@ ERT_API void ert_destroy(ert_ctx *ctx);
 /* ERFilter::set_thresh_step / set_min_area  (src/ER.cpp:21-30) */
 ERT_API int ert_set_thresh_step(ert_ctx *ctx, int step);
 ERT_API int ert_set_min_area(ert_ctx *ctx, int min_area);
+/* all constructor parameters at once (applies from the next batch on) */
+ERT_API int ert_set_params(ert_ctx *ctx, const ert_params *params);
 /* option: also return the 1024-bin histograms of pooled regions (costs a D2H copy) */
 ERT_API int ert_set_return_hist(ert_ctx *ctx, int on);
 /* option (debug / A-B): 0 = skip the shared-memory tile pass and link every edge in global memory */
@@ -143,7 +145,9 @@ ERT_API int ert_set_nms_sequential(ert_ctx *ctx, int on);
 /* scheduling: 1 (default) = the tile-build kernels of all contexts on a device run in submission order (an event
  * chain); keeps the oldest batch in flight from being starved when several contexts are used round-robin */
 ERT_API int ert_set_tile_fifo(ert_ctx *ctx, int on);
-/* tuning: tile shape / CTA size of the tile-build kernel (0 = default 64x32 pixels, 256 threads) */
+/* tuning / A-B: which tile-build kernel runs: 0 (default) = k_tile_build2 (64x32 tile + halo through one tensor-map TMA
+ * box, 256 threads, 4 pixels per lane); 1 = the round-1 kernel (512 threads, 32 row copies); 2 = round-1 with a shared
+ * work queue.  All produce identical results. */
 ERT_API int ert_set_tile_config(ert_ctx *ctx, int id);
 /* debug: per-phase cycle sums (clock64, thread 0 of every CTA) of the tile-build kernel since the last call */
 ERT_API int ert_debug_phase_cycles(ert_ctx *ctx, int enable, unsigned long long *out16);
@@ -153,9 +157,19 @@ ERT_API int ert_set_capacity(ert_ctx *ctx, int kept_per_plane, int pool_per_plan
 /* new CascadeBoost(path) -> CascadeBoost::load_classifier  (src/adaboost.cpp:498-501, 873-951).
  * Parses the reference's text format byte-compatibly.  which = ERT_CASCADE_STRONG | _WEAK. */
 ERT_API int ert_load_cascade(ert_ctx *ctx, int which, const char *path);
+/* A cascade handed over in memory instead of a file: what CascadeBoost holds after load_classifier / training
+ * (num_of_iter[], thresh[], and per stump RealDecisionStump::get_para() = dim, thresh, cp, cn; src/adaboost.cpp:138-146). */
+ERT_API int ert_set_cascade(ert_ctx *ctx, int which, int n_stages, const int *stage_len, const int *stage_thr, int n_stumps, const int *dim,
+                            const double *thr, const double *cp, const double *cn);
+/* the header of a loaded cascade (num_of_iter / threshold lines, src/adaboost.cpp:896-921): returns the number of stages and
+ * fills up to cap entries of stage_len / stage_thr (either may be NULL); CascadeBoost::get_num_iter = sum of stage_len */
+ERT_API int ert_cascade_stage_info(ert_ctx *ctx, int which, int *stage_len, int *stage_thr, int cap);
 /* svm_load_model  (src/svm.cpp:2876; inc/svm.h:77).  c_svc + rbf probability models. */
 ERT_API int ert_load_svm(ert_ctx *ctx, const char *path);
 ERT_API int ert_svm_nr_class(ert_ctx *ctx);   /* svm_get_nr_class (inc/svm.h:81) */
+ERT_API int ert_svm_total_sv(ert_ctx *ctx);   /* svm_get_nr_sv (inc/svm.h:84) */
+ERT_API int ert_svm_labels(ert_ctx *ctx, int *label);   /* svm_get_labels (inc/svm.h:82); returns nr_class */
+ERT_API double ert_svm_gamma(ert_ctx *ctx);   /* model->param.gamma */
 /* u8 features: 1 (default) = RBF distances as two exact-integer tcgen05 GEMMs (kind::i8); 0 = FP64 CUDA-core kernel */
 ERT_API int ert_set_svm_tensor_cores(ert_ctx *ctx, int on);
 ERT_API int ert_svm_dims(ert_ctx *ctx);
@@ -208,6 +222,10 @@ ERT_API int ert_classify_regions(ert_ctx *ctx, const uint8_t *plane, int width, 
 ERT_API int ert_lbp_hist(ert_ctx *ctx, const uint8_t *plane, int width, int height, int stride_bytes, const int32_t *rects, int n,
                          double *hist);
 
+/* ERFilter::calc_LBP(input(rect), 24)  (src/ER.cpp:819-845): the 24 x 24 mean-LBP code image of every rect, codes = n x 576 bytes */
+ERT_API int ert_calc_lbp(ert_ctx *ctx, const uint8_t *plane, int width, int height, int stride_bytes, const int32_t *rects, int n,
+                         uint8_t *codes);
+
 /* CascadeBoost::predict(vector<double> fv)  (src/adaboost.cpp:507-542) for n feature vectors of
  * `dims` doubles each; score = predict's return value (-DBL_MAX when a stage rejects). */
 ERT_API int ert_cascade_predict_batch(ert_ctx *ctx, int which, const double *fv, int n, int dims, double *score);
@@ -232,6 +250,10 @@ ERT_API int ert_er_track(ert_ctx *ctx, const ert_track_result **out);
  * (ch, x, y, w, h, area), channel-major as classify fills strong[ch] / weak[ch]. */
 ERT_API int ert_er_track_regions(ert_ctx *ctx, const uint8_t *bgr, int width, int height, int stride_bytes, const int32_t *strong,
                                  int n_strong, const int32_t *weak, int n_weak, const ert_track_result **out);
+/* The same with the frame given as the three planes compute_channels produced (channel[0..2] = Y, Cr, Cb, rows
+ * stride_bytes apart): exactly what ERFilter::er_track's (channel, Ycrcb) arguments hold (src/ER.cpp:532, 545-546). */
+ERT_API int ert_er_track_regions_ycc(ert_ctx *ctx, const uint8_t *y, const uint8_t *cr, const uint8_t *cb, int width, int height, int stride_bytes,
+                                     const int32_t *strong, int n_strong, const int32_t *weak, int n_weak, const ert_track_result **out);
 
 /* OCR::chain_run(src, thresh, slope) for a batch of regions (src/OCR.cpp:67-140; called from ERFilter::er_ocr,
  * src/ER.cpp:728-735): threshold(255 - src, OTSU) -> rotate_mat when |slope| > 0.01 -> ARAN(30) -> extract_feature

@@ -81,34 +81,37 @@ public:
 	size_t step;
 	uchar *data;
 	std::shared_ptr<std::vector<uchar> > buf;
+	int cn;   // channels: 1 (CV_8UC1) everywhere on the path; 3 only for the BGR / YCrCb frames handed to compute_channels
 
-	Mat() : rows(0), cols(0), step(0), data(nullptr) {}
-	Mat(int r, int c, int /*type*/) { create(r, c); }
+	Mat() : rows(0), cols(0), step(0), data(nullptr), cn(1) {}
+	Mat(int r, int c, int type) { create(r, c, type); }
 	// non-owning view of caller memory (used by the oracle's C wrapper)
-	Mat(int r, int c, int /*type*/, void *ext, size_t step_) : rows(r), cols(c), step(step_), data((uchar *)ext) {}
+	Mat(int r, int c, int type, void *ext, size_t step_) : rows(r), cols(c), step(step_), data((uchar *)ext), cn(type == CV_8UC3 ? 3 : 1) {}
 
-	void create(int r, int c)
+	void create(int r, int c, int type = CV_8UC1)
 	{
-		rows = r; cols = c; step = (size_t)c;
-		buf = std::make_shared<std::vector<uchar> >((size_t)r * c, (uchar)0);
+		cn = (type == CV_8UC3) ? 3 : 1;
+		rows = r; cols = c; step = (size_t)c * cn;
+		buf = std::make_shared<std::vector<uchar> >((size_t)r * c * cn, (uchar)0);
 		data = buf->data();
 	}
 	static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
-	int type() const { return CV_8UC1; }
+	int type() const { return cn == 3 ? CV_8UC3 : CV_8UC1; }
+	int channels() const { return cn; }
 	size_t total() const { return (size_t)rows * cols; }
 	bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
 
 	Mat clone() const
 	{
-		Mat m(rows, cols, CV_8UC1);
-		for (int i = 0; i < rows; i++) memcpy(m.data + (size_t)i * m.step, data + (size_t)i * step, (size_t)cols);
+		Mat m(rows, cols, type());
+		for (int i = 0; i < rows; i++) memcpy(m.data + (size_t)i * m.step, data + (size_t)i * step, (size_t)cols * cn);
 		return m;
 	}
 	Mat operator()(const Rect &r) const
 	{
 		Mat m;
-		m.rows = r.height; m.cols = r.width; m.step = step; m.buf = buf;
-		m.data = data + (size_t)r.y * step + r.x;
+		m.rows = r.height; m.cols = r.width; m.step = step; m.buf = buf; m.cn = cn;
+		m.data = data + (size_t)r.y * step + (size_t)r.x * cn;
 		return m;
 	}
 	uchar *ptr(int i = 0) { return data + (size_t)i * step; }

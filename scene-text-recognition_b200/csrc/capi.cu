@@ -156,13 +156,17 @@ int set_plane_table(ert_ctx *c, int n_planes, bool bgr_mode)
 	for (int p = 0; p < n_planes; p++) {
 		if (bgr_mode) {
 			const int f = p / 6, ch = p % 6;
-			t[p].src = c->d_ycc + ((size_t)f * 3 + (ch % 3)) * c->ycc_bytes;
+			t[p].z = f * 3 + (ch % 3);
+			t[p].src = c->d_ycc + (size_t)t[p].z * c->ycc_bytes;
 			t[p].invert = ch >= 3;
 		} else {
+			t[p].z = p;
 			t[p].src = c->d_ycc + (size_t)p * c->ycc_bytes;
 			t[p].invert = 0;
 		}
 	}
+	// the tile kernel's view of the plane buffer: (x, y, source plane), one haloed box per tile through the TMA unit
+	if (make_tile_tensor_map(&c->wk.tmap, c->d_ycc, c->W, c->H, c->pitch, bgr_mode ? n_planes / 2 : n_planes)) return -1;
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->d_planes, t.data(), sizeof(PlaneSrc) * n_planes, cudaMemcpyHostToDevice, c->stream));
 	// the table is tiny; make the pageable staging copy safe before `t` dies
 	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -206,6 +210,8 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 	cudaStream_t st = c->stream;
 	const ExtractParams EP = make_extract_params(c, n_planes);
 	const int dslot = c->device & 63;
+	// the device status word belongs to ONE batch: an overflow of an earlier batch must not poison this one
+	ERT_CUDA_CHECK(cudaMemsetAsync(c->wk.status, 0, sizeof(uint32_t), st));
 	if (c->tile_fifo) {
 		std::lock_guard<std::mutex> lk(g_fifo.mu);
 		if (g_fifo.last[dslot] && g_fifo.owner[dslot] != c) ERT_CUDA_CHECK(cudaStreamWaitEvent(st, g_fifo.last[dslot], 0));
@@ -361,6 +367,13 @@ int ert_set_thresh_step(ert_ctx *c, int step)
 	c->prm.thresh_step = step; return 0;
 }
 int ert_set_min_area(ert_ctx *c, int m) { c->prm.min_area = m; return 0; }
+int ert_set_params(ert_ctx *c, const ert_params *p)
+{
+	if (!c || !p) { set_error("bad arguments"); return -1; }
+	if (p->thresh_step < 5 || p->thresh_step > 255) { set_error("thresh_step %d unsupported (5..255)", p->thresh_step); return -1; }
+	c->prm = *p;     // read at enqueue time: applies to the next batch
+	return 0;
+}
 int ert_set_return_hist(ert_ctx *c, int on)
 {
 	if (on && !c->return_hist && c->planes_cap) { cudaStreamSynchronize(c->stream); free_workspace(c); }   // re-allocate with the host histogram buffer
@@ -385,7 +398,8 @@ int ert_set_tile_config(ert_ctx *c, int id)
 }
 int ert_set_capacity(ert_ctx *c, int kept, int pool)
 {
-	if (kept < 16 || pool < 16 || kept > (1 << 22)) { set_error("bad capacity"); return -1; }
+	// pool: k_track keeps one bit per candidate of a frame (6 planes x pool) in 48 KB of shared memory
+	if (kept < 16 || pool < 16 || kept > (1 << 22) || pool > 32768) { set_error("bad capacity (kept 16..4194304, pool 16..32768)"); return -1; }
 	cudaStreamSynchronize(c->stream);
 	free_workspace(c);
 	c->kept_cap = kept; c->pool_cap = pool;
@@ -453,6 +467,27 @@ int ert_load_cascade(ert_ctx *c, int which, const char *path)
 	return (int)h.stumps.size();
 }
 
+int ert_set_cascade(ert_ctx *c, int which, int n_stages, const int *stage_len, const int *stage_thr, int n_stumps, const int *dim, const double *thr,
+                    const double *cp, const double *cn)
+{
+	if (!c || which < 0 || which > 1 || n_stages < 1 || n_stumps < 1 || !stage_len || !stage_thr || !dim || !thr || !cp || !cn) { set_error("bad arguments"); return -1; }
+	long long total = 0;
+	for (int i = 0; i < n_stages; i++) { if (stage_len[i] < 0) { set_error("negative stage length"); return -1; } total += stage_len[i]; }
+	if (total != n_stumps) { set_error("stage lengths sum to %lld, %d stumps given", total, n_stumps); return -1; }
+	for (int j = 0; j < n_stumps; j++) if (dim[j] < 0 || dim[j] >= 1024) { set_error("stump dimension %d outside the 1024-bin feature", dim[j]); return -1; }
+	CascadeHost &h = c->casc[which];
+	h.loaded = false;
+	h.stage_len.assign(stage_len, stage_len + n_stages);
+	h.stage_thr.assign(stage_thr, stage_thr + n_stages);
+	h.stumps.resize((size_t)n_stumps);
+	for (int j = 0; j < n_stumps; j++) { Stump st; st.dim = dim[j]; st.thr = thr[j]; st.cp = cp[j]; st.cn = cn[j]; st.pad = 0; h.stumps[(size_t)j] = st; }
+	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));   // a batch in flight may still read the old tables
+	if (dev_upload(&h.d_stumps, h.stumps) || dev_upload(&h.d_len, h.stage_len) || dev_upload(&h.d_thr, h.stage_thr)) return -1;
+	h.loaded = true;
+	return n_stumps;
+}
+
 int ert_load_svm(ert_ctx *c, const char *path)
 {
 	FILE *f = fopen(path, "rb");
@@ -462,7 +497,14 @@ int ert_load_svm(ert_ctx *c, const char *path)
 	if (fread(txt.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); set_error("short read on %s", path); return -1; }
 	fclose(f); txt[sz] = 0;
 	SvmHost &m = c->svm;
-	m = SvmHost();
+	{
+		// a reload replaces the model: release the previous device tables, keep the caller's tensor-core choice
+		const bool keep_tc = m.use_tc;
+		cudaFree(m.d_sv); cudaFree(m.d_coef); cudaFree(m.d_rho); cudaFree(m.d_probA); cudaFree(m.d_probB);
+		cudaFree(m.d_label); cudaFree(m.d_nsv); cudaFree(m.d_start); cudaFree(m.d_svj); cudaFree(m.d_sve); cudaFree(m.d_ss);
+		m = SvmHost();
+		m.use_tc = keep_tc;
+	}
 	char *p = txt.data();
 	auto next_line = [&](char *&line) { line = p; char *e = strchr(p, '\n'); if (!e) { p += strlen(p); return; } *e = 0; p = e + 1; };
 	std::string svm_type, kernel_type;
@@ -493,6 +535,18 @@ int ert_load_svm(ert_ctx *c, const char *path)
 		set_error("%s: only c_svc + rbf models with probability estimates are supported (svm_type=%s kernel_type=%s)", path, svm_type.c_str(), kernel_type.c_str());
 		return -1;
 	}
+	{
+		const size_t npair = (size_t)m.nr_class * (m.nr_class - 1) / 2;
+		long long nsv_sum = 0;
+		for (int v : m.nsv) nsv_sum += v;
+		if (m.rho.size() != npair || m.probA.size() != npair || m.probB.size() != npair || m.label.size() != (size_t)m.nr_class ||
+		    m.nsv.size() != (size_t)m.nr_class || nsv_sum != m.l || m.nr_class > 4096 || m.l > (1 << 22)) {
+			set_error("%s: malformed model header (nr_class %d, total_sv %d, rho %zu, label %zu, nr_sv %zu summing to %lld)", path, m.nr_class, m.l,
+			          m.rho.size(), m.label.size(), m.nsv.size(), nsv_sum);
+			m = SvmHost();
+			return -1;
+		}
+	}
 	const int k1 = m.nr_class - 1;
 	m.coef.assign((size_t)k1 * m.l, 0.0);
 	std::vector<int> idx; std::vector<double> val; std::vector<int> rowstart((size_t)m.l + 1, 0);
@@ -510,13 +564,15 @@ int ert_load_svm(ert_ctx *c, const char *path)
 			s = e + 1;
 			const double v = strtod(s, &e);
 			s = e;
+			if (id < 0 || id >= (1 << 20)) { set_error("%s: support vector %d has feature index %ld outside 0..%d", path, i, id, (1 << 20) - 1); m = SvmHost(); return -1; }
 			idx.push_back((int)id); val.push_back(v);
 			if (id > maxidx) maxidx = (int)id;
 		}
 	}
 	rowstart[m.l] = (int)idx.size();
 	m.dims = maxidx + 1;
-	if (m.dims < 1) { set_error("%s: no support vector entries", path); return -1; }
+	if (m.dims < 1) { set_error("%s: no support vector entries", path); m = SvmHost(); return -1; }
+	if ((size_t)m.l * (size_t)m.dims > ((size_t)1 << 31)) { set_error("%s: %d support vectors x %d dimensions is more than this loader densifies", path, m.l, m.dims); m = SvmHost(); return -1; }
 	m.sv.assign((size_t)m.l * m.dims, 0.0);
 	for (int i = 0; i < m.l; i++)
 		for (int q = rowstart[i]; q < rowstart[i + 1]; q++) if (idx[q] >= 0) m.sv[(size_t)i * m.dims + idx[q]] = val[q];
@@ -560,7 +616,24 @@ int ert_load_svm(ert_ctx *c, const char *path)
 	return m.l;
 }
 
+int ert_cascade_stage_info(ert_ctx *c, int which, int *stage_len, int *stage_thr, int cap)
+{
+	if (!c || which < 0 || which > 1 || !c->casc[which].loaded) { set_error("cascade %d is not loaded", which); return -1; }
+	const CascadeHost &h = c->casc[which];
+	const int n = (int)h.stage_len.size();
+	for (int i = 0; i < n && i < cap; i++) { if (stage_len) stage_len[i] = h.stage_len[i]; if (stage_thr) stage_thr[i] = h.stage_thr[i]; }
+	return n;
+}
+
 int ert_svm_nr_class(ert_ctx *c) { return c->svm.loaded ? c->svm.nr_class : -1; }
+int ert_svm_total_sv(ert_ctx *c) { return c->svm.loaded ? c->svm.l : -1; }
+int ert_svm_labels(ert_ctx *c, int *label)
+{
+	if (!c || !c->svm.loaded || !label) { set_error("svm model is not loaded"); return -1; }
+	for (int i = 0; i < c->svm.nr_class; i++) label[i] = c->svm.label[i];
+	return c->svm.nr_class;
+}
+double ert_svm_gamma(ert_ctx *c) { return c->svm.loaded ? c->svm.gamma : 0.0; }
 int ert_set_svm_tensor_cores(ert_ctx *c, int on) { c->svm.use_tc = on != 0; return 0; }
 int ert_svm_dims(ert_ctx *c) { return c->svm.loaded ? c->svm.dims : -1; }
 
@@ -698,7 +771,7 @@ int ert_nms_nodes(ert_ctx *c, const ert_node *nodes, int n, int W, int H, int32_
 }
 
 static int classify_common(ert_ctx *c, const uint8_t *plane, int W, int H, int stride, const int32_t *rects, int n, int32_t *label,
-                           double *ss, double *ws, uint8_t *hist_u8, double *hist_f64, bool need_cascade)
+                           double *ss, double *ws, uint8_t *hist_u8, double *hist_f64, bool need_cascade, uint8_t *codes = nullptr)
 {
 	if (!c || !plane || !rects || n < 0 || stride < W) { set_error("bad arguments"); return -1; }
 	if (n == 0) return 0;
@@ -713,7 +786,7 @@ static int classify_common(ert_ctx *c, const uint8_t *plane, int W, int H, int s
 	const size_t nodes_b = sizeof(OutNode) * (size_t)n, pool_b = sizeof(int32_t) * (size_t)n;
 	// s0: plane, s1: nodes + pool + counts + PlaneSrc, s2: hist, s3: label + scores
 	if (c->s0.ensure((size_t)pitch * H) || c->s1.ensure(nodes_b + pool_b + 64 + sizeof(PlaneSrc)) || c->s2.ensure((size_t)n * 1024) ||
-	    c->s3.ensure((size_t)n * (sizeof(int32_t) + 2 * sizeof(double)) + 64)) return -1;
+	    c->s3.ensure((size_t)n * (sizeof(int32_t) + 2 * sizeof(double)) + 64) || (codes && c->s4.ensure((size_t)n * 576))) return -1;
 	ERT_CUDA_CHECK(cudaMemcpy2DAsync(c->s0.p, (size_t)pitch, plane, (size_t)stride, (size_t)W, (size_t)H, cudaMemcpyHostToDevice, st));
 	std::vector<OutNode> hn((size_t)n);
 	std::vector<int32_t> hp((size_t)n);
@@ -733,7 +806,7 @@ static int classify_common(ert_ctx *c, const uint8_t *plane, int W, int H, int s
 	ERT_CUDA_CHECK(cudaMemcpyAsync(d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, st));
 	ERT_CUDA_CHECK(cudaMemcpyAsync(d_ps, &ps, sizeof ps, cudaMemcpyHostToDevice, st));
 	ClassifyParams CP; CP.pitch = pitch; CP.pool_cap = n; CP.node_cap = n;
-	if (launch_lbp_hist(CP, 1, d_ps, d_nodes, d_pool, d_counts, c->d_aran_tbl, (uint8_t *)c->s2.p, st)) return -1;
+	if (launch_lbp_hist(CP, 1, d_ps, d_nodes, d_pool, d_counts, c->d_aran_tbl, (uint8_t *)c->s2.p, st, codes ? (uint8_t *)c->s4.p : nullptr)) return -1;
 	int32_t *d_label = (int32_t *)c->s3.p;
 	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
 	double *d_ws = d_ss + n;
@@ -745,6 +818,7 @@ static int classify_common(ert_ctx *c, const uint8_t *plane, int W, int H, int s
 	if (ss) ERT_CUDA_CHECK(cudaMemcpy(ss, d_ss, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
 	if (ws) ERT_CUDA_CHECK(cudaMemcpy(ws, d_ws, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
 	if (hist_u8) ERT_CUDA_CHECK(cudaMemcpy(hist_u8, c->s2.p, (size_t)n * 1024, cudaMemcpyDeviceToHost));
+	if (codes) ERT_CUDA_CHECK(cudaMemcpy(codes, c->s4.p, (size_t)n * 576, cudaMemcpyDeviceToHost));
 	if (hist_f64) {
 		std::vector<uint8_t> tmp((size_t)n * 1024);
 		ERT_CUDA_CHECK(cudaMemcpy(tmp.data(), c->s2.p, (size_t)n * 1024, cudaMemcpyDeviceToHost));
@@ -762,6 +836,12 @@ int ert_classify_regions(ert_ctx *c, const uint8_t *plane, int W, int H, int str
 int ert_lbp_hist(ert_ctx *c, const uint8_t *plane, int W, int H, int stride, const int32_t *rects, int n, double *hist)
 {
 	return classify_common(c, plane, W, H, stride, rects, n, nullptr, nullptr, nullptr, nullptr, hist, false);
+}
+
+int ert_calc_lbp(ert_ctx *c, const uint8_t *plane, int W, int H, int stride, const int32_t *rects, int n, uint8_t *codes)
+{
+	if (!codes) { set_error("bad arguments"); return -1; }
+	return classify_common(c, plane, W, H, stride, rects, n, nullptr, nullptr, nullptr, nullptr, nullptr, false, codes);
 }
 
 int ert_cascade_predict_batch(ert_ctx *c, int which, const double *fv, int n, int dims, double *score)

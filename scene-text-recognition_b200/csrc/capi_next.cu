@@ -236,10 +236,13 @@ int ert_er_track(ert_ctx *c, const ert_track_result **out)
 	return finish_track(c, n_frames, out);
 }
 
-int ert_er_track_regions(ert_ctx *c, const uint8_t *bgr, int W, int H, int stride, const int32_t *strong, int ns, const int32_t *weak, int nw,
-                         const ert_track_result **out)
+// strong / weak rows -> candidate records; frame = either one BGR image (converted on the device) or its three
+// Y / Cr / Cb planes as compute_channels delivers them (channel[0..2], src/ER.cpp:122-124)
+static int track_regions_common(ert_ctx *c, const uint8_t *bgr, const uint8_t *const ycc[3], int W, int H, int stride, const int32_t *strong, int ns,
+                                const int32_t *weak, int nw, const ert_track_result **out)
 {
-	if (!c || !bgr || W < 1 || H < 1 || stride < 3 * W || ns < 0 || nw < 0 || (ns && !strong) || (nw && !weak)) { set_error("bad arguments"); return -1; }
+	const int min_stride = bgr ? 3 * W : W;
+	if (!c || W < 1 || H < 1 || stride < min_stride || ns < 0 || nw < 0 || (ns && !strong) || (nw && !weak)) { set_error("bad arguments"); return -1; }
 	const int n = ns + nw;
 	std::vector<ert_tracked> hc((size_t)std::max(n, 1));
 	for (int i = 0; i < n; i++) {
@@ -259,11 +262,16 @@ int ert_er_track_regions(ert_ctx *c, const uint8_t *bgr, int W, int H, int strid
 	cudaStream_t st = c->stream;
 	const int pitch = extract_pitch(W);
 	const size_t in_b = (size_t)stride * H, plane_b = (size_t)pitch * H;
-	if (c->o0.ensure(in_b) || c->o1.ensure(plane_b * 3)) return -1;
+	if ((bgr && c->o0.ensure(in_b)) || c->o1.ensure(plane_b * 3)) return -1;
 	// the track buffers may be shared with a batch in flight: this entry point is synchronous and owns them while it runs
 	if (ensure_track(c, 1, n)) return -1;
-	ERT_CUDA_CHECK(cudaMemcpyAsync(c->o0.p, bgr, in_b, cudaMemcpyHostToDevice, st));
-	if (launch_channels((const uint8_t *)c->o0.p, in_b, stride, W, H, 1, (uint8_t *)c->o1.p, pitch, st)) return -1;
+	if (bgr) {
+		ERT_CUDA_CHECK(cudaMemcpyAsync(c->o0.p, bgr, in_b, cudaMemcpyHostToDevice, st));
+		if (launch_channels((const uint8_t *)c->o0.p, in_b, stride, W, H, 1, (uint8_t *)c->o1.p, pitch, st)) return -1;
+	} else {
+		for (int k = 0; k < 3; k++)
+			ERT_CUDA_CHECK(cudaMemcpy2DAsync((uint8_t *)c->o1.p + (size_t)k * plane_b, (size_t)pitch, ycc[k], (size_t)stride, (size_t)W, (size_t)H, cudaMemcpyHostToDevice, st));
+	}
 	const int32_t cnt[2] = {n, ns};
 	if (n) ERT_CUDA_CHECK(cudaMemcpyAsync(c->tk.cand, hc.data(), sizeof(ert_tracked) * (size_t)n, cudaMemcpyHostToDevice, st));
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->tk.n_cand, &cnt[0], sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -273,6 +281,21 @@ int ert_er_track_regions(ert_ctx *c, const uint8_t *bgr, int W, int H, int strid
 	if (launch_track(c->tk, 1, c->h_cand, c->h_cand_off, c->h_nstrong, c->h_track_off, c->h_tracked, st)) return -1;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[11], st));
 	return finish_track(c, 1, out);     // synchronises: the staging vector and cnt[] may go out of scope afterwards
+}
+
+int ert_er_track_regions(ert_ctx *c, const uint8_t *bgr, int W, int H, int stride, const int32_t *strong, int ns, const int32_t *weak, int nw,
+                         const ert_track_result **out)
+{
+	if (!bgr) { set_error("bad arguments"); return -1; }
+	return track_regions_common(c, bgr, nullptr, W, H, stride, strong, ns, weak, nw, out);
+}
+
+int ert_er_track_regions_ycc(ert_ctx *c, const uint8_t *y, const uint8_t *cr, const uint8_t *cb, int W, int H, int stride, const int32_t *strong, int ns,
+                             const int32_t *weak, int nw, const ert_track_result **out)
+{
+	if (!y || !cr || !cb) { set_error("bad arguments"); return -1; }
+	const uint8_t *const ycc[3] = {y, cr, cb};
+	return track_regions_common(c, nullptr, ycc, W, H, stride, strong, ns, weak, nw, out);
 }
 
 int ert_ocr_chain_run_plane(ert_ctx *c, const uint8_t *plane, int W, int H, int stride, const ert_ocr_region *regions, int n,

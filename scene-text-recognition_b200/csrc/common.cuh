@@ -45,6 +45,7 @@ struct OutNode { int32_t level, area, x, y, w, h, parent, nchild; };
 struct PlaneSrc {
 	const uint8_t *src;   // u8 plane, row pitch = pitch bytes
 	int invert;           // 1: value = 255 - src
+	int z;                // index of the source plane inside the context's plane buffer (third coordinate of the tile tensor map)
 };
 
 struct ExtractParams {

@@ -40,7 +40,7 @@ constexpr int HIST_WARPS = 8;
 __global__ void __launch_bounds__(HIST_WARPS * 32) k_lbp_hist(ClassifyParams P, const PlaneSrc *__restrict__ planes,
                                                                const OutNode *__restrict__ nodes, const int32_t *__restrict__ pool,
                                                                const int32_t *__restrict__ counts, const uint8_t *__restrict__ aran_tbl,
-                                                               uint8_t *__restrict__ hist_out)
+                                                               uint8_t *__restrict__ hist_out, uint8_t *__restrict__ codes_out)
 {
 	__shared__ uint8_t s_patch[HIST_WARPS][26 * 26 + 28];
 	__shared__ uint32_t s_hist[HIST_WARPS][1024];
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_lbp_hist(ClassifyParams P, 
 		const int code = (8 * v0 > s) | ((8 * v1 > s) << 1) | ((8 * v2 > s) << 2) | ((8 * v3 > s) << 3) |
 		                 ((8 * v4 > s) << 4) | ((8 * v5 > s) << 5) | ((8 * v6 > s) << 6) | ((8 * v7 > s) << 7);
 		atomicAdd(&hist[(i / 12) * 512 + (j / 12) * 256 + code], 1u);
+		if (codes_out) codes_out[((size_t)plane * P.pool_cap + r) * 576 + t] = (uint8_t)code;   // calc_LBP's 24x24 image (src/ER.cpp:819-845)
 	}
 	__syncwarp();
 	uint32_t *out = reinterpret_cast<uint32_t *>(hist_out + ((size_t)plane * P.pool_cap + r) * 1024);
@@ -259,10 +260,10 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_cascade_stage(const uint8_t *
 }
 
 int launch_lbp_hist(const ClassifyParams &P, int n_planes, const PlaneSrc *planes, const OutNode *nodes, const int32_t *pool,
-                    const int32_t *counts, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st)
+                    const int32_t *counts, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st, uint8_t *codes_out)
 {
 	dim3 grid((P.pool_cap + HIST_WARPS - 1) / HIST_WARPS, n_planes);
-	k_lbp_hist<<<grid, HIST_WARPS * 32, 0, st>>>(P, planes, nodes, pool, counts, aran_tbl, hist_out);
+	k_lbp_hist<<<grid, HIST_WARPS * 32, 0, st>>>(P, planes, nodes, pool, counts, aran_tbl, hist_out, codes_out);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }

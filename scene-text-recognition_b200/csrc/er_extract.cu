@@ -859,7 +859,8 @@ int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 
 // tile configurations (selectable at run time for tuning; id 0 is the default)
 struct TileCfg { int tw, th, nt; };
-static const TileCfg g_tile_cfgs[] = {{64, 32, 512}, {64, 32, 256}, {128, 32, 512}, {32, 32, 256}, {64, 32, 512}};
+// 0 = k_tile_build2 (er_tile.cu); 1 = the round-1 kernel (also the record-less debug mode local_union = 0); 2 = round-1 with a shared work queue
+static const TileCfg g_tile_cfgs[] = {{64, 32, 256}, {64, 32, 512}, {64, 32, 512}};
 int tile_config_count() { return (int)(sizeof(g_tile_cfgs) / sizeof(g_tile_cfgs[0])); }
 size_t ring_words_per_plane(int W, int H)
 {
@@ -922,12 +923,10 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	ERT_CUDA_CHECK(cudaMemsetAsync(wk.kept_count, 0, sizeof(uint32_t) * P.n_planes, st));
 	if (ev_tile_begin) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_begin, st));
 	int rc = -1;
-	switch (wk.tile_cfg) {
-	case 1: rc = launch_tile<64, 32, 256, 8, true>(P, d_planes, wk, local_union, st); break;
-	case 2: rc = launch_tile<128, 32, 512, 8, true>(P, d_planes, wk, local_union, st); break;
-	case 3: rc = launch_tile<32, 32, 256, 8, true>(P, d_planes, wk, local_union, st); break;
-	case 4: rc = launch_tile<64, 32, 512, 12, false>(P, d_planes, wk, local_union, st); break;   // shared work queue instead of per-warp shares
-	default: rc = launch_tile<64, 32, 512, 8, true>(P, d_planes, wk, local_union, st); break;
+	switch (local_union ? wk.tile_cfg : 1) {
+	case 1: rc = launch_tile<64, 32, 512, 8, true>(P, d_planes, wk, local_union, st); break;
+	case 2: rc = launch_tile<64, 32, 512, 12, false>(P, d_planes, wk, local_union, st); break;   // shared work queue instead of per-warp shares
+	default: rc = launch_tile_v2(P, d_planes, wk, st); break;
 	}
 	if (rc) return rc;
 	if (ev_tile_end) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_end, st));

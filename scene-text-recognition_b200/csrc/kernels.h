@@ -5,6 +5,9 @@
 
 namespace ert {
 
+// CUtensorMap (128 bytes, 64-byte aligned) without pulling <cuda.h> into every translation unit
+struct alignas(64) TileTensorMap { uint64_t opaque[16]; };
+
 struct ExtractWork {
 	uint32_t *par;          // [n_planes][N] keyed forest
 	NodeAttr *attr;         // [n_planes][N] node attributes (sparse)
@@ -19,6 +22,7 @@ struct ExtractWork {
 	int tile_cfg;           // index into the tile configuration table
 	unsigned long long *prof;   // optional [16] per-phase cycle sums of k_tile_build (debug)
 	uint32_t *ring_rec;     // [n_planes][tiles][2*(TW+TH)] root keys on the tile sides (seam records)
+	TileTensorMap tmap;     // (x, y, source plane) view of the plane buffer for k_tile_build2's haloed TMA box
 };
 
 struct NmsParams {
@@ -91,6 +95,8 @@ struct OcrJob {
 int launch_ocr_features(const OcrJob *d_jobs, int n, uint8_t *d_feat1800, uint8_t *d_img30, cudaStream_t st);
 
 int extract_pitch(int W);
+int make_tile_tensor_map(TileTensorMap *out, const uint8_t *d_planes0, int W, int H, int pitch, int n_src_planes);
+int launch_tile_v2(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st);
 int tile_config_count();
 size_t ring_words_per_plane(int W, int H);
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st);
@@ -105,7 +111,7 @@ int launch_nms(const NmsParams &P, int n_planes, const KeptRec *kept, const uint
                uint32_t *status, cudaStream_t st);
 
 int launch_lbp_hist(const ClassifyParams &P, int n_planes, const PlaneSrc *planes, const OutNode *nodes, const int32_t *pool,
-                    const int32_t *counts, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st);
+                    const int32_t *counts, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st, uint8_t *codes_out = nullptr);
 int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const int32_t *counts, int pool_cap, const CascadeDev &strong,
                       const CascadeDev &weak, int n_strong, int n_weak, int32_t *label, double *sscore, double *wscore, cudaStream_t st);
 int launch_cascade_f64(const double *fv, size_t row_stride, int n_rows, const CascadeDev &strong, const CascadeDev &weak,

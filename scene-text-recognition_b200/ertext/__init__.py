@@ -90,6 +90,8 @@ EXPORTS = [
     "ert_cascade_predict_batch", "ert_cascade_classify_u8", "ert_svm_predict_probability_batch",
     "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
     "ert_bench_cascade_u8", "ert_bench_svm_u8",
+    "ert_set_params", "ert_set_cascade", "ert_cascade_stage_info", "ert_svm_total_sv", "ert_svm_labels", "ert_svm_gamma", "ert_calc_lbp",
+    "ert_er_track_regions_ycc",
 ]
 
 _lib = None

@@ -87,6 +87,34 @@ def test_kept_capacity_overflow_is_reported(ert):
         ert.set_capacity(16384, 2048); ert.set_min_area(120)
 
 
+def test_status_word_belongs_to_one_batch(ert):
+    """an overflow reported for one batch must not poison the next batch on the same context (the status word is per batch)"""
+    img = make_plane(1, 300, 300, "noise")
+    ert.set_capacity(64, 64)
+    ert.set_min_area(3)
+    try:
+        assert ert.planes_detect(img).status & 2
+        ert.set_min_area(120)                      # does not touch the workspace: same context, same status word
+        res = ert.planes_detect(np.full((64, 64), 77, np.uint8))
+        assert res.status == 0 and len(res.planes[0].nodes) == 1
+    finally:
+        ert.set_capacity(16384, 2048); ert.set_min_area(120)
+
+
+@pytest.mark.parametrize("cfg", [1, 2])
+def test_tile_kernel_generations_agree(ert, cfg):
+    """the round-1 tile kernels (kept for A/B) and k_tile_build2 produce byte-identical results"""
+    imgs = [make_plane(7, 257, 191, k) for k in ("noise", "blobs", "walls", "checker")] 
+    base = [ert.planes_detect(im) for im in imgs]
+    ert.set_tile_config(cfg)
+    try:
+        for im, b in zip(imgs, base):
+            g = ert.planes_detect(im)
+            assert g.planes[0].nodes.tobytes() == b.planes[0].nodes.tobytes() and g.planes[0].pool.tobytes() == b.planes[0].pool.tobytes()
+    finally:
+        ert.set_tile_config(0)
+
+
 @pytest.mark.gpu
 def test_enqueue_planes_matches_planes_detect_and_overlaps_scales(ert):
     """asynchronous plane entry point: two contexts, two plane sizes in flight at once == the synchronous calls"""
