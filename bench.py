@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the er_track / chain_run leg (SURVEY 8f rows, outside the timed region)")
     ap.add_argument("--no-tile-fifo", action="store_true", help="A/B: do not chain the tile kernels of the contexts in submission order")
+    ap.add_argument("--no-stream-split", action="store_true", help="A/B: run every stage of a batch on ONE stream (no high-priority post stream)")
     ap.add_argument("--contexts", type=int, default=5, help="contexts / streams used round-robin (copy/compute overlap)")
     return ap.parse_args()
 
@@ -218,6 +219,8 @@ def run_ours(a, rank, local_rank, world):
         c.set_stream(s.cuda_stream)
         if a.no_tile_fifo:
             c.set_tile_fifo(False)
+        if a.no_stream_split:
+            c.set_stream_split(False)
 
     gatherer = edist.RegionGatherer(dev) if world > 1 else None
     stats = {"tile_ms": [], "extract_ms": [], "nms_ms": [], "classify_ms": [], "launches": 0, "d2h": 0, "regions": 0, "kept": 0, "steps": 0}

@@ -145,6 +145,10 @@ ERT_API int ert_set_nms_sequential(ert_ctx *ctx, int on);
 /* scheduling: 1 (default) = the tile-build kernels of all contexts on a device run in submission order (an event
  * chain); keeps the oldest batch in flight from being starved when several contexts are used round-robin */
 ERT_API int ert_set_tile_fifo(ert_ctx *ctx, int on);
+/* scheduling: 1 (default) = the stages after the tile-build kernel (seams, fold, refit, NMS, classify, result compaction,
+ * er_track) run on a second, highest-priority stream of the context and are joined back into the context's stream:
+ * their narrow kernels then take CTA slots between the tile CTAs of the other contexts' batches; 0 = one stream */
+ERT_API int ert_set_stream_split(ert_ctx *ctx, int on);
 /* tuning / A-B: which tile-build kernel runs: 0 (default) = k_tile_build2 (64x32 tile + halo through one tensor-map TMA
  * box, 256 threads, 4 pixels per lane); 1 = the round-1 kernel (512 threads, 32 row copies); 2 = round-1 with a shared
  * work queue.  All produce identical results. */
@@ -266,6 +270,39 @@ ERT_API int ert_ocr_chain_run_plane(ert_ctx *ctx, const uint8_t *plane, int widt
 /* OCR::extract_feature path only (no SVM model needed): out->value/label/prob_all are NULL. */
 ERT_API int ert_ocr_features_plane(ert_ctx *ctx, const uint8_t *plane, int width, int height, int stride_bytes,
                                    const ert_ocr_region *regions, int n, const ert_ocr_result **out);
+
+/* ---- multi-GPU: the final region gather -----------------------------------------------------------
+ * One process per GPU; rank r of G owns frames {f : f mod G = r}; no collective on the compute path.  After a batch the
+ * labelled regions (strong[] / weak[] of ERFilter::classify, src/ER.cpp:507-528) of all ranks are gathered on every rank:
+ * packed on the device, per-rank counts by ncclAllGather, then ONE grouped exchange of exactly the records each rank
+ * holds, on the gather's own side stream, pipelined behind the data path (collected one or two batches later).
+ * NCCL is loaded at run time (libnccl.so.2); world = 1 needs no NCCL at all. */
+typedef struct ert_dist ert_dist;
+typedef struct {
+	int32_t frame, plane;          /* global frame id (frame_ids[local frame]) and channel 0..5 */
+	int32_t level, area, x, y, w, h;
+	int32_t label;                 /* ERT_LABEL_STRONG / ERT_LABEL_WEAK */
+	int32_t pool_index;            /* position inside the plane's pool (classify's push order) */
+} ert_region_record;
+typedef struct {
+	int32_t world;
+	int32_t n_records;
+	const int32_t *rank_offset;            /* world + 1: records of rank r are [rank_offset[r], rank_offset[r+1]) */
+	const ert_region_record *records;      /* pinned host memory, valid until the next collect on this handle */
+	long long sequence;                    /* which enqueue this is (0, 1, 2, ...) */
+} ert_gather_result;
+/* rank 0: a fresh NCCL unique id (128 bytes) to hand to every rank out of band (torch.distributed, MPI, a file) */
+ERT_API int ert_dist_unique_id(void *id128);
+/* collective over all ranks (ncclCommInitRank); id128 may be NULL for world = 1 */
+ERT_API ert_dist *ert_dist_create(int device, int rank, int world, const void *id128, int max_records_per_rank);
+ERT_API void ert_dist_destroy(ert_dist *d);
+/* call right after ert_enqueue_host / ert_detect_classify_device on ctx (batch still in flight), on every rank, in the same
+ * order: packs the batch's labelled regions on the device and starts the gather; returns at once.  frame_ids[n_frames] = the
+ * global ids of the batch's frames (NULL: 0..n_frames-1).  At most 3 gathers may be outstanding. */
+ERT_API int ert_gather_regions_enqueue(ert_dist *d, ert_ctx *ctx, const int32_t *frame_ids, int n_frames);
+/* the oldest outstanding gather; blocks only if it has not finished (collective when it has to drain) */
+ERT_API int ert_gather_regions_collect(ert_dist *d, const ert_gather_result **out);
+ERT_API int ert_gather_regions_outstanding(ert_dist *d);
 
 /* ---- plumbing -------------------------------------------------------------------------------- */
 /* use an external CUDA stream (cudaStream_t as integer, e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */

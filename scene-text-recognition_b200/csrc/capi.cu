@@ -216,7 +216,9 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 		std::lock_guard<std::mutex> lk(g_fifo.mu);
 		if (g_fifo.last[dslot] && g_fifo.owner[dslot] != c) ERT_CUDA_CHECK(cudaStreamWaitEvent(st, g_fifo.last[dslot], 0));
 	}
-	if (launch_extract(EP, c->d_planes, c->wk, c->local_union, st, c->ev[8], c->ev[9])) return -1;
+	if (launch_extract(EP, c->d_planes, c->wk, c->local_union, st, c->ev[8], c->ev[9], c->work_stream())) return -1;
+	const cudaStream_t st_main = st;
+	st = c->work_stream();
 	if (c->tile_fifo) {
 		std::lock_guard<std::mutex> lk(g_fifo.mu);
 		g_fifo.last[dslot] = c->ev[9]; g_fifo.owner[dslot] = c;      // ev[9] is recorded right after the tile kernel
@@ -250,6 +252,11 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 	if (upto >= ERT_STAGE_TRACK) {
 		if (c->frames_cap != -1) { set_error("ERT_STAGE_TRACK needs a BGR batch (er_track reads the YCrCb frame)"); return -1; }
 		if (enqueue_track(c, n_planes / 6)) return -1;
+	}
+	if (st != st_main) {
+		// join: whatever is enqueued on the context's stream afterwards (and a synchronize on it) sees the finished batch
+		ERT_CUDA_CHECK(cudaEventRecord(c->ev_post_done, st));
+		ERT_CUDA_CHECK(cudaStreamWaitEvent(st_main, c->ev_post_done, 0));
 	}
 	return 0;
 }
@@ -332,6 +339,12 @@ ert_ctx *ert_create(const ert_params *params, int device)
 	c->device = device;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); delete c; return nullptr; }
 	for (int i = 0; i < 12; i++) cudaEventCreate(&c->ev[i]);
+	{
+		int least = 0, greatest = 0;
+		cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		if (cudaStreamCreateWithPriority(&c->post_stream, cudaStreamNonBlocking, greatest) != cudaSuccess) c->post_stream = nullptr;
+		cudaEventCreateWithFlags(&c->ev_post_done, cudaEventDisableTiming);
+	}
 	build_aran_table(c);
 	if (cudaMalloc((void **)&c->d_aran_tbl, 64) != cudaSuccess || cudaMemcpy(c->d_aran_tbl, c->aran_tbl_h, 64, cudaMemcpyHostToDevice) != cudaSuccess) {
 		set_error("aran table upload failed"); delete c; return nullptr;
@@ -357,6 +370,8 @@ void ert_destroy(ert_ctx *c)
 	c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
 	free_next(c);
 	for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
+	if (c->post_stream) { cudaStreamSynchronize(c->post_stream); cudaStreamDestroy(c->post_stream); }
+	if (c->ev_post_done) cudaEventDestroy(c->ev_post_done);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -382,6 +397,7 @@ int ert_set_return_hist(ert_ctx *c, int on)
 }
 int ert_set_nms_sequential(ert_ctx *c, int on) { c->nms_sequential = on ? 1 : 0; return 0; }
 int ert_set_tile_fifo(ert_ctx *c, int on) { c->tile_fifo = on ? 1 : 0; return 0; }
+int ert_set_stream_split(ert_ctx *c, int on) { cudaStreamSynchronize(c->stream); if (c->post_stream) cudaStreamSynchronize(c->post_stream); c->split_streams = on ? 1 : 0; return 0; }
 int ert_set_tile_local_union(ert_ctx *c, int on) { c->local_union = on ? 1 : 0; return 0; }
 int ert_debug_phase_cycles(ert_ctx *c, int enable, unsigned long long *out16)
 {

@@ -192,7 +192,7 @@ namespace ert {
 int enqueue_track(ert_ctx *c, int n_frames)
 {
 	if (ensure_track(c, n_frames, 6 * c->pool_cap)) return -1;
-	cudaStream_t st = c->stream;
+	cudaStream_t st = c->pending ? c->work_stream() : c->stream;   // fused with a batch: the batch's post stream; stand-alone: the context's stream
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[10], st));
 	if (launch_track_gather(c->tk, n_frames, c->d_out_nodes, c->d_out_pool, c->d_out_counts, c->d_label, c->kept_cap, c->pool_cap, st)) return -1;
 	if (launch_calc_color(c->tk, n_frames, c->d_ycc, c->ycc_bytes, c->pitch, st)) return -1;

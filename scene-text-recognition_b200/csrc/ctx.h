@@ -72,6 +72,10 @@ struct ert_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool own_stream = true;
+	cudaStream_t post_stream = nullptr;   // highest priority: everything after the tile kernel (seams .. result compaction, er_track)
+	cudaEvent_t ev_post_done = nullptr;   // joins the post stream back into `stream`
+	int split_streams = 1;
+	cudaStream_t work_stream() const { return (split_streams && post_stream) ? post_stream : stream; }
 	cudaEvent_t ev[12];
 	int local_union = 1;
 	int nms_sequential = 0;  // 1: run the reference's walk on one thread per plane (audit / A-B) instead of the level-parallel form

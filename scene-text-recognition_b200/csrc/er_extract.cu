@@ -860,7 +860,8 @@ int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 // tile configurations (selectable at run time for tuning; id 0 is the default)
 struct TileCfg { int tw, th, nt; };
 // 0 = k_tile_build2 (er_tile.cu); 1 = the round-1 kernel (also the record-less debug mode local_union = 0); 2 = round-1 with a shared work queue
-static const TileCfg g_tile_cfgs[] = {{64, 32, 256}, {64, 32, 512}, {64, 32, 512}};
+// 3..5 = k_tile_build2 variants for A/B (see er_tile.cu: OPT bits)
+static const TileCfg g_tile_cfgs[] = {{64, 32, 256}, {64, 32, 512}, {64, 32, 512}, {64, 32, 256}, {64, 32, 256}, {64, 32, 256}};
 int tile_config_count() { return (int)(sizeof(g_tile_cfgs) / sizeof(g_tile_cfgs[0])); }
 size_t ring_words_per_plane(int W, int H)
 {
@@ -915,7 +916,7 @@ int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, i
 }
 
 int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
-                   cudaEvent_t ev_tile_begin, cudaEvent_t ev_tile_end)
+                   cudaEvent_t ev_tile_begin, cudaEvent_t ev_tile_end, cudaStream_t st_post)
 {
 	const TileCfg tc = g_tile_cfgs[(wk.tile_cfg >= 0 && wk.tile_cfg < tile_config_count()) ? wk.tile_cfg : 0];
 	const int TILE_W = tc.tw, TILE_H = tc.th;
@@ -926,10 +927,20 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	switch (local_union ? wk.tile_cfg : 1) {
 	case 1: rc = launch_tile<64, 32, 512, 8, true>(P, d_planes, wk, local_union, st); break;
 	case 2: rc = launch_tile<64, 32, 512, 12, false>(P, d_planes, wk, local_union, st); break;   // shared work queue instead of per-warp shares
-	default: rc = launch_tile_v2(P, d_planes, wk, st); break;
+	case 3: rc = launch_tile_v2(P, d_planes, wk, st, 0); break;
+	case 4: rc = launch_tile_v2(P, d_planes, wk, st, 1); break;
+	case 5: rc = launch_tile_v2(P, d_planes, wk, st, 2); break;
+	default: rc = launch_tile_v2(P, d_planes, wk, st, 3); break;
 	}
 	if (rc) return rc;
 	if (ev_tile_end) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_end, st));
+	if (st_post && st_post != st) {
+		// everything after the SM-filling tile kernel runs on the context's high-priority stream: its narrow, latency-bound
+		// kernels get CTA slots as soon as tile CTAs of OTHER batches retire, instead of queueing behind whole tile grids
+		if (!ev_tile_end) { set_error("launch_extract: the split-stream mode needs the tile-end event"); return -1; }
+		ERT_CUDA_CHECK(cudaStreamWaitEvent(st_post, ev_tile_end, 0));
+		st = st_post;
+	}
 	{
 		// with local_union == 0 every pixel is its own tile-local node and ALL edges are seams (debug A/B mode)
 		const int tw = local_union ? TILE_W : 1, th = local_union ? TILE_H : 1;

@@ -66,6 +66,9 @@ __device__ __forceinline__ uint32_t t2_smem_u32(const void *p) { return (uint32_
 // levels differ (also true when q is KEY_NONE: its level field is 0xFFFF)
 __device__ __forceinline__ bool lvl_differs(uint32_t q, uint32_t k) { return (q ^ k) > 0xFFFFu; }
 
+// OPT bit 0: fold interior subtrees with arrival counters (two CTA barriers) instead of one CTA barrier per level
+// OPT bit 1: skip a horizontal edge whose pixel pair repeats the pair right above it (joined through two same-level vertical pairs)
+template <int OPT>
 __global__ void __launch_bounds__(t2::NT, 4)
 k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const PlaneSrc *__restrict__ planes, uint32_t *__restrict__ par_g,
               NodeAttr *__restrict__ attr_g, uint32_t *__restrict__ node_list, uint32_t *__restrict__ node_count, uint32_t *status,
@@ -198,6 +201,8 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 		const bool has_below = y < TH - 1;
 		const uint32_t Lw = lds_u32(box_s + (uint32_t)((y + YOFF) * BOXW + XOFF + x0));
 		const uint32_t Lbw = has_below ? lds_u32(box_s + (uint32_t)((y + YOFF + 1) * BOXW + XOFF + x0)) : 0xFFFFFFFFu;
+		// row above (inside the tile only): 0xFE never equals a level, so nothing is skipped in the tile's first row
+		const uint32_t Law = ((OPT & 2) && y > 0) ? lds_u32(box_s + (uint32_t)((y + YOFF - 1) * BOXW + XOFF + x0)) : 0xFEFEFEFEu;
 		const uint4 pw = lds_v4(par_s + p0 * 4u);
 		uint4 qw = make_uint4(KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE);
 		if (has_below) qw = lds_v4(par_s + (p0 + TW) * 4u);
@@ -216,10 +221,21 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 		const uint32_t Lm = __shfl_up_sync(FULL, L3, 1), Bm = __shfl_up_sync(FULL, B3, 1);   // last pixel of the lane to the left
 		const bool first = (lane & 15) == 0, last = (lane & 15) == 15;
 		const uint32_t L4 = ka4 >> 16;
-		const bool h0 = (L0 != L1) && (L0 != 255u) && (L1 != 255u);
-		const bool h1 = (L1 != L2) && (L1 != 255u) && (L2 != 255u);
-		const bool h2 = (L2 != L3) && (L2 != 255u) && (L3 != 255u);
-		const bool h3 = !last && (L3 != L4) && (L3 != 255u) && (L4 != 255u);
+		bool h0 = (L0 != L1) && (L0 != 255u) && (L1 != 255u);
+		bool h1 = (L1 != L2) && (L1 != 255u) && (L2 != 255u);
+		bool h2 = (L2 != L3) && (L2 != 255u) && (L3 != 255u);
+		bool h3 = !last && (L3 != L4) && (L3 != 255u) && (L4 != 255u);
+		if (OPT & 2) {
+			// the pair right above has the same two levels: (x, y) ~ (x, y-1) and (x+1, y) ~ (x+1, y-1) are same-level vertical
+			// pairs (united by their own edges, or by what their skip rule leans on: pairs further LEFT), and the pair above is
+			// joined by its own horizontal edge (or, recursively, by the row above it) -- no cycle, row 0 keeps all its edges
+			const uint32_t A0 = Law & 255u, A1 = (Law >> 8) & 255u, A2 = (Law >> 16) & 255u, A3 = Law >> 24;
+			const uint32_t A4 = __shfl_down_sync(FULL, Law, 1) & 255u;
+			h0 = h0 && !(A0 == L0 && A1 == L1);
+			h1 = h1 && !(A1 == L1 && A2 == L2);
+			h2 = h2 && !(A2 == L2 && A3 == L3);
+			h3 = h3 && !(A3 == L3 && A4 == L4);
+		}
 		const bool v0 = (L0 != 255u) && (B0 != 255u) && (first || Lm != L0 || Bm != B0);
 		const bool v1 = (L1 != 255u) && (B1 != 255u) && (L0 != L1 || B0 != B1);
 		const bool v2 = (L2 != 255u) && (B2 != 255u) && (L1 != L2 || B1 != B2);
@@ -359,6 +375,7 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 	ERT_PHASE(9);
 
 	// ---- phase C: every level root points at its parent's LEVEL ROOT (roots only: a few % of the pixels) ----
+	if (OPT & 1) for (int i = tid; i < TPX / 8; i += NT) sts_v4(runs_s + (uint32_t)i * 16u, 0u, 0u, 0u, 0u);   // arrival counters of phase D3 (the run records are dead)
 	{
 		const uint32_t nr = s_nroots;
 		for (uint32_t i0 = warp * 32; i0 < nr; i0 += NT) {
@@ -431,9 +448,53 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 	__syncthreads();
 	ERT_PHASE(6);
 
-	// ---- phase D3: fold interior subtrees bottom-up, one level per round (a tile holds few distinct levels) ----
+	// ---- phase D3: fold interior subtrees bottom-up (pixels, node count, bbox travel to the parent) ----
 	const uint32_t nroots = s_nroots;
-	{
+	if (OPT & 1) {
+		// arrival counters (u16 pairs in the run-list words, zeroed during phase C): an interior node with no interior child
+		// starts; a thread carries a finished node into its parent and continues upward only if it was the last child to
+		// arrive -- three CTA barriers instead of one per level.  BORDER is upward closed, so interior nodes have interior children only.
+		uint32_t *pend = reinterpret_cast<uint32_t *>(sm + OFF_RUNS);
+		for (uint32_t i = tid; i < nroots; i += NT) {
+			const uint32_t p = rootlist[i];
+			if (cnt[p] & ACC_BORDER) continue;
+			const uint32_t up = par[p];
+			if (up == KEY_NONE) continue;
+			const uint32_t q = up & 0xFFFFu;
+			atomicAdd(&pend[q >> 1], 1u << ((q & 1u) * 16u));
+		}
+		__syncthreads();
+		// who starts is decided BEFORE any counter moves (a node whose counter reaches zero later is carried by its last child)
+		uint32_t starts = 0;
+		static_assert(TPX / NT <= 32, "one start bit per root handled by a thread");
+		for (uint32_t i = tid, k = 0; i < nroots; i += NT, ++k) {
+			const uint32_t cur = rootlist[i];
+			if (!(cnt[cur] & ACC_BORDER) && !((pend[cur >> 1] >> ((cur & 1u) * 16u)) & 0xFFFFu)) starts |= 1u << k;
+		}
+		__syncthreads();
+		for (uint32_t i = tid, k = 0; i < nroots; i += NT, ++k) {
+			if (!((starts >> k) & 1u)) continue;
+			uint32_t cur = rootlist[i];
+			for (int guard = 0; guard < 64; ++guard) {
+				const uint32_t up = par[cur];
+				if (up == KEY_NONE) break;
+				const uint32_t q = up & 0xFFFFu;
+				const uint32_t acc = *reinterpret_cast<volatile uint32_t *>(&cnt[cur]);
+				atomicAdd(&cnt[q], acc);
+				atomicMin(&xmn[q], *reinterpret_cast<volatile uint32_t *>(&xmn[cur]));
+				atomicMax(&xmx[q], *reinterpret_cast<volatile uint32_t *>(&xmx[cur]));
+				atomicOr(&ymask[q], *reinterpret_cast<volatile uint32_t *>(&ymask[cur]));
+				__threadfence_block();
+				const uint32_t sh = (q & 1u) * 16u;
+				const uint32_t old = atomicSub(&pend[q >> 1], 1u << sh);
+				if (((old >> sh) & 0xFFFFu) != 1u) break;                          // not the last child
+				if (*reinterpret_cast<volatile uint32_t *>(&cnt[q]) & ACC_BORDER) break;   // BORDER nodes keep what they gathered and go global
+				__threadfence_block();
+				cur = q;
+			}
+		}
+		__syncthreads();
+	} else {
 		const int lo = (int)s_minlvl, hi_l = (int)s_maxlvl;
 		for (int Lc = lo; Lc < hi_l; ++Lc) {
 			for (uint32_t i = tid; i < nroots; i += NT) {
@@ -561,16 +622,27 @@ int make_tile_tensor_map(TileTensorMap *out, const uint8_t *d_planes0, int W, in
 	return 0;
 }
 
-int launch_tile_v2(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st)
+template <int OPT>
+static int launch_tile_v2_opt(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st)
 {
-	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build2, cudaFuncAttributeMaxDynamicSharedMemorySize, t2::SMEM_BYTES));
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build2<OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2::SMEM_BYTES));
 	const int tiles_x = (P.W + t2::TW - 1) / t2::TW, tiles_y = (P.H + t2::TH - 1) / t2::TH;
 	dim3 grid(tiles_x * tiles_y, P.n_planes);
 	CUtensorMap tm;
 	memcpy(&tm, &wk.tmap, sizeof tm);
-	k_tile_build2<<<grid, t2::NT, t2::SMEM_BYTES, st>>>(tm, P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, wk.prof, wk.ring_rec);
+	k_tile_build2<OPT><<<grid, t2::NT, t2::SMEM_BYTES, st>>>(tm, P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, wk.prof, wk.ring_rec);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
+}
+
+int launch_tile_v2(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st, int opt)
+{
+	switch (opt) {
+	case 0: return launch_tile_v2_opt<0>(P, d_planes, wk, st);
+	case 1: return launch_tile_v2_opt<1>(P, d_planes, wk, st);
+	case 2: return launch_tile_v2_opt<2>(P, d_planes, wk, st);
+	default: return launch_tile_v2_opt<3>(P, d_planes, wk, st);
+	}
 }
 
 } // namespace ert

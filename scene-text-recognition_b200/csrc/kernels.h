@@ -96,13 +96,13 @@ int launch_ocr_features(const OcrJob *d_jobs, int n, uint8_t *d_feat1800, uint8_
 
 int extract_pitch(int W);
 int make_tile_tensor_map(TileTensorMap *out, const uint8_t *d_planes0, int W, int H, int pitch, int n_src_planes);
-int launch_tile_v2(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st);
+int launch_tile_v2(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st, int opt);
 int tile_config_count();
 size_t ring_words_per_plane(int W, int H);
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st);
 int launch_unpack_planes(const uint8_t *d_ycc, int pitch, int W, int H, uint8_t *d_out6, cudaStream_t st);
 int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
-                   cudaEvent_t ev_tile_begin = nullptr, cudaEvent_t ev_tile_end = nullptr);
+                   cudaEvent_t ev_tile_begin = nullptr, cudaEvent_t ev_tile_end = nullptr, cudaStream_t st_post = nullptr);
 
 size_t nms_scratch_stride(int kept_cap);
 int launch_nms(const NmsParams &P, int n_planes, const KeptRec *kept, const uint32_t *kept_count, const NodeAttr *attr,

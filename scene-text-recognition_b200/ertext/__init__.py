@@ -91,7 +91,8 @@ EXPORTS = [
     "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
     "ert_bench_cascade_u8", "ert_bench_svm_u8",
     "ert_set_params", "ert_set_cascade", "ert_cascade_stage_info", "ert_svm_total_sv", "ert_svm_labels", "ert_svm_gamma", "ert_calc_lbp",
-    "ert_er_track_regions_ycc",
+    "ert_er_track_regions_ycc", "ert_set_stream_split",
+    "ert_dist_unique_id", "ert_dist_create", "ert_dist_destroy", "ert_gather_regions_enqueue", "ert_gather_regions_collect", "ert_gather_regions_outstanding",
 ]
 
 _lib = None
@@ -111,7 +112,7 @@ def load_library():
     L.ert_create.restype = C.c_void_p
     L.ert_create.argtypes = [C.POINTER(ErtParams), C.c_int]
     L.ert_destroy.argtypes = [C.c_void_p]
-    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_set_tile_fifo", "ert_set_nms_sequential"):
+    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_set_tile_fifo", "ert_set_nms_sequential", "ert_set_stream_split"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_int]
     L.ert_set_capacity.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ert_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
@@ -244,6 +245,9 @@ class ErText:
 
     def set_tile_fifo(self, on):
         self._check(self.L.ert_set_tile_fifo(self.ctx, int(on)))
+
+    def set_stream_split(self, on):
+        self._check(self.L.ert_set_stream_split(self.ctx, int(on)))
 
     def set_tile_config(self, i):
         self._check(self.L.ert_set_tile_config(self.ctx, i))
