@@ -72,6 +72,12 @@ typedef struct {
 	 * [0] extract (incl. channels) [1] nms [2] classify [3] h2d [4] d2h [5] total
 	 * [6] the tile-build kernel alone (the dominant kernel; roofline numerator) [7] rest of extract */
 	double stage_ms[8];
+	/* The one documented deviation made observable: per plane, the number of tree nodes into which the
+	 * overlap chains of TWO OR MORE children could continue (src/ER.cpp:455-462).  Only there does non_maximum_supression's
+	 * result depend on the order of siblings -- the reference's flood order, here a canonical order; everywhere else the
+	 * pool is provably the reference's.  -1 per plane / in total when the sequential audit walk ran (it does not count). */
+	const int32_t *plane_order_sensitive;   /* n_planes */
+	int32_t order_sensitive_total;
 } ert_result;
 
 /* One strong or weak region as ERFilter::er_track leaves it (src/ER.cpp:536-558): the fields of `struct ER`
@@ -137,8 +143,6 @@ ERT_API int ert_set_min_area(ert_ctx *ctx, int min_area);
 ERT_API int ert_set_params(ert_ctx *ctx, const ert_params *params);
 /* option: also return the 1024-bin histograms of pooled regions (costs a D2H copy) */
 ERT_API int ert_set_return_hist(ert_ctx *ctx, int on);
-/* option (debug / A-B): 0 = skip the shared-memory tile pass and link every edge in global memory */
-ERT_API int ert_set_tile_local_union(ert_ctx *ctx, int on);
 /* audit / A-B: 1 = non_maximum_supression's walk on ONE thread per plane, literally as the reference orders it;
  * 0 (default) = the level-parallel statement of the same result (er_nms.cu).  Pools are identical either way. */
 ERT_API int ert_set_nms_sequential(ert_ctx *ctx, int on);
@@ -149,14 +153,19 @@ ERT_API int ert_set_tile_fifo(ert_ctx *ctx, int on);
  * er_track) run on a second, highest-priority stream of the context and are joined back into the context's stream:
  * their narrow kernels then take CTA slots between the tile CTAs of the other contexts' batches; 0 = one stream */
 ERT_API int ert_set_stream_split(ert_ctx *ctx, int on);
-/* tuning / A-B: which tile-build kernel runs: 0 (default) = k_tile_build2 (64x32 tile + halo through one tensor-map TMA
- * box, 256 threads, 4 pixels per lane); 1 = the round-1 kernel (512 threads, 32 row copies); 2 = round-1 with a shared
- * work queue.  All produce identical results. */
+/* tuning / A-B: variant of the tile-build kernel (k_tile_build2: 64x32 tile + halo through one tensor-map TMA box, 256
+ * threads, 4 pixels per lane): 0 (default) = arrival-counter fold + horizontal edge skip; 1 = neither; 2 = fold only;
+ * 3 = edge skip only.  All produce identical results. */
 ERT_API int ert_set_tile_config(ert_ctx *ctx, int id);
+/* A-B: 1 (default) = seams through k_seam_link_list (edges compacted per CTA, warp-converged drain); 0 = k_seam_link_rec */
+ERT_API int ert_set_seam_list(ert_ctx *ctx, int on);
 /* debug: per-phase cycle sums (clock64, thread 0 of every CTA) of the tile-build kernel since the last call */
 ERT_API int ert_debug_phase_cycles(ert_ctx *ctx, int enable, unsigned long long *out16);
 /* capacity hints (defaults: 16384 kept nodes and 2048 pooled regions per plane) */
 ERT_API int ert_set_capacity(ert_ctx *ctx, int kept_per_plane, int pool_per_plane);
+/* slots of the global node arrays per plane (tile-local nodes that leave their tiles); 0 = default: one per 4 pixels, at
+ * least 8192 (one per pixel while MIN_AREA < 32).  A batch that needs more reports the status flag "node-overflow". */
+ERT_API int ert_set_node_capacity(ert_ctx *ctx, int slots_per_plane);
 
 /* new CascadeBoost(path) -> CascadeBoost::load_classifier  (src/adaboost.cpp:498-501, 873-951).
  * Parses the reference's text format byte-compatibly.  which = ERT_CASCADE_STRONG | _WEAK. */
@@ -176,6 +185,8 @@ ERT_API int ert_svm_labels(ert_ctx *ctx, int *label);   /* svm_get_labels (inc/s
 ERT_API double ert_svm_gamma(ert_ctx *ctx);   /* model->param.gamma */
 /* u8 features: 1 (default) = RBF distances as two exact-integer tcgen05 GEMMs (kind::i8); 0 = FP64 CUDA-core kernel */
 ERT_API int ert_set_svm_tensor_cores(ert_ctx *ctx, int on);
+/* A-B: 1 = the round-1 probability kernel (one warp per vector walks the coefficient table); 0 (default) = k_svm_decide_prob */
+ERT_API int ert_set_svm_legacy_prob(ert_ctx *ctx, int on);
 ERT_API int ert_svm_dims(ert_ctx *ctx);
 
 /* ---- the batched hot path ---------------------------------------------------------------
@@ -211,6 +222,16 @@ ERT_API int ert_planes_detect(ert_ctx *ctx, const uint8_t *planes, int n_planes,
  * enqueued).  One context per scale runs the levels of a pyramid concurrently (BASELINE config 4). */
 ERT_API int ert_enqueue_planes(ert_ctx *ctx, const uint8_t *planes, int n_planes, int width, int height, int stride_bytes,
                                size_t plane_stride_bytes, int upto);
+
+/* Image pyramid on the device (BASELINE configs 2 and 4; the reference itself runs native scale only, src/ER.cpp:122-127,
+ * and SURVEY 8d defines a level as the same per-plane path on the cv::resize(INTER_LINEAR)'d plane, the primitive of
+ * src/OCR.cpp:401).  `src` = a context with a batch in flight (any of the enqueue calls above); `dst` = another context of
+ * the same device: receives src's source planes resized to (width / div, height / div) -- bit-exact cv::resize semantics
+ * incl. the exact-2x area path -- and runs the path on them.  Collect each level with ert_fetch_result(dst).  src's next
+ * batch waits on the device until every level has read its planes. */
+ERT_API int ert_enqueue_pyramid_level(ert_ctx *dst, ert_ctx *src, int div, int upto);
+/* BGR entry points: 6 (default) = the six channels of compute_channels; 3 = Y, Cr, Cb only (BASELINE config 4) */
+ERT_API int ert_set_planes_per_frame(ert_ctx *ctx, int n);
 
 /* ERFilter::non_maximum_supression(ER *root, ..., pool, input) on a caller tree (src/ER.cpp:416):
  * nodes in DFS pre-order with the caller's child order (as ert_result delivers them, or as

@@ -246,6 +246,8 @@ void ref_svm_predict_probability(void *ctx, const double *x, int n, int dims, in
 // planes er_tree_extract -> non_maximum_supression -> classify.
 // mode 0 ("R", reference-faithful): frames one at a time, omp parallel for over the 6 planes.
 // mode 1 ("T", throughput-fair):   frames spread over nthreads, planes sequential inside a frame.
+// mode 2 ("U", throughput-fair at a fixed step): the n_frames * 6 (frame, plane) units spread over nthreads, so that a
+//         step of few frames still keeps every host thread busy.
 // counts: per frame 4 ints = kept nodes, pool, strong, weak.  Returns wall seconds.
 double ref_detect_frames(void *ctx, const uchar *bgr, int n_frames, int w, int h, int mode, int nthreads,
                          int *counts, double *stage_seconds /*3: extract,nms,classify summed over planes*/)
@@ -285,6 +287,19 @@ double ref_detect_frames(void *ctx, const uchar *bgr, int n_frames, int w, int h
 			for (int k = 0; k < 4; k++) { counts[4 * f + k] = 0; for (int i = 0; i < 6; i++) counts[4 * f + k] += cnt[i][k]; }
 			for (int i = 0; i < 6; i++) { st_e += se[i]; st_n += sn[i]; st_c += sc[i]; }
 		}
+	} else if (mode == 2) {
+		std::vector<std::vector<cv::Mat> > chs((size_t)n_frames);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+		for (int f = 0; f < n_frames; f++) channels_from_bgr(bgr + (size_t)f * w * h * 3, w, h, w * 3, chs[(size_t)f]);
+		std::vector<int> cnt((size_t)n_frames * 6 * 4, 0);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1) reduction(+ : st_e, st_n, st_c)
+		for (int u = 0; u < n_frames * 6; u++) {
+			double se, sn, sc;
+			do_plane(chs[(size_t)(u / 6)][(size_t)(u % 6)], &cnt[(size_t)u * 4], &se, &sn, &sc);
+			st_e += se; st_n += sn; st_c += sc;
+		}
+		for (int f = 0; f < n_frames; f++)
+			for (int k = 0; k < 4; k++) { counts[4 * f + k] = 0; for (int i = 0; i < 6; i++) counts[4 * f + k] += cnt[((size_t)f * 6 + i) * 4 + k]; }
 	} else {
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1) reduction(+ : st_e, st_n, st_c)
 		for (int f = 0; f < n_frames; f++) {

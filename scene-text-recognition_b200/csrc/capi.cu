@@ -35,9 +35,11 @@ __global__ void k_compact_results(int n_planes, int node_cap, int pool_cap, cons
                                   const double *__restrict__ ss, const double *__restrict__ ws, const uint8_t *__restrict__ hist,
                                   int32_t *__restrict__ h_node_off, int32_t *__restrict__ h_pool_off, OutNode *__restrict__ h_nodes,
                                   int32_t *__restrict__ h_pool, int32_t *__restrict__ h_label, double *__restrict__ h_ss,
-                                  double *__restrict__ h_ws, uint8_t *__restrict__ h_hist, int with_labels)
+                                  double *__restrict__ h_ws, uint8_t *__restrict__ h_hist, int with_labels,
+                                  const int32_t *__restrict__ order_sens, int32_t *__restrict__ h_order_sens)
 {
 	const int plane = blockIdx.x;
+	if (threadIdx.x == 0 && h_order_sens) h_order_sens[plane] = order_sens ? order_sens[plane] : -1;
 	int noff = 0, poff = 0;
 	for (int p = 0; p < plane; p++) { noff += counts[2 * p]; poff += counts[2 * p + 1]; }
 	const int nn = counts[2 * plane], np = counts[2 * plane + 1];
@@ -72,10 +74,11 @@ namespace {
 void free_workspace(ert_ctx *c)
 {
 	cudaFree(c->d_ycc); cudaFree(c->d_planes);
-	cudaFree(c->wk.par); cudaFree(c->wk.attr); cudaFree(c->wk.node_list); cudaFree(c->wk.node_count); cudaFree(c->wk.ring_rec);
+	cudaFree(c->wk.par); cudaFree(c->wk.attr); cudaFree(c->wk.node_key); cudaFree(c->wk.node_count); cudaFree(c->wk.start_key); cudaFree(c->wk.ring_rec);
 	cudaFree(c->wk.reach_root); cudaFree(c->wk.lone_level); cudaFree(c->wk.kept); cudaFree(c->wk.kept_count); cudaFree(c->wk.status);
 	cudaFree(c->d_nms_scratch); cudaFree(c->d_out_nodes); cudaFree(c->d_out_pool); cudaFree(c->d_out_counts); cudaFree(c->d_label);
-	cudaFree(c->d_ss); cudaFree(c->d_ws); cudaFree(c->d_hist);
+	cudaFree(c->d_ss); cudaFree(c->d_ws); cudaFree(c->d_hist); cudaFree(c->d_order_sens); cudaFreeHost(c->h_order_sens);
+	c->d_order_sens = nullptr; c->h_order_sens = nullptr;
 	cudaFreeHost(c->h_node_off); cudaFreeHost(c->h_pool_off); cudaFreeHost(c->h_pool); cudaFreeHost(c->h_label);
 	cudaFreeHost(c->h_nodes); cudaFreeHost(c->h_ss); cudaFreeHost(c->h_ws); cudaFreeHost(c->h_hist); cudaFreeHost(c->h_status);
 	c->d_ycc = nullptr; c->d_planes = nullptr; c->wk = ExtractWork{};
@@ -84,7 +87,7 @@ void free_workspace(ert_ctx *c)
 	c->h_node_off = c->h_pool_off = c->h_pool = c->h_label = nullptr; c->h_nodes = nullptr; c->h_ss = c->h_ws = nullptr;
 	c->h_hist = nullptr; c->h_status = nullptr;
 	c->planes_cap = 0; c->frames_cap = 0; c->W = c->H = 0;
-	c->cap_np = c->cap_ycc = c->cap_ring = 0;
+	c->cap_np = c->cap_ycc = c->cap_ring = 0; c->cap_nodes = 0;
 	c->table_planes = 0; c->table_W = c->table_H = 0;
 }
 
@@ -101,6 +104,37 @@ int dmalloc(T **p, size_t n)
 	return 0;
 }
 
+// compact tables of a cascade for u8 histograms + upload (h.stumps / stage_len / stage_thr are filled)
+int upload_cascade(CascadeHost &h)
+{
+	h.cpcn.resize(h.stumps.size()); h.dimthr.resize(h.stumps.size());
+	for (size_t j = 0; j < h.stumps.size(); j++) {
+		const Stump &s0 = h.stumps[j];
+		h.cpcn[j] = make_double2(s0.cp, s0.cn);
+		const double ct = ceil(s0.thr);       // integer counts: h < thr  <=>  h < ceil(thr)
+		const uint32_t ithr = (uint32_t)(ct < 0.0 ? 0.0 : (ct > 65535.0 ? 65535.0 : ct));
+		h.dimthr[j] = (uint32_t)s0.dim | (ithr << 16);
+	}
+	if (dev_upload(&h.d_stumps, h.stumps) || dev_upload(&h.d_len, h.stage_len) || dev_upload(&h.d_thr, h.stage_thr) ||
+	    dev_upload(&h.d_cpcn, h.cpcn) || dev_upload(&h.d_dimthr, h.dimthr)) return -1;
+	return 0;
+}
+
+int ensure_cascade_scratch(ert_ctx *c, int rows, int planes)
+{
+	CascadeScratch &sc = c->csc;
+	if (rows <= sc.rows_cap && planes <= sc.planes_cap) return 0;
+	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	if (c->post_stream) ERT_CUDA_CHECK(cudaStreamSynchronize(c->post_stream));
+	const int R = std::max(rows, sc.rows_cap), P = std::max(planes, sc.planes_cap);
+	cudaFree(sc.stage_sum); cudaFree(sc.done); cudaFree(sc.pool_prefix);
+	sc = CascadeScratch{};
+	if (dmalloc(&sc.stage_sum, (size_t)R * 32) || dmalloc(&sc.done, (size_t)R) || dmalloc(&sc.pool_prefix, (size_t)P + 1)) return -1;
+	ERT_CUDA_CHECK(cudaMemset(sc.done, 0, sizeof(uint32_t) * (size_t)R));
+	sc.rows_cap = R; sc.planes_cap = P;
+	return 0;
+}
+
 // Workspace by CAPACITY: buffers grow to the largest (planes x pixels) seen and are reused for anything smaller, so
 // alternating plane sizes (the scales of a pyramid, BASELINE config 4) costs no allocation after the first pass.
 // Nothing in the workspace needs clearing between batches (sparse slots are initialised by the kernel that creates them).
@@ -112,28 +146,38 @@ int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 	}
 	const int pitch = extract_pitch(W);
 	const size_t N = (size_t)W * H;
-	const size_t need_np = N * n_planes, need_ycc = (size_t)pitch * H * n_planes, need_ring = ring_words_per_plane(W, H) * n_planes;
+	// slots of the global node arrays per plane: the tile-local nodes that leave their tiles (seam-touching ones and
+	// interior ones the reference keeps) -- measured 13 per 64x32 tile on the benchmark frames, ~300 on uniform noise;
+	// default one slot per 4 pixels (at least 8192: any plane of up to 4 tiles fits whatever it holds); with a tiny MIN_AREA
+	// nearly every tile-local node is one the reference keeps, so every pixel may need a slot
+	const size_t node_cap = c->node_cap_user > 0 ? (size_t)c->node_cap_user : std::max<size_t>(8192, c->prm.min_area >= 32 ? N / 4 : N);
+	const size_t need_np = node_cap * n_planes, need_ycc = (size_t)pitch * H * n_planes, need_ring = ring_words_per_plane(W, H) * n_planes;
 	if (n_planes <= c->planes_cap && need_np <= c->cap_np && need_ycc <= c->cap_ycc && need_ring <= c->cap_ring) {
 		c->W = W; c->H = H; c->pitch = pitch; c->ycc_bytes = (size_t)pitch * H;
+		c->wk.node_cap = (int)node_cap;
 		return 0;
 	}
 	const int P = std::max(n_planes, c->planes_cap);
 	const size_t cap_np = std::max(need_np, c->cap_np), cap_ycc = std::max(need_ycc, c->cap_ycc), cap_ring = std::max(need_ring, c->cap_ring);
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
 	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	if (c->post_stream) ERT_CUDA_CHECK(cudaStreamSynchronize(c->post_stream));
 	free_workspace(c);
 	c->W = W; c->H = H; c->pitch = pitch;
 	c->ycc_bytes = (size_t)pitch * H;
 	if (dmalloc(&c->d_ycc, cap_ycc + 256)) return -1;
 	ERT_CUDA_CHECK(cudaMemset(c->d_ycc, 0, cap_ycc + 256));
 	if (dmalloc(&c->d_planes, (size_t)P)) return -1;
-	if (dmalloc(&c->wk.par, cap_np) || dmalloc(&c->wk.attr, cap_np) || dmalloc(&c->wk.node_list, cap_np)) return -1;
+	if (dmalloc(&c->wk.par, cap_np) || dmalloc(&c->wk.attr, cap_np) || dmalloc(&c->wk.node_key, cap_np) || dmalloc(&c->wk.start_key, (size_t)4 * P)) return -1;
+	c->wk.node_cap = (int)node_cap;
 	if (dmalloc(&c->wk.ring_rec, cap_ring)) return -1;
 	if (dmalloc(&c->wk.node_count, (size_t)P) || dmalloc(&c->wk.reach_root, (size_t)P) || dmalloc(&c->wk.lone_level, (size_t)P)) return -1;
 	if (dmalloc(&c->wk.kept, (size_t)P * c->kept_cap) || dmalloc(&c->wk.kept_count, (size_t)P) || dmalloc(&c->wk.status, 1)) return -1;
 	ERT_CUDA_CHECK(cudaMemset(c->wk.status, 0, sizeof(uint32_t)));
 	c->wk.node_blocks = 32;
 	c->wk.tile_cfg = c->tile_cfg;
+	c->wk.seam_list = c->seam_list;
+	c->wk.node_cap = (int)node_cap;
 	c->wk.prof = c->d_prof;
 	c->nms_stride = nms_scratch_stride(c->kept_cap);
 	if (dmalloc(&c->d_nms_scratch, c->nms_stride * P)) return -1;
@@ -142,6 +186,7 @@ int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 	if (dmalloc(&c->d_ss, (size_t)P * c->pool_cap) || dmalloc(&c->d_ws, (size_t)P * c->pool_cap)) return -1;
 	if (dmalloc(&c->d_hist, (size_t)P * c->pool_cap * 1024)) return -1;
 	if (hmalloc(&c->h_node_off, (size_t)P + 1) || hmalloc(&c->h_pool_off, (size_t)P + 1)) return -1;
+	if (dmalloc(&c->d_order_sens, (size_t)P) || hmalloc(&c->h_order_sens, (size_t)P)) return -1;
 	if (hmalloc(&c->h_nodes, (size_t)P * c->kept_cap) || hmalloc(&c->h_pool, (size_t)P * c->pool_cap)) return -1;
 	if (hmalloc(&c->h_label, (size_t)P * c->pool_cap) || hmalloc(&c->h_ss, (size_t)P * c->pool_cap) || hmalloc(&c->h_ws, (size_t)P * c->pool_cap)) return -1;
 	// the pooled-region histograms travel to the host only on request: 1 KB per region, 100 MB of pinned memory at the defaults
@@ -155,7 +200,8 @@ int set_plane_table(ert_ctx *c, int n_planes, bool bgr_mode)
 	std::vector<PlaneSrc> t((size_t)n_planes);
 	for (int p = 0; p < n_planes; p++) {
 		if (bgr_mode) {
-			const int f = p / 6, ch = p % 6;
+			const int ppf = c->planes_per_frame;
+			const int f = p / ppf, ch = p % ppf;
 			t[p].z = f * 3 + (ch % 3);
 			t[p].src = c->d_ycc + (size_t)t[p].z * c->ycc_bytes;
 			t[p].invert = ch >= 3;
@@ -166,7 +212,7 @@ int set_plane_table(ert_ctx *c, int n_planes, bool bgr_mode)
 		}
 	}
 	// the tile kernel's view of the plane buffer: (x, y, source plane), one haloed box per tile through the TMA unit
-	if (make_tile_tensor_map(&c->wk.tmap, c->d_ycc, c->W, c->H, c->pitch, bgr_mode ? n_planes / 2 : n_planes)) return -1;
+	if (make_tile_tensor_map(&c->wk.tmap, c->d_ycc, c->W, c->H, c->pitch, bgr_mode ? 3 * (n_planes / c->planes_per_frame) : n_planes)) return -1;
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->d_planes, t.data(), sizeof(PlaneSrc) * n_planes, cudaMemcpyHostToDevice, c->stream));
 	// the table is tiny; make the pageable staging copy safe before `t` dies
 	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -181,13 +227,14 @@ ExtractParams make_extract_params(const ert_ctx *c, int n_planes)
 	P.qscale = (float)(1.0 / (double)c->prm.thresh_step);
 	P.min_area = c->prm.min_area;
 	P.kept_cap = c->kept_cap;
+	P.node_cap = c->wk.node_cap;
 	return P;
 }
 
 NmsParams make_nms_params(const ert_ctx *c, int W, int H)
 {
 	NmsParams P;
-	P.W = W; P.H = H; P.N = (size_t)W * H;
+	P.W = W; P.H = H; P.N = (size_t)c->wk.node_cap;
 	P.kept_cap = c->kept_cap; P.pool_cap = c->pool_cap;
 	P.min_area = c->prm.min_area; P.max_area = c->prm.max_area; P.stability_t = c->prm.stability_t;
 	P.overlap_coef = c->prm.overlap_coef;
@@ -216,7 +263,7 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 		std::lock_guard<std::mutex> lk(g_fifo.mu);
 		if (g_fifo.last[dslot] && g_fifo.owner[dslot] != c) ERT_CUDA_CHECK(cudaStreamWaitEvent(st, g_fifo.last[dslot], 0));
 	}
-	if (launch_extract(EP, c->d_planes, c->wk, c->local_union, st, c->ev[8], c->ev[9], c->work_stream())) return -1;
+	if (launch_extract(EP, c->d_planes, c->wk, st, c->ev[8], c->ev[9], c->work_stream())) return -1;
 	const cudaStream_t st_main = st;
 	st = c->work_stream();
 	if (c->tile_fifo) {
@@ -227,22 +274,25 @@ int enqueue_pipeline(ert_ctx *c, int n_planes, int upto)
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[2], st));
 	const NmsParams NP = make_nms_params(c, c->W, c->H);
 	if (launch_nms(NP, n_planes, c->wk.kept, c->wk.kept_count, c->wk.attr, c->wk.reach_root, c->wk.lone_level, nullptr, nullptr,
-	               c->d_nms_scratch, c->nms_stride, c->d_out_nodes, c->d_out_pool, c->d_out_counts, c->wk.status, st)) return -1;
+	               c->d_nms_scratch, c->nms_stride, c->d_out_nodes, c->d_out_pool, c->d_out_counts, c->wk.status, st, c->d_order_sens)) return -1;
 	c->launches += 1;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[3], st));
 	const bool do_classify = upto >= ERT_STAGE_CLASSIFY;
 	if (do_classify) {
 		if (!c->casc[0].loaded || !c->casc[1].loaded) { set_error("classify requested but cascades are not loaded"); return -1; }
 		ClassifyParams CP; CP.pitch = c->pitch; CP.pool_cap = c->pool_cap; CP.node_cap = c->kept_cap;
-		if (launch_lbp_hist(CP, n_planes, c->d_planes, c->d_out_nodes, c->d_out_pool, c->d_out_counts, c->d_aran_tbl, c->d_hist, st)) return -1;
-		if (launch_cascade_u8(c->d_hist, 1024, n_planes * c->pool_cap, c->d_out_counts, c->pool_cap, c->casc[0].dev(), c->casc[1].dev(),
-		                      (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), c->d_label, c->d_ss, c->d_ws, st)) return -1;
-		c->launches += 2;
+		if (ensure_cascade_scratch(c, n_planes * c->pool_cap, n_planes)) return -1;
+		if (launch_pool_prefix(c->d_out_counts, n_planes, c->pool_cap, c->csc.pool_prefix, st)) return -1;
+		if (launch_lbp_hist(CP, n_planes, c->d_planes, c->d_out_nodes, c->d_out_pool, c->csc.pool_prefix, c->d_aran_tbl, c->d_hist, st)) return -1;
+		if (launch_cascade_u8(c->d_hist, 1024, n_planes * c->pool_cap, c->csc.pool_prefix, n_planes, c->pool_cap, c->casc[0].dev(), c->casc[1].dev(),
+		                      c->d_label, c->d_ss, c->d_ws, c->csc, st)) return -1;
+		c->launches += 3;
 	}
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
 	k_compact_results<<<n_planes, 256, 0, st>>>(n_planes, c->kept_cap, c->pool_cap, c->d_out_counts, c->d_out_nodes, c->d_out_pool, c->d_label,
 	                                           c->d_ss, c->d_ws, c->d_hist, c->h_node_off, c->h_pool_off, c->h_nodes, c->h_pool, c->h_label,
-	                                           c->h_ss, c->h_ws, (c->return_hist && do_classify) ? c->h_hist : nullptr, do_classify ? 1 : 0);
+	                                           c->h_ss, c->h_ws, (c->return_hist && do_classify) ? c->h_hist : nullptr, do_classify ? 1 : 0,
+	                                           c->nms_sequential ? nullptr : c->d_order_sens, c->h_order_sens);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	c->launches += 1;
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->wk.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -273,6 +323,9 @@ int finish_result(ert_ctx *c, const ert_result **out)
 	r.pool_strong_score = c->h_ss; r.pool_weak_score = c->h_ws;
 	r.pool_hist = (c->return_hist && c->pending_upto >= ERT_STAGE_CLASSIFY) ? c->h_hist : nullptr;
 	r.status = *c->h_status;
+	r.plane_order_sensitive = c->h_order_sens;
+	r.order_sensitive_total = 0;
+	for (int p = 0; p < r.n_planes; p++) { if (c->h_order_sens[p] < 0) { r.order_sensitive_total = -1; break; } r.order_sensitive_total += c->h_order_sens[p]; }
 	float ms;
 	auto el = [&](int a, int b) { ms = 0.f; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return (double)ms; };
 	r.stage_ms[3] = el(0, 1); r.stage_ms[0] = el(1, 2); r.stage_ms[1] = el(2, 3); r.stage_ms[2] = el(3, 4); r.stage_ms[4] = el(4, 5);
@@ -325,6 +378,7 @@ const char *ert_status_string(uint32_t s)
 	if (s & ERR_KEPT_OVERFLOW) strcat(buf, "kept-overflow ");
 	if (s & ERR_POOL_OVERFLOW) strcat(buf, "pool-overflow ");
 	if (s & ERR_NMS_OVERFLOW) strcat(buf, "nms-overflow ");
+	if (s & ERR_NODE_OVERFLOW) strcat(buf, "node-overflow ");
 	return buf;
 }
 
@@ -344,6 +398,8 @@ ert_ctx *ert_create(const ert_params *params, int device)
 		cudaDeviceGetStreamPriorityRange(&least, &greatest);
 		if (cudaStreamCreateWithPriority(&c->post_stream, cudaStreamNonBlocking, greatest) != cudaSuccess) c->post_stream = nullptr;
 		cudaEventCreateWithFlags(&c->ev_post_done, cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&c->ev_planes, cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&c->ev_resized, cudaEventDisableTiming);
 	}
 	build_aran_table(c);
 	if (cudaMalloc((void **)&c->d_aran_tbl, 64) != cudaSuccess || cudaMemcpy(c->d_aran_tbl, c->aran_tbl_h, 64, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -363,8 +419,9 @@ void ert_destroy(ert_ctx *c)
 	}
 	free_workspace(c);
 	cudaFree(c->d_bgr); cudaFree(c->d_aran_tbl);
-	for (int k = 0; k < 2; k++) { cudaFree(c->casc[k].d_stumps); cudaFree(c->casc[k].d_len); cudaFree(c->casc[k].d_thr); }
-	cudaFree(c->svm.d_sv); cudaFree(c->svm.d_coef); cudaFree(c->svm.d_rho); cudaFree(c->svm.d_probA); cudaFree(c->svm.d_probB);
+	for (int k = 0; k < 2; k++) { cudaFree(c->casc[k].d_stumps); cudaFree(c->casc[k].d_len); cudaFree(c->casc[k].d_thr); cudaFree(c->casc[k].d_cpcn); cudaFree(c->casc[k].d_dimthr); }
+	cudaFree(c->csc.stage_sum); cudaFree(c->csc.done); cudaFree(c->csc.pool_prefix);
+	cudaFree(c->svm.d_sv); cudaFree(c->svm.d_coef); cudaFree(c->svm.d_coefT); cudaFree(c->svm.d_rho); cudaFree(c->svm.d_probA); cudaFree(c->svm.d_probB);
 	cudaFree(c->svm.d_label); cudaFree(c->svm.d_nsv); cudaFree(c->svm.d_start);
 	cudaFree(c->svm.d_svj); cudaFree(c->svm.d_sve); cudaFree(c->svm.d_ss);
 	c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
@@ -372,6 +429,8 @@ void ert_destroy(ert_ctx *c)
 	for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
 	if (c->post_stream) { cudaStreamSynchronize(c->post_stream); cudaStreamDestroy(c->post_stream); }
 	if (c->ev_post_done) cudaEventDestroy(c->ev_post_done);
+	if (c->ev_planes) cudaEventDestroy(c->ev_planes);
+	if (c->ev_resized) cudaEventDestroy(c->ev_resized);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -398,7 +457,6 @@ int ert_set_return_hist(ert_ctx *c, int on)
 int ert_set_nms_sequential(ert_ctx *c, int on) { c->nms_sequential = on ? 1 : 0; return 0; }
 int ert_set_tile_fifo(ert_ctx *c, int on) { c->tile_fifo = on ? 1 : 0; return 0; }
 int ert_set_stream_split(ert_ctx *c, int on) { cudaStreamSynchronize(c->stream); if (c->post_stream) cudaStreamSynchronize(c->post_stream); c->split_streams = on ? 1 : 0; return 0; }
-int ert_set_tile_local_union(ert_ctx *c, int on) { c->local_union = on ? 1 : 0; return 0; }
 int ert_debug_phase_cycles(ert_ctx *c, int enable, unsigned long long *out16)
 {
 	if (enable && !c->d_prof) { ERT_CUDA_CHECK(cudaMalloc((void **)&c->d_prof, 16 * sizeof(unsigned long long))); ERT_CUDA_CHECK(cudaMemset(c->d_prof, 0, 16 * sizeof(unsigned long long))); }
@@ -407,6 +465,7 @@ int ert_debug_phase_cycles(ert_ctx *c, int enable, unsigned long long *out16)
 	c->wk.prof = c->d_prof;
 	return 0;
 }
+int ert_set_seam_list(ert_ctx *c, int on) { c->seam_list = on ? 1 : 0; c->wk.seam_list = c->seam_list; return 0; }
 int ert_set_tile_config(ert_ctx *c, int id)
 {
 	if (id < 0 || id >= tile_config_count()) { set_error("tile config %d out of range", id); return -1; }
@@ -419,6 +478,16 @@ int ert_set_capacity(ert_ctx *c, int kept, int pool)
 	cudaStreamSynchronize(c->stream);
 	free_workspace(c);
 	c->kept_cap = kept; c->pool_cap = pool;
+	return 0;
+}
+
+int ert_set_node_capacity(ert_ctx *c, int slots_per_plane)
+{
+	if (slots_per_plane < 0 || slots_per_plane > (1 << KEY_IDX_BITS)) { set_error("bad node capacity"); return -1; }
+	cudaStreamSynchronize(c->stream);
+	if (c->post_stream) cudaStreamSynchronize(c->post_stream);
+	free_workspace(c);
+	c->node_cap_user = slots_per_plane;
 	return 0;
 }
 
@@ -478,7 +547,9 @@ int ert_load_cascade(ert_ctx *c, int which, const char *path)
 	}
 	for (const Stump &st : h.stumps) if (st.dim < 0 || st.dim >= 1024) { set_error("%s: stump dimension %d outside the 1024-bin feature", path, st.dim); return -1; }
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
-	if (dev_upload(&h.d_stumps, h.stumps) || dev_upload(&h.d_len, h.stage_len) || dev_upload(&h.d_thr, h.stage_thr)) return -1;
+	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));   // a batch in flight may still read the old tables
+	if (c->post_stream) ERT_CUDA_CHECK(cudaStreamSynchronize(c->post_stream));
+	if (upload_cascade(h)) return -1;
 	h.loaded = true;
 	return (int)h.stumps.size();
 }
@@ -499,7 +570,8 @@ int ert_set_cascade(ert_ctx *c, int which, int n_stages, const int *stage_len, c
 	for (int j = 0; j < n_stumps; j++) { Stump st; st.dim = dim[j]; st.thr = thr[j]; st.cp = cp[j]; st.cn = cn[j]; st.pad = 0; h.stumps[(size_t)j] = st; }
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
 	ERT_CUDA_CHECK(cudaStreamSynchronize(c->stream));   // a batch in flight may still read the old tables
-	if (dev_upload(&h.d_stumps, h.stumps) || dev_upload(&h.d_len, h.stage_len) || dev_upload(&h.d_thr, h.stage_thr)) return -1;
+	if (c->post_stream) ERT_CUDA_CHECK(cudaStreamSynchronize(c->post_stream));
+	if (upload_cascade(h)) return -1;
 	h.loaded = true;
 	return n_stumps;
 }
@@ -516,7 +588,7 @@ int ert_load_svm(ert_ctx *c, const char *path)
 	{
 		// a reload replaces the model: release the previous device tables, keep the caller's tensor-core choice
 		const bool keep_tc = m.use_tc;
-		cudaFree(m.d_sv); cudaFree(m.d_coef); cudaFree(m.d_rho); cudaFree(m.d_probA); cudaFree(m.d_probB);
+		cudaFree(m.d_sv); cudaFree(m.d_coef); cudaFree(m.d_coefT); cudaFree(m.d_rho); cudaFree(m.d_probA); cudaFree(m.d_probB);
 		cudaFree(m.d_label); cudaFree(m.d_nsv); cudaFree(m.d_start); cudaFree(m.d_svj); cudaFree(m.d_sve); cudaFree(m.d_ss);
 		m = SvmHost();
 		m.use_tc = keep_tc;
@@ -626,6 +698,9 @@ int ert_load_svm(ert_ctx *c, const char *path)
 		}
 	}
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	m.coefT.assign((size_t)m.l * k1, 0.0);
+	for (int j = 0; j < k1; j++) for (int i = 0; i < m.l; i++) m.coefT[(size_t)i * k1 + j] = m.coef[(size_t)j * m.l + i];
+	if (dev_upload(&m.d_coefT, m.coefT)) return -1;
 	if (dev_upload(&m.d_sv, m.sv) || dev_upload(&m.d_coef, m.coef) || dev_upload(&m.d_rho, m.rho) || dev_upload(&m.d_probA, m.probA) ||
 	    dev_upload(&m.d_probB, m.probB) || dev_upload(&m.d_label, m.label) || dev_upload(&m.d_nsv, m.nsv) || dev_upload(&m.d_start, m.start)) return -1;
 	m.loaded = true;
@@ -651,7 +726,16 @@ int ert_svm_labels(ert_ctx *c, int *label)
 }
 double ert_svm_gamma(ert_ctx *c) { return c->svm.loaded ? c->svm.gamma : 0.0; }
 int ert_set_svm_tensor_cores(ert_ctx *c, int on) { c->svm.use_tc = on != 0; return 0; }
+int ert_set_svm_legacy_prob(ert_ctx *c, int on) { c->svm.legacy_prob = on ? 1 : 0; return 0; }
 int ert_svm_dims(ert_ctx *c) { return c->svm.loaded ? c->svm.dims : -1; }
+
+// contexts that build pyramid levels from this context's planes must have read them before the next batch overwrites them
+static int wait_for_readers(ert_ctx *c)
+{
+	for (cudaEvent_t e : c->readers) ERT_CUDA_CHECK(cudaStreamWaitEvent(c->stream, e, 0));
+	c->readers.clear();
+	return 0;
+}
 
 // ---- the batched hot path ----------------------------------------------------------------------
 static int detect_common(ert_ctx *c, const uint8_t *bgr, bool on_device, int n_frames, int W, int H, int stride, int upto)
@@ -659,12 +743,14 @@ static int detect_common(ert_ctx *c, const uint8_t *bgr, bool on_device, int n_f
 	if (!c || !bgr || n_frames < 1) { set_error("bad arguments"); return -1; }
 	if (stride < 3 * W) { set_error("stride %d < 3*width", stride); return -1; }
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
-	const int n_planes = 6 * n_frames;
+	const int n_planes = c->planes_per_frame * n_frames;
+	if (upto >= ERT_STAGE_TRACK && c->planes_per_frame != 6) { set_error("ERT_STAGE_TRACK needs all six channels (ert_set_planes_per_frame)"); return -1; }
+	if (wait_for_readers(c)) return -1;       // pyramid levels still reading this context's planes / plane table
 	if (ensure_workspace(c, n_planes, W, H)) return -1;
 	// the plane table (plane -> source pointer, invert flag) depends on the layout, the plane pitch and the plane count
-	if (c->frames_cap != -1 || c->table_W != W || c->table_H != H || n_planes > c->table_planes) {
+	if (c->frames_cap != -1 || c->table_W != W || c->table_H != H || n_planes > c->table_planes || c->table_ppf != c->planes_per_frame) {
 		if (set_plane_table(c, n_planes, true)) return -1;
-		c->frames_cap = -1; c->table_W = W; c->table_H = H; c->table_planes = n_planes;
+		c->frames_cap = -1; c->table_W = W; c->table_H = H; c->table_planes = n_planes; c->table_ppf = c->planes_per_frame;
 	}
 	c->launches = 0;
 	cudaStream_t st = c->stream;
@@ -683,6 +769,7 @@ static int detect_common(ert_ctx *c, const uint8_t *bgr, bool on_device, int n_f
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
 	if (launch_channels(d_in, frame_bytes, stride, W, H, n_frames, c->d_ycc, c->pitch, st)) return -1;
 	c->launches += 1;
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev_planes, st));
 	return enqueue_pipeline(c, n_planes, upto);
 }
 
@@ -735,6 +822,7 @@ int ert_enqueue_planes(ert_ctx *c, const uint8_t *planes, int n_planes, int W, i
 	if (!c || !planes || n_planes < 1 || stride < W) { set_error("bad arguments"); return -1; }
 	if (upto >= ERT_STAGE_TRACK) { set_error("ERT_STAGE_TRACK needs a BGR batch (er_track reads the YCrCb frame)"); return -1; }
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
+	if (wait_for_readers(c)) return -1;
 	if (ensure_workspace(c, n_planes, W, H)) return -1;
 	if (set_plane_table(c, n_planes, false)) return -1;
 	c->frames_cap = 0; c->table_planes = 0;   // plane table no longer in BGR layout
@@ -745,7 +833,46 @@ int ert_enqueue_planes(ert_ctx *c, const uint8_t *planes, int n_planes, int W, i
 		ERT_CUDA_CHECK(cudaMemcpy2DAsync(c->d_ycc + (size_t)p * c->ycc_bytes, (size_t)c->pitch, planes + (size_t)p * plane_stride, (size_t)stride,
 		                                 (size_t)W, (size_t)H, cudaMemcpyHostToDevice, st));
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
+	ERT_CUDA_CHECK(cudaEventRecord(c->ev_planes, st));
 	return enqueue_pipeline(c, n_planes, upto);
+}
+
+// A pyramid level on the device: every plane of the batch `src` has in flight (for a BGR batch the channels of
+// compute_channels, inverted ones inverted first), resized by cv::resize(INTER_LINEAR) semantics to (width / div,
+// height / div) straight into `dst`'s plane buffer, then the same per-plane path on `dst`.  Nothing but the frame itself
+// ever crosses the bus.
+int ert_enqueue_pyramid_level(ert_ctx *dst, ert_ctx *src, int div, int upto)
+{
+	if (!dst || !src || dst == src || div < 2) { set_error("bad arguments"); return -1; }
+	if (dst->device != src->device) { set_error("ert_enqueue_pyramid_level: both contexts must live on one device"); return -1; }
+	if (!src->pending || src->pending_planes < 1) { set_error("ert_enqueue_pyramid_level: the source context has no batch in flight"); return -1; }
+	if (upto >= ERT_STAGE_TRACK) { set_error("ert_enqueue_pyramid_level: er_track runs on the native-scale batch only"); return -1; }
+	const int dw = src->W / div, dh = src->H / div;
+	if (dw < 1 || dh < 1) { set_error("ert_enqueue_pyramid_level: %dx%d / %d is empty", src->W, src->H, div); return -1; }
+	ERT_CUDA_CHECK(cudaSetDevice(dst->device));
+	const int n_planes = src->pending_planes;
+	if (wait_for_readers(dst)) return -1;
+	if (ensure_workspace(dst, n_planes, dw, dh)) return -1;
+	if (set_plane_table(dst, n_planes, false)) return -1;
+	dst->frames_cap = 0; dst->table_planes = 0;        // the level holds its planes one by one (no BGR layout)
+	dst->launches = 0;
+	cudaStream_t st = dst->stream;
+	ERT_CUDA_CHECK(cudaEventRecord(dst->ev[0], st));
+	ERT_CUDA_CHECK(cudaStreamWaitEvent(st, src->ev_planes, 0));
+	ERT_CUDA_CHECK(cudaEventRecord(dst->ev[1], st));
+	if (launch_resize_planes(src->d_planes, n_planes, src->W, src->H, src->pitch, dst->d_ycc, dw, dh, dst->pitch, dst->ycc_bytes, st)) return -1;
+	dst->launches += 1;
+	ERT_CUDA_CHECK(cudaEventRecord(dst->ev_resized, st));
+	ERT_CUDA_CHECK(cudaEventRecord(dst->ev_planes, st));
+	src->readers.push_back(dst->ev_resized);
+	return enqueue_pipeline(dst, n_planes, upto);
+}
+
+int ert_set_planes_per_frame(ert_ctx *c, int n)
+{
+	if (n != 3 && n != 6) { set_error("planes per frame: 6 (Y, Cr, Cb and their inverses) or 3 (Y, Cr, Cb)"); return -1; }
+	c->planes_per_frame = n;
+	return 0;
 }
 
 int ert_planes_detect(ert_ctx *c, const uint8_t *planes, int n_planes, int W, int H, int stride, size_t plane_stride, int upto, const ert_result **out)
@@ -822,12 +949,14 @@ static int classify_common(ert_ctx *c, const uint8_t *plane, int W, int H, int s
 	ERT_CUDA_CHECK(cudaMemcpyAsync(d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, st));
 	ERT_CUDA_CHECK(cudaMemcpyAsync(d_ps, &ps, sizeof ps, cudaMemcpyHostToDevice, st));
 	ClassifyParams CP; CP.pitch = pitch; CP.pool_cap = n; CP.node_cap = n;
-	if (launch_lbp_hist(CP, 1, d_ps, d_nodes, d_pool, d_counts, c->d_aran_tbl, (uint8_t *)c->s2.p, st, codes ? (uint8_t *)c->s4.p : nullptr)) return -1;
+	if (ensure_cascade_scratch(c, n, 1)) return -1;
+	if (launch_pool_prefix(d_counts, 1, n, c->csc.pool_prefix, st)) return -1;
+	if (launch_lbp_hist(CP, 1, d_ps, d_nodes, d_pool, c->csc.pool_prefix, c->d_aran_tbl, (uint8_t *)c->s2.p, st, codes ? (uint8_t *)c->s4.p : nullptr)) return -1;
 	int32_t *d_label = (int32_t *)c->s3.p;
 	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
 	double *d_ws = d_ss + n;
 	if (need_cascade) {
-		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), d_label, d_ss, d_ws, st)) return -1;
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, 0, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, c->csc, st)) return -1;
 	}
 	ERT_CUDA_CHECK(cudaStreamSynchronize(st));   // staging vectors hn/hp may go out of scope now
 	if (label) ERT_CUDA_CHECK(cudaMemcpy(label, d_label, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
@@ -893,7 +1022,8 @@ int ert_cascade_classify_u8(ert_ctx *c, const uint8_t *hist, int n, int32_t *lab
 	int32_t *d_label = (int32_t *)c->s3.p;
 	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
 	double *d_ws = d_ss + n;
-	if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), d_label, d_ss, d_ws, st)) return -1;
+	if (n < 32768 && ensure_cascade_scratch(c, n, 1)) return -1;
+	if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, 0, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, c->csc, st)) return -1;
 	if (label) ERT_CUDA_CHECK(cudaMemcpyAsync(label, d_label, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
 	if (ss) ERT_CUDA_CHECK(cudaMemcpyAsync(ss, d_ss, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
 	if (ws) ERT_CUDA_CHECK(cudaMemcpyAsync(ws, d_ws, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -936,11 +1066,12 @@ int ert_bench_cascade_u8(ert_ctx *c, const uint8_t *hist, int n, int iters, doub
 	int32_t *d_label = (int32_t *)c->s3.p;
 	double *d_ss = (double *)((uint8_t *)c->s3.p + (((size_t)n * 4 + 63) / 64) * 64);
 	double *d_ws = d_ss + n;
+	if (n < 32768 && ensure_cascade_scratch(c, n, 1)) return -1;
 	for (int w = 0; w < 3; w++)
-		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), d_label, d_ss, d_ws, st)) return -1;
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, 0, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, c->csc, st)) return -1;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[6], st));
 	for (int i = 0; i < iters; i++)
-		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, n, c->casc[0].dev(), c->casc[1].dev(), (int)c->casc[0].stumps.size(), (int)c->casc[1].stumps.size(), d_label, d_ss, d_ws, st)) return -1;
+		if (launch_cascade_u8((const uint8_t *)c->s2.p, 1024, n, nullptr, 0, n, c->casc[0].dev(), c->casc[1].dev(), d_label, d_ss, d_ws, c->csc, st)) return -1;
 	ERT_CUDA_CHECK(cudaEventRecord(c->ev[7], st));
 	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
 	float ms = 0;

@@ -7,10 +7,11 @@
 namespace ert {
 
 // ---------------------------------------------------------------------------------------------
-// Keys.  A pixel of a plane is named by key = level << 26 | pixel index (index = y*W + x).
-// Ordering keys as unsigned integers orders pixels by (level, raster position); the component
-// tree is held as a forest par[] in which par[p] is always the key of an ANCESTOR of p
-// (strictly larger key), or KEY_NONE.  See DESIGN.md "keyed lock-free union-find".
+// Keys.  Inside a tile a pixel is named by key = level << 16 | tile-local pixel index; in the GLOBAL forest a
+// tile-local node that leaves its tile is named by key = level << 26 | slot, slot = its position in the plane's node
+// array (handed out by the tile kernel).  Ordering keys as unsigned integers orders nodes by (level, index); the
+// component tree is held as a forest par[] in which par[i] is always the key of an ANCESTOR of i (strictly larger
+// key), or KEY_NONE.  See DESIGN.md "keyed lock-free union-find".
 // ---------------------------------------------------------------------------------------------
 constexpr int      KEY_IDX_BITS = 26;
 constexpr uint32_t KEY_IDX_MASK = (1u << KEY_IDX_BITS) - 1u;
@@ -22,7 +23,7 @@ __host__ __device__ __forceinline__ uint32_t make_key(uint32_t level, uint32_t i
 __host__ __device__ __forceinline__ uint32_t key_level(uint32_t k) { return k >> KEY_IDX_BITS; }
 __host__ __device__ __forceinline__ uint32_t key_idx(uint32_t k) { return k & KEY_IDX_MASK; }
 
-// Per-node attributes, one 32-byte sector per pixel slot (only slots of tree nodes are touched).
+// Per-node attributes, one 32-byte sector per node slot (dense: slots are handed out consecutively per plane).
 struct __align__(32) NodeAttr {
 	uint32_t cnt;    // pixels: own-level pixels after the tile pass, whole subtree after refit
 	uint32_t nn;     // number of tree nodes in the subtree (1 = self); 0 marks an alias (merged across a seam)
@@ -55,6 +56,7 @@ struct ExtractParams {
 	float qscale;           // (float)(1.0/step)
 	int min_area;
 	int kept_cap;           // capacity of the kept list per plane
+	int node_cap;           // capacity of the global node arrays per plane (slots)
 };
 
 // device-side status flags (bit-or'ed)
@@ -63,6 +65,7 @@ enum : uint32_t {
 	ERR_KEPT_OVERFLOW = 2u,
 	ERR_POOL_OVERFLOW = 4u,
 	ERR_NMS_OVERFLOW  = 8u,
+	ERR_NODE_OVERFLOW = 16u, // more tile-local nodes left their tiles than the plane's node array holds (ert_set_node_capacity)
 };
 
 __device__ __forceinline__ int quantize_level(int v, float qscale)

@@ -16,7 +16,14 @@ struct CascadeHost {
 	bool loaded = false;
 	Stump *d_stumps = nullptr;
 	int *d_len = nullptr, *d_thr = nullptr;
-	CascadeDev dev() const { CascadeDev c; c.stumps = d_stumps; c.stage_len = d_len; c.stage_thr = d_thr; c.n_stages = (int)stage_len.size(); return c; }
+	std::vector<double2> cpcn; std::vector<uint32_t> dimthr;      // compact tables for u8 histograms
+	double2 *d_cpcn = nullptr; uint32_t *d_dimthr = nullptr;
+	CascadeDev dev() const
+	{
+		CascadeDev c; c.stumps = d_stumps; c.stage_len = d_len; c.stage_thr = d_thr; c.n_stages = (int)stage_len.size();
+		c.cpcn = d_cpcn; c.dimthr = d_dimthr;
+		return c;
+	}
 };
 
 struct SvmHost {
@@ -26,6 +33,8 @@ struct SvmHost {
 	std::vector<double> rho, probA, probB, coef, sv;
 	std::vector<int> label, nsv, start;
 	double *d_sv = nullptr, *d_coef = nullptr, *d_rho = nullptr, *d_probA = nullptr, *d_probB = nullptr;
+	std::vector<double> coefT; double *d_coefT = nullptr;
+	int legacy_prob = 0;
 	int *d_label = nullptr, *d_nsv = nullptr, *d_start = nullptr;
 	std::vector<uint8_t> svj; std::vector<int8_t> sve; std::vector<double> ss;
 	uint8_t *d_svj = nullptr; int8_t *d_sve = nullptr; double *d_ss = nullptr;
@@ -33,7 +42,7 @@ struct SvmHost {
 	bool use_tc = true;
 	SvmDev dev() const
 	{
-		SvmDev m; m.nr_class = nr_class; m.l = l; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef;
+		SvmDev m; m.nr_class = nr_class; m.l = l; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef; m.coefT = d_coefT; m.legacy_prob = legacy_prob;
 		m.rho = d_rho; m.probA = d_probA; m.probB = d_probB; m.label = d_label; m.nsv = d_nsv; m.start = d_start;
 		m.svj = use_tc ? d_svj : nullptr; m.sve = d_sve; m.ss = d_ss; m.inv_s255 = inv_s255;
 		return m;
@@ -75,12 +84,16 @@ struct ert_ctx {
 	cudaStream_t post_stream = nullptr;   // highest priority: everything after the tile kernel (seams .. result compaction, er_track)
 	cudaEvent_t ev_post_done = nullptr;   // joins the post stream back into `stream`
 	int split_streams = 1;
+	int planes_per_frame = 6;             // BGR entry points: 6 = Y, Cr, Cb and their inverses (compute_channels); 3 = Y, Cr, Cb only
+	cudaEvent_t ev_planes = nullptr;      // the batch's source planes are complete in d_ycc (pyramid levels of other contexts wait on it)
+	cudaEvent_t ev_resized = nullptr;     // this context finished READING another context's planes (ert_enqueue_pyramid_level)
+	std::vector<cudaEvent_t> readers;     // events of contexts that still read this context's planes: the next batch waits for them
 	cudaStream_t work_stream() const { return (split_streams && post_stream) ? post_stream : stream; }
 	cudaEvent_t ev[12];
-	int local_union = 1;
 	int nms_sequential = 0;  // 1: run the reference's walk on one thread per plane (audit / A-B) instead of the level-parallel form
 	int tile_fifo = 1;       // chain the tile kernels of all contexts on the device in submission order
 	int tile_cfg = 0;
+	int seam_list = 1;       // seam kernel: compacted edge lists (1) or one thread per seam position (0, round 1)
 	int return_hist = 0;
 	int kept_cap = 16384, pool_cap = 2048;
 	int launches = 0;
@@ -93,8 +106,9 @@ struct ert_ctx {
 
 	// workspace geometry
 	int W = 0, H = 0, pitch = 0, planes_cap = 0, frames_cap = 0;
-	size_t cap_np = 0, cap_ycc = 0, cap_ring = 0;   // capacities: planes x pixels, plane bytes, seam-record words
-	int table_planes = 0, table_W = 0, table_H = 0; // what the BGR-layout plane table on the device was built for
+	size_t cap_np = 0, cap_ycc = 0, cap_ring = 0, cap_nodes = 0;   // capacities: planes x node slots, plane bytes, seam-record words
+	int node_cap_user = 0;   // ert_set_node_capacity: slots per plane (0 = one per 4 pixels)
+	int table_planes = 0, table_W = 0, table_H = 0, table_ppf = 0; // what the BGR-layout plane table on the device was built for
 	uint8_t *d_bgr = nullptr; size_t bgr_cap = 0;
 	uint8_t *d_ycc = nullptr;          // frames_cap*3 planes (BGR mode) or planes_cap planes (plane mode)
 	size_t ycc_bytes = 0;
@@ -111,11 +125,13 @@ struct ert_ctx {
 	double *h_ss = nullptr, *h_ws = nullptr;
 	uint8_t *h_hist = nullptr;
 	uint32_t *h_status = nullptr;
+	int32_t *d_order_sens = nullptr, *h_order_sens = nullptr;   // per plane: nodes where the NMS outcome depends on the sibling order
 	ert_result res{};
 	int pending_planes = 0, pending_upto = 0;
 	bool pending = false;
 
 	ert::Scratch s0, s1, s2, s3, s4;
+	ert::CascadeScratch csc{};          // stage sums / arrival counters / pool prefix of the cascade kernel
 
 	// ---- rows after the detect path (capi_next.cu): er_track and OCR::chain_run ----
 	ert::TrackWork tk{};                    // device candidate / colour / tracked buffers

@@ -35,28 +35,55 @@ __device__ __forceinline__ int src_px(const PlaneSrc &ps, int pitch, int x, int 
 	return ps.invert ? 255 - v : v;
 }
 
-constexpr int HIST_WARPS = 8;
+constexpr int HIST_WARPS = 4;
+constexpr int HIST_GRID = 148 * 4;
 
-__global__ void __launch_bounds__(HIST_WARPS * 32) k_lbp_hist(ClassifyParams P, const PlaneSrc *__restrict__ planes,
+// largest plane with pool_prefix[plane] <= r
+__device__ __forceinline__ int plane_of_region(const int32_t *__restrict__ pool_prefix, int n_planes, int r)
+{
+	int lo = 0, hi = n_planes - 1;
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(pool_prefix + mid) <= r) lo = mid; else hi = mid - 1; }
+	return lo;
+}
+
+__global__ void k_pool_prefix(const int32_t *__restrict__ counts, int n_planes, int pool_cap, int32_t *__restrict__ pool_prefix)
+{
+	const int lane = threadIdx.x;
+	int carry = 0;
+	for (int p0 = 0; p0 < n_planes; p0 += 32) {
+		const int p = p0 + lane;
+		const int c = (p < n_planes) ? min(counts[2 * p + 1], pool_cap) : 0;
+		int inc = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+		if (p < n_planes) pool_prefix[p] = carry + inc - c;
+		carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+	}
+	if (lane == 0) pool_prefix[n_planes] = carry;
+}
+
+// One WARP per pooled region, warps stride over all regions of the batch (found through pool_prefix): the grid does not
+// depend on the per-plane capacity, and a CTA (4 warps, 7 KB of shared memory, histogram bins packed four to a word --
+// a bin never exceeds the 144 pixels of its block) fits beside the resident tile-kernel CTAs of other batches.
+__global__ void __launch_bounds__(HIST_WARPS * 32) k_lbp_hist(ClassifyParams P, int n_planes, const PlaneSrc *__restrict__ planes,
                                                                const OutNode *__restrict__ nodes, const int32_t *__restrict__ pool,
-                                                               const int32_t *__restrict__ counts, const uint8_t *__restrict__ aran_tbl,
+                                                               const int32_t *__restrict__ pool_prefix, const uint8_t *__restrict__ aran_tbl,
                                                                uint8_t *__restrict__ hist_out, uint8_t *__restrict__ codes_out)
 {
 	__shared__ uint8_t s_patch[HIST_WARPS][26 * 26 + 28];
-	__shared__ uint32_t s_hist[HIST_WARPS][1024];
+	__shared__ uint32_t s_hist[HIST_WARPS][256];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int plane = blockIdx.y;
-	const int r = blockIdx.x * HIST_WARPS + warp;
-	const int npool = min(counts[2 * plane + 1], P.pool_cap);
-	if (r >= npool) return;
-	const OutNode nd = nodes[(size_t)plane * P.node_cap + pool[(size_t)plane * P.pool_cap + r]];
-	const PlaneSrc ps = planes[plane];
+	const int total = pool_prefix[n_planes];
 	uint8_t *patch = s_patch[warp];
 	uint32_t *hist = s_hist[warp];
+	for (int item = blockIdx.x * HIST_WARPS + warp; item < total; item += gridDim.x * HIST_WARPS) {
+	const int plane = plane_of_region(pool_prefix, n_planes, item);
+	const int r = item - pool_prefix[plane];
+	const OutNode nd = nodes[(size_t)plane * P.node_cap + pool[(size_t)plane * P.pool_cap + r]];
+	const PlaneSrc ps = planes[plane];
 	for (int i = lane; i < 26 * 26 + 28; i += 32) patch[i] = 0;
-	for (int i = lane; i < 1024; i += 32) hist[i] = 0;
+	for (int i = lane; i < 256; i += 32) hist[i] = 0;
 	__syncwarp();
-
 	const int L = 26;
 	const int sw = nd.w, sh = nd.h;
 	const int minor = aran_minor(sw, sh, L, aran_tbl);
@@ -107,14 +134,14 @@ __global__ void __launch_bounds__(HIST_WARPS * 32) k_lbp_hist(ClassifyParams P, 
 		const int s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;   // bit set iff v > s/8.0  <=>  8v > s
 		const int code = (8 * v0 > s) | ((8 * v1 > s) << 1) | ((8 * v2 > s) << 2) | ((8 * v3 > s) << 3) |
 		                 ((8 * v4 > s) << 4) | ((8 * v5 > s) << 5) | ((8 * v6 > s) << 6) | ((8 * v7 > s) << 7);
-		atomicAdd(&hist[(i / 12) * 512 + (j / 12) * 256 + code], 1u);
+		const int bin = (i / 12) * 512 + (j / 12) * 256 + code;
+		atomicAdd(&hist[bin >> 2], 1u << (8 * (bin & 3)));
 		if (codes_out) codes_out[((size_t)plane * P.pool_cap + r) * 576 + t] = (uint8_t)code;   // calc_LBP's 24x24 image (src/ER.cpp:819-845)
 	}
 	__syncwarp();
 	uint32_t *out = reinterpret_cast<uint32_t *>(hist_out + ((size_t)plane * P.pool_cap + r) * 1024);
-	for (int it = 0; it < 8; it++) {
-		const int b = (it * 32 + lane) * 4;
-		out[it * 32 + lane] = hist[b] | (hist[b + 1] << 8) | (hist[b + 2] << 16) | (hist[b + 3] << 24);
+	for (int it = 0; it < 8; it++) out[it * 32 + lane] = hist[it * 32 + lane];     // bin 4w + b is byte b of word w: the u8[1024] layout
+	__syncwarp();
 	}
 }
 
@@ -163,126 +190,111 @@ __global__ void k_cascade(const T *__restrict__ fv, size_t row_stride, int n_row
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-cooperative stage evaluation for u8 histograms.  Stump tables live in shared memory in a compact
-// form (dim, integer threshold, cp, cn: for integer counts h < thr <=> h < ceil(thr)); 32 lanes gather and select
-// 32 stumps at once, then the stage sum is accumulated in FILE ORDER by broadcasting the 32 selected values one
-// after the other (every lane performs the same non-fused double adds) -- bit-identical stage sums, ~20x less
-// latency than one thread walking the table.
+// k_cascade_stage : one WARP per (region, cascade STAGE).  A stage's sum starts from zero (src/adaboost.cpp:528-529), so
+// the 4 + 6 stages of the two cascades are independent computations: a warp evaluates one stage -- 32 lanes gather and
+// select 32 stumps at once (compact tables {cp, cn}, dim | ceil(thr) << 16 read coalesced through L2; for integer counts
+// h < thr <=> h < ceil(thr)), then the stage sum is accumulated in FILE ORDER by broadcasting the 32 selected values one
+// after the other with non-fused double adds: bit-identical stage sums.  The warp that delivers a region's last stage
+// applies the stage thresholds in order (CascadeBoost::predict: the last stage's sum, -DBL_MAX at the first failing
+// stage).  Latency = the longest stage (1210 stumps), not the sum of the stages a region survives (up to 4014); no
+// shared-memory tables (the round-1 form staged 96 KB per CTA, which cannot sit beside the tile kernel's CTAs).
 // ---------------------------------------------------------------------------------------------
-struct StumpC { double cp, cn; uint16_t dim, ithr; uint32_t pad; };
+constexpr int CS_WARPS = 4;
+constexpr int CS_GRID = 148 * 4;
 
-// ---------------------------------------------------------------------------------------------
-// k_cascade_stage : one CTA per region, one WARP per cascade STAGE.  A stage's sum starts from zero
-// (src/adaboost.cpp:528-529), so the stages of both cascades are independent computations: each warp evaluates one
-// stage as described above (32 stumps gathered at once, added in FILE ORDER with non-fused double adds),
-// and one thread then applies the stage thresholds in order.  Same bits as walking the stages one after the other,
-// but the latency is the longest stage (1210 stumps) instead of the sum of the stages a region survives (up to 4014).
-// Persistent CTAs: the stump tables are loaded into shared memory once per CTA.
-// ---------------------------------------------------------------------------------------------
-constexpr int CS_WARPS = 12;
-
-__global__ void __launch_bounds__(CS_WARPS * 32) k_cascade_stage(const uint8_t *__restrict__ hist, int n_rows, const int32_t *__restrict__ counts,
-                                                                 int n_planes, int pool_cap, CascadeDev strong, CascadeDev weak, int n_strong,
-                                                                 int n_weak, int32_t *__restrict__ label, double *__restrict__ sscore,
-                                                                 double *__restrict__ wscore)
+__global__ void __launch_bounds__(CS_WARPS * 32) k_cascade_stage(const uint8_t *__restrict__ hist, int n_rows, const int32_t *__restrict__ pool_prefix,
+                                                                 int n_planes, int pool_cap, CascadeDev strong, CascadeDev weak,
+                                                                 int32_t *__restrict__ label, double *__restrict__ sscore, double *__restrict__ wscore,
+                                                                 double *__restrict__ stage_sum, uint32_t *__restrict__ done)
 {
-	extern __shared__ __align__(16) uint8_t csm[];
-	StumpC *st = reinterpret_cast<StumpC *>(csm);                 // strong stumps, then weak stumps
-	double *s_score = reinterpret_cast<double *>(st + n_strong + n_weak);   // [32] stage sums of the current region
-	int *meta = reinterpret_cast<int *>(s_score + 32);            // [0..15] strong len, [16..31] strong thr, [32..47] weak len, [48..63] weak thr
-	int *stage_off = meta + 64;                                   // [32] first stump of stage s (strong stages, then weak stages)
-	uint8_t *hs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(stage_off + 32) + 15) & ~(uintptr_t)15);   // 1024 histogram bytes (uint4 copies)
-	int *pref = reinterpret_cast<int *>(hs + 1024);               // [n_planes + 1] first region of each plane (pipeline flavour)
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	for (int i = tid; i < n_strong + n_weak; i += blockDim.x) {
-		const Stump s0 = (i < n_strong) ? strong.stumps[i] : weak.stumps[i - n_strong];
-		StumpC c;
-		c.cp = s0.cp; c.cn = s0.cn; c.dim = (uint16_t)s0.dim;
-		const double ct = ceil(s0.thr);
-		c.ithr = (uint16_t)(ct < 0.0 ? 0.0 : (ct > 65535.0 ? 65535.0 : ct));
-		c.pad = 0;
-		st[i] = c;
-	}
-	if (tid < 16) {
-		meta[tid] = (tid < strong.n_stages) ? strong.stage_len[tid] : 0;
-		meta[16 + tid] = (tid < strong.n_stages) ? strong.stage_thr[tid] : 0;
-		meta[32 + tid] = (tid < weak.n_stages) ? weak.stage_len[tid] : 0;
-		meta[48 + tid] = (tid < weak.n_stages) ? weak.stage_thr[tid] : 0;
-	}
-	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const int gw = blockIdx.x * CS_WARPS + (threadIdx.x >> 5), nw_total = gridDim.x * CS_WARPS;
 	const int ns = strong.n_stages, nw = weak.n_stages, nst = ns + nw;
-	if (tid == 0) {
-		int o = 0;
-		for (int s2 = 0; s2 < ns; s2++) { stage_off[s2] = o; o += meta[s2]; }
-		o = n_strong;
-		for (int s2 = 0; s2 < nw; s2++) { stage_off[ns + s2] = o; o += meta[32 + s2]; }
-		if (counts) {
-			int acc = 0;
-			for (int p = 0; p < n_planes; p++) { pref[p] = acc; acc += min(counts[2 * p + 1], pool_cap); }
-			pref[n_planes] = acc;
-		}
-	}
-	__syncthreads();
-	const int total = counts ? pref[n_planes] : n_rows;
-	for (int r = blockIdx.x; r < total; r += gridDim.x) {
+	const int total = pool_prefix ? pool_prefix[n_planes] : n_rows;
+	const long long items = (long long)total * nst;
+	for (long long it = gw; it < items; it += nw_total) {
+		const int r = (int)(it / nst), s2 = (int)(it % nst);
 		size_t idx = (size_t)r;
-		if (counts) {
-			int lo = 0, hi = n_planes - 1;                             // largest plane with pref[plane] <= r
-			while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pref[mid] <= r) lo = mid; else hi = mid - 1; }
-			idx = (size_t)lo * pool_cap + (size_t)(r - pref[lo]);
+		if (pool_prefix) {
+			const int plane = plane_of_region(pool_prefix, n_planes, r);
+			idx = (size_t)plane * pool_cap + (size_t)(r - pool_prefix[plane]);
 		}
-		__syncthreads();                                               // the previous region's readers are done with hs / s_score
-		if (tid < 64) reinterpret_cast<uint4 *>(hs)[tid] = reinterpret_cast<const uint4 *>(hist + idx * 1024)[tid];
-		__syncthreads();
-		for (int s2 = warp; s2 < nst; s2 += CS_WARPS) {
-			const StumpC *tbl = st + stage_off[s2];
-			const int len = (s2 < ns) ? meta[s2] : meta[32 + s2 - ns];
-			double score = 0.0;
-			for (int c0 = 0; c0 < len; c0 += 32) {
-				const int j = c0 + lane;
-				double v = 0.0;
-				if (j < len) { const StumpC t = tbl[j]; v = ((int)hs[t.dim] < (int)t.ithr) ? t.cp : t.cn; }
-				const int m = min(32, len - c0);
+		const CascadeDev &c = (s2 < ns) ? strong : weak;
+		const int sl = (s2 < ns) ? s2 : s2 - ns;
+		int off = 0;
+		for (int q = 0; q < sl; q++) off += c.stage_len[q];
+		const int len = c.stage_len[sl];
+		const uint8_t *hs = hist + idx * 1024;
+		double score = 0.0;
+		// software pipeline: the next chunk's table entries are in flight while this chunk's 32 adds retire
+		double2 cc = make_double2(0.0, 0.0);
+		uint32_t dt = 0;
+		if (lane < len) { cc = __ldg(c.cpcn + off + lane); dt = __ldg(c.dimthr + off + lane); }
+		for (int c0 = 0; c0 < len; c0 += 32) {
+			const int j = c0 + lane;
+			double v = 0.0;
+			if (j < len) v = ((uint32_t)__ldg(hs + (dt & 0xFFFFu)) < (dt >> 16)) ? cc.x : cc.y;
+			const int jn = j + 32;
+			if (jn < len) { cc = __ldg(c.cpcn + off + jn); dt = __ldg(c.dimthr + off + jn); }
+			const int m = min(32, len - c0);
+			if (m == 32) {
+				// full chunk, unrolled: the 32 broadcasts do not depend on the running sum and pipeline ahead of the add chain
+#pragma unroll
+				for (int i = 0; i < 32; i++) score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, v, i));
+			} else {
 				for (int i = 0; i < m; i++) score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, v, i));
 			}
-			if (lane == 0) s_score[s2] = score;
 		}
-		__syncthreads();
-		if (tid == 0) {
-			double sres = 0.0, wres = 0.0;                              // CascadeBoost::predict: the last stage's sum, -DBL_MAX on the first failing stage
-			for (int s2 = 0; s2 < ns; s2++) { sres = s_score[s2]; if (sres < (double)meta[16 + s2]) { sres = ERT_NEG_DBL_MAX; break; } }
-			for (int s2 = 0; s2 < nw; s2++) { wres = s_score[ns + s2]; if (wres < (double)meta[48 + s2]) { wres = ERT_NEG_DBL_MAX; break; } }
+		uint32_t arrived = 0;
+		if (lane == 0) {
+			stage_sum[(size_t)r * 32 + s2] = score;
+			__threadfence();
+			arrived = atomicAdd(&done[r], 1u);
+		}
+		arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
+		if (arrived == (uint32_t)(nst - 1) && lane == 0) {
+			__threadfence();
+			const volatile double *ss = stage_sum + (size_t)r * 32;
+			double sres = 0.0, wres = 0.0;
+			for (int q = 0; q < ns; q++) { sres = ss[q]; if (sres < (double)strong.stage_thr[q]) { sres = ERT_NEG_DBL_MAX; break; } }
+			for (int q = 0; q < nw; q++) { wres = ss[ns + q]; if (wres < (double)weak.stage_thr[q]) { wres = ERT_NEG_DBL_MAX; break; } }
 			label[idx] = (sres > ERT_NEG_DBL_MAX) ? 2 : ((wres > ERT_NEG_DBL_MAX) ? 1 : 0);
 			if (sscore) sscore[idx] = sres;
 			if (wscore) wscore[idx] = wres;
+			done[r] = 0;                                   // ready for the next launch
 		}
 	}
 }
 
-int launch_lbp_hist(const ClassifyParams &P, int n_planes, const PlaneSrc *planes, const OutNode *nodes, const int32_t *pool,
-                    const int32_t *counts, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st, uint8_t *codes_out)
+int launch_pool_prefix(const int32_t *counts, int n_planes, int pool_cap, int32_t *pool_prefix, cudaStream_t st)
 {
-	dim3 grid((P.pool_cap + HIST_WARPS - 1) / HIST_WARPS, n_planes);
-	k_lbp_hist<<<grid, HIST_WARPS * 32, 0, st>>>(P, planes, nodes, pool, counts, aran_tbl, hist_out, codes_out);
+	k_pool_prefix<<<1, 32, 0, st>>>(counts, n_planes, pool_cap, pool_prefix);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
 
-int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const int32_t *counts, int pool_cap, const CascadeDev &strong,
-                      const CascadeDev &weak, int n_strong, int n_weak, int32_t *label, double *sscore, double *wscore, cudaStream_t st)
+int launch_lbp_hist(const ClassifyParams &P, int n_planes, const PlaneSrc *planes, const OutNode *nodes, const int32_t *pool,
+                    const int32_t *pool_prefix, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st, uint8_t *codes_out)
+{
+	k_lbp_hist<<<HIST_GRID, HIST_WARPS * 32, 0, st>>>(P, n_planes, planes, nodes, pool, pool_prefix, aran_tbl, hist_out, codes_out);
+	ERT_CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const int32_t *pool_prefix, int n_planes, int pool_cap, const CascadeDev &strong,
+                      const CascadeDev &weak, int32_t *label, double *sscore, double *wscore, const CascadeScratch &sc, cudaStream_t st)
 {
 	if (n_rows <= 0) return 0;
-	const int n_planes = counts ? n_rows / pool_cap : 0;
-	const size_t smem = (size_t)(n_strong + n_weak) * sizeof(StumpC) + 32 * sizeof(double) + 96 * sizeof(int) + 16 + 1024 + (size_t)(n_planes + 1) * sizeof(int);
-	// few regions (the pipeline: tens per plane): one CTA per region, one warp per cascade stage -- the latency is the
-	// longest stage; very many regions (candidate sweeps): one thread per region keeps 32 independent sums per warp in flight
-	const bool few = (counts != nullptr) || n_rows < 32768;
-	if (few && row_stride == 1024 && strong.n_stages <= 16 && weak.n_stages <= 16 && smem <= 200 * 1024) {
-		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_cascade_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		const int grid = counts ? 148 * 2 : (int)std::min<long long>(n_rows, 148 * 2);
-		k_cascade_stage<<<grid, CS_WARPS * 32, smem, st>>>(hist, n_rows, counts, n_planes, pool_cap, strong, weak, n_strong, n_weak, label, sscore, wscore);
+	// few regions (the pipeline: tens per plane): one warp per (region, stage) -- the latency is the longest stage; very many
+	// regions (candidate sweeps): one thread per region keeps 32 independent sums per warp in flight
+	const bool few = (pool_prefix != nullptr) || n_rows < 32768;
+	if (few && row_stride == 1024 && strong.n_stages + weak.n_stages <= 32 && strong.cpcn && weak.cpcn && sc.stage_sum && n_rows <= sc.rows_cap) {
+		const long long items = (long long)n_rows * (strong.n_stages + weak.n_stages);
+		const int grid = pool_prefix ? CS_GRID : (int)std::min<long long>((items + CS_WARPS - 1) / CS_WARPS, CS_GRID);
+		k_cascade_stage<<<grid, CS_WARPS * 32, 0, st>>>(hist, n_rows, pool_prefix, n_planes, pool_cap, strong, weak, label, sscore, wscore, sc.stage_sum, sc.done);
 	} else {
-		k_cascade<uint8_t><<<(n_rows + 127) / 128, 128, 0, st>>>(hist, row_stride, n_rows, counts, pool_cap, strong, weak, label, sscore, wscore);
+		if (pool_prefix) { set_error("launch_cascade_u8: the per-plane form needs the cascade scratch"); return -1; }
+		k_cascade<uint8_t><<<(n_rows + 127) / 128, 128, 0, st>>>(hist, row_stride, n_rows, nullptr, pool_cap, strong, weak, label, sscore, wscore);
 	}
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;

@@ -127,9 +127,11 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
                                             const OutNode *__restrict__ in_nodes, const int32_t *__restrict__ in_offsets,
                                             uint8_t *__restrict__ scratch, size_t scratch_stride, int smem_cap,
                                             OutNode *__restrict__ out_nodes, int32_t *__restrict__ out_pool,
-                                            int32_t *__restrict__ out_counts /* per plane: n_nodes, n_pool */, uint32_t *status)
+                                            int32_t *__restrict__ out_counts /* per plane: n_nodes, n_pool */, uint32_t *status,
+                                            int32_t *__restrict__ order_sens /* per plane, may be null */)
 {
 	extern __shared__ __align__(16) uint8_t nms_smem[];
+	if (order_sens && threadIdx.x == 0) order_sens[blockIdx.x] = 0;
 	__shared__ int s_npool, s_lmin, s_lmax, s_bad;
 	__shared__ int32_t s_scan[NT / 32 + 1];
 	const int tid = threadIdx.x;
@@ -274,6 +276,11 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 		const int T = P.stability_t;
 		const int lmin = s_lmin, lmax = s_lmax;
 		for (int j = tid; j < n; j += NT) { size[j] = 1; fpass[j] = 0x7FFFFFFF; }
+		// v.done (a byte per node, the sequential walk's flag) counts here how many children's chains may continue into a
+		// node: bit 0 = one, bit 1 = two or more.  With two or more the walk's outcome depends on which sibling is visited
+		// first -- the ONLY place where the canonical sibling order can differ from the reference's flood order.
+		uint32_t *pass_bits = reinterpret_cast<uint32_t *>(v.done);
+		for (int j = tid; j < (n + 3) / 4; j += NT) pass_bits[j] = 0;
 		__syncthreads();
 		for (int L = lmin; L <= lmax; ++L) {                      // bottom-up: children (lower levels) are final
 			for (int j = tid; j < n; j += NT) {
@@ -285,10 +292,20 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 				if (p >= 0) {
 					atomicAdd(&size[p], size[j]);
 					// the test the walk makes when the chain started at o, having taken j, looks at p (src/ER.cpp:457)
-					if (overlap_exceeds(bb_inter(&v.bx[4 * o], &v.bx[4 * p]), bb_area(&v.bx[4 * p]), P.overlap_coef)) atomicMin(&fpass[p], j);
+					if (overlap_exceeds(bb_inter(&v.bx[4 * o], &v.bx[4 * p]), bb_area(&v.bx[4 * p]), P.overlap_coef)) {
+						atomicMin(&fpass[p], j);
+						const uint32_t sh = 8u * ((uint32_t)p & 3u);
+						if (atomicOr(&pass_bits[p >> 2], 1u << sh) & (1u << sh)) atomicOr(&pass_bits[p >> 2], 2u << sh);
+					}
 				}
 			}
 			__syncthreads();
+		}
+		if (order_sens) {
+			int contested = 0;
+			for (int j = tid; j < n; j += NT) contested += (v.done[j] >> 1) & 1;
+			contested = __reduce_add_sync(0xFFFFFFFFu, contested);
+			if ((tid & 31) == 0 && contested) atomicAdd(&order_sens[plane], contested);
 		}
 		// DFS pre-order index and depth, top-down: pre(child) = pre(parent) + 1 + sizes of the siblings before it
 		for (int j = tid; j < n; j += NT) S[j] = size[j];
@@ -467,12 +484,12 @@ size_t nms_scratch_stride(int kept_cap)
 int launch_nms(const NmsParams &P, int n_planes, const KeptRec *kept, const uint32_t *kept_count, const NodeAttr *attr,
                const uint32_t *reach_root, const int32_t *lone_level, const OutNode *in_nodes, const int32_t *in_offsets,
                uint8_t *scratch, size_t scratch_stride, OutNode *out_nodes, int32_t *out_pool, int32_t *out_counts,
-               uint32_t *status, cudaStream_t st)
+               uint32_t *status, cudaStream_t st, int32_t *order_sens)
 {
 	const size_t smem = nms_view_bytes(NMS_SMEM_NODES);
 		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_nms<NMS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	k_nms<NMS_NT><<<n_planes, NMS_NT, smem, st>>>(P, kept, kept_count, attr, reach_root, lone_level, in_nodes, in_offsets,
-	                                              scratch, scratch_stride, NMS_SMEM_NODES, out_nodes, out_pool, out_counts, status);
+	                                              scratch, scratch_stride, NMS_SMEM_NODES, out_nodes, out_pool, out_counts, status, order_sens);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }

@@ -68,11 +68,14 @@ __device__ __forceinline__ bool lvl_differs(uint32_t q, uint32_t k) { return (q 
 
 // OPT bit 0: fold interior subtrees with arrival counters (two CTA barriers) instead of one CTA barrier per level
 // OPT bit 1: skip a horizontal edge whose pixel pair repeats the pair right above it (joined through two same-level vertical pairs)
-template <int OPT>
-__global__ void __launch_bounds__(t2::NT, 4)
+// OPT bit 2: combine the runs of one node inside a warp before the shared-memory reductions of the counting pass
+// MINB: resident CTAs per SM the register allocation aims at (shared memory allows 4; 5 caps the kernel at 48 registers,
+// which leaves room for two small CTAs of the other stages beside four tile CTAs)
+template <int OPT, int MINB>
+__global__ void __launch_bounds__(t2::NT, MINB)
 k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const PlaneSrc *__restrict__ planes, uint32_t *__restrict__ par_g,
-              NodeAttr *__restrict__ attr_g, uint32_t *__restrict__ node_list, uint32_t *__restrict__ node_count, uint32_t *status,
-              int tiles_x, unsigned long long *prof, uint32_t *__restrict__ ring_rec)
+              NodeAttr *__restrict__ attr_g, uint32_t *__restrict__ node_key, uint32_t *__restrict__ node_count, uint32_t *__restrict__ start_key,
+              uint32_t *status, int tiles_x, unsigned long long *prof, uint32_t *__restrict__ ring_rec)
 {
 	using namespace t2;
 	long long t_prev = prof ? clock64() : 0;
@@ -88,9 +91,6 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 	const int X0 = tx * TW, Y0 = ty * TH;
 	const int rows = min(TH, P.H - Y0), cols = min(TW, P.W - X0);
 	const PlaneSrc ps = planes[plane];
-	const size_t N = (size_t)P.W * P.H;
-	uint32_t *parP = par_g + (size_t)plane * N;
-	NodeAttr *attrP = attr_g + (size_t)plane * N;
 
 	const uint32_t sraw = t2_smem_u32(smem_raw);
 	const uint32_t sb = (sraw + 127u) & ~127u;
@@ -355,7 +355,20 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 			}
 			const uint32_t r = k & 0xFFFFu;
 			const bool isroot = live && (r == e);
-			if (live) {
+			if (OPT & 4) {
+				// runs of one node that sit in the same warp (a smooth region spans many rows) are combined first: one set of
+				// shared-memory reductions per distinct node instead of one per run (same-address atomics serialise)
+				const uint32_t grp = __match_any_sync(FULL, live ? r : (0x10000u + (uint32_t)lane));
+				const uint32_t g_cnt = __reduce_add_sync(grp, live ? xe - xs + 1u + (isroot ? ACC_NODE : 0u) : 0u);
+				const uint32_t g_mn = __reduce_min_sync(grp, xs), g_mx = __reduce_max_sync(grp, xe), g_ym = __reduce_or_sync(grp, 1u << y);
+				if (live && (uint32_t)lane == (uint32_t)(__ffs(grp) - 1)) {
+					const uint32_t ar = attr_s + (r << 2);
+					reds_add(ar, g_cnt);
+					reds_min(ar + TPX * 4, g_mn);
+					reds_max(ar + 2 * TPX * 4, g_mx);
+					reds_or(ar + 3 * TPX * 4, g_ym);
+				}
+			} else if (live) {
 				const uint32_t ar = attr_s + (r << 2);
 				reds_add(ar, xe - xs + 1u + (isroot ? ACC_NODE : 0u));
 				reds_min(ar + TPX * 4, xs);
@@ -516,7 +529,11 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 
 	// ---- phase E: emit.  BORDER nodes go to the global forest with what they have gathered (own pixels + interior
 	// descendants); interior nodes are emitted only if the reference would keep them (area > MIN_AREA), already
-	// complete (pend = NODE_COMPLETE); seam positions publish the root that stands for them. ----
+	// complete (pend = NODE_COMPLETE).  Every emitted node gets a SLOT in the plane's dense node arrays; the parent of
+	// an emitted node is always emitted too (BORDER is upward closed, areas grow towards the root), so parent pointers
+	// and seam records name slots.  Three steps: reserve the tile's slot range, write the records (and remember every
+	// node's slot in its cnt word), then resolve parent slots / seam records / start candidates. ----
+	constexpr uint32_t SLOT_SET = 0x80000000u;
 	uint32_t my_emit = 0;
 	for (uint32_t i = tid; i < nroots; i += NT) {
 		const uint32_t acc = cnt[rootlist[i]];
@@ -526,8 +543,16 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 	my_emit = __reduce_add_sync(FULL, my_emit);
 	if (lane == 0 && my_emit) atomicAdd(&s_nemit, my_emit);
 	__syncthreads();
-	if (tid == 0) { s_base = s_nemit ? atomicAdd(&node_count[plane], s_nemit) : 0u; s_cursor = 0; }
+	if (tid == 0) {
+		s_base = s_nemit ? atomicAdd(&node_count[plane], s_nemit) : 0u;
+		s_cursor = 0;
+		if (s_base + s_nemit > (uint32_t)P.node_cap) atomicOr(status, ERR_NODE_OVERFLOW);
+	}
 	__syncthreads();
+	const bool fits = s_base + s_nemit <= (uint32_t)P.node_cap;     // an overflowing tile publishes nothing (the batch is flagged)
+	uint32_t *parP = par_g + (size_t)plane * P.node_cap;
+	NodeAttr *attrP = attr_g + (size_t)plane * P.node_cap;
+	uint32_t *keyP = node_key + (size_t)plane * P.node_cap;
 	for (uint32_t i0 = warp * 32; i0 < nroots; i0 += NT) {
 		const uint32_t i = i0 + lane;
 		bool emit = false;
@@ -541,54 +566,59 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 		uint32_t wbase = 0;
 		if (lane == 0 && emask) wbase = atomicAdd(&s_cursor, (uint32_t)__popc(emask));
 		wbase = __shfl_sync(FULL, wbase, 0);
-		if (!emit) continue;
+		if (i < nroots) cnt[p] = 0;                       // no slot (only this thread reads / writes this root's cnt word here)
+		if (!emit || !fits) continue;
+		const uint32_t slot = s_base + wbase + (uint32_t)__popc(emask & lt);
 		const int y = (int)p / TW, x = (int)p % TW;
-		const uint32_t L = ERT_LV(p);
 		const uint32_t gidx = (uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x);
-		const uint32_t pk = par[p];
-		uint32_t gpar = KEY_NONE;
-		if (pk != KEY_NONE) {
-			const uint32_t q = pk & 0xFFFFu;
-			gpar = make_key(pk >> 16, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
-		}
-		parP[gidx] = gpar;
-		uint4 *a = reinterpret_cast<uint4 *>(&attrP[gidx]);
+		uint4 *a = reinterpret_cast<uint4 *>(&attrP[slot]);
 		a[0] = make_uint4(acc & ACC_MASK, (acc >> 15) & ACC_MASK, (acc & ACC_BORDER) ? 0u : NODE_COMPLETE, 0u);
 		const uint32_t ym = ymask[p];
 		a[1] = make_uint4((uint32_t)X0 + xmn[p], (uint32_t)Y0 + (uint32_t)(__ffs(ym) - 1), (uint32_t)X0 + xmx[p], (uint32_t)Y0 + (uint32_t)(31 - __clz(ym)));
-		const uint32_t pos = s_base + wbase + (uint32_t)__popc(emask & lt);
-		node_list[(size_t)plane * N + pos] = make_key(L, gidx);
+		keyP[slot] = make_key(ERT_LV(p), gidx);
+		cnt[p] = SLOT_SET | slot;
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < nroots; i += NT) {
+		const uint32_t p = rootlist[i];
+		const uint32_t sp = cnt[p];
+		if (!(sp & SLOT_SET)) continue;
+		const uint32_t pk = par[p];
+		uint32_t gpar = KEY_NONE;
+		if (pk != KEY_NONE) gpar = make_key(pk >> 16, cnt[pk & 0xFFFFu] & ~SLOT_SET);
+		parP[sp & ~SLOT_SET] = gpar;
 	}
 	{
-		// seam records: for every position on the four tile sides the GLOBAL key of the level root of the node that
-		// stands for the pixel there (KEY_NONE where no edge crosses), laid out contiguously per tile so that
-		// k_seam_link_rec reads both sides of a seam coalesced and starts every union at a root
+		// seam records: for every position on the four tile sides the GLOBAL key (level, slot) of the node that stands
+		// for the pixel there (KEY_NONE where no edge crosses), laid out contiguously per tile so that the seam kernel
+		// reads both sides of a seam coalesced and starts every union at a root
 		uint32_t *rec = ring_rec + ((size_t)plane * gridDim.x + blockIdx.x) * RING;
 		for (int i = tid; i < RING + 3; i += NT) {
 			if (i < RING) {
 				const uint32_t a = s_ringA[i];
-				rec[i] = (a == 0xFFFFu) ? KEY_NONE
-				                        : make_key(ERT_LV(a), (uint32_t)(Y0 + (int)(a / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(a % TW)));
+				rec[i] = (a == 0xFFFFu || !fits) ? KEY_NONE : make_key(ERT_LV(a), cnt[a] & ~SLOT_SET);
 				continue;
 			}
-			// the flood's start candidates (global pixels 0, 1, W) are looked up by PIXEL in k_emit_kept: a candidate that is
-			// not its node's level root publishes its root in par[]
+			// the flood's start candidates (global pixels 0, 1, W; all inside tile 0): the key of the node that holds each of
+			// them (phase D2 made those nodes BORDER, so they have a slot); KEY_NONE for a wall or a pixel that does not exist
+			if (blockIdx.x != 0) continue;
 			const int gi = i - RING;
-			const int x = ((gi == 1) ? 1 : 0) - X0, y = ((gi == 2) ? 1 : 0) - Y0;
-			if (x < 0 || y < 0 || x >= cols || y >= rows) continue;
-			const int p = y * TW + x;
-			const uint32_t L = ERT_LV(p);
-			if (L == 255u) continue;
-			uint32_t kk = (L << 16) | (uint32_t)p;
-			for (int guard = 0; guard < 65536; ++guard) {
-				const uint32_t q2 = par[kk & 0xFFFFu];
-				if (lvl_differs(q2, kk)) break;
-				kk = q2;
+			const int x = (gi == 1) ? 1 : 0, y = (gi == 2) ? 1 : 0;
+			uint32_t key = KEY_NONE;
+			if (x < cols && y < rows && fits) {
+				const int p = y * TW + x;
+				const uint32_t L = ERT_LV(p);
+				if (L != 255u) {
+					uint32_t kk = (L << 16) | (uint32_t)p;
+					for (int guard = 0; guard < 65536; ++guard) {
+						const uint32_t q2 = par[kk & 0xFFFFu];
+						if (lvl_differs(q2, kk)) break;
+						kk = q2;
+					}
+					key = make_key(L, cnt[kk & 0xFFFFu] & ~SLOT_SET);
+				}
 			}
-			const uint32_t q = kk & 0xFFFFu;
-			if (q != (uint32_t)p)
-				parP[(uint32_t)(Y0 + y) * (uint32_t)P.W + (uint32_t)(X0 + x)] =
-					make_key(L, (uint32_t)(Y0 + (int)(q / TW)) * (uint32_t)P.W + (uint32_t)(X0 + (int)(q % TW)));
+			start_key[(size_t)plane * 4 + gi] = key;
 		}
 	}
 	ERT_PHASE(8);
@@ -622,15 +652,15 @@ int make_tile_tensor_map(TileTensorMap *out, const uint8_t *d_planes0, int W, in
 	return 0;
 }
 
-template <int OPT>
+template <int OPT, int MINB>
 static int launch_tile_v2_opt(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st)
 {
-	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build2<OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2::SMEM_BYTES));
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_tile_build2<OPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2::SMEM_BYTES));
 	const int tiles_x = (P.W + t2::TW - 1) / t2::TW, tiles_y = (P.H + t2::TH - 1) / t2::TH;
 	dim3 grid(tiles_x * tiles_y, P.n_planes);
 	CUtensorMap tm;
 	memcpy(&tm, &wk.tmap, sizeof tm);
-	k_tile_build2<OPT><<<grid, t2::NT, t2::SMEM_BYTES, st>>>(tm, P, d_planes, wk.par, wk.attr, wk.node_list, wk.node_count, wk.status, tiles_x, wk.prof, wk.ring_rec);
+	k_tile_build2<OPT, MINB><<<grid, t2::NT, t2::SMEM_BYTES, st>>>(tm, P, d_planes, wk.par, wk.attr, wk.node_key, wk.node_count, wk.start_key, wk.status, tiles_x, wk.prof, wk.ring_rec);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
@@ -638,10 +668,12 @@ static int launch_tile_v2_opt(const ExtractParams &P, const PlaneSrc *d_planes, 
 int launch_tile_v2(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st, int opt)
 {
 	switch (opt) {
-	case 0: return launch_tile_v2_opt<0>(P, d_planes, wk, st);
-	case 1: return launch_tile_v2_opt<1>(P, d_planes, wk, st);
-	case 2: return launch_tile_v2_opt<2>(P, d_planes, wk, st);
-	default: return launch_tile_v2_opt<3>(P, d_planes, wk, st);
+	case 0: return launch_tile_v2_opt<0, 4>(P, d_planes, wk, st);
+	case 1: return launch_tile_v2_opt<1, 4>(P, d_planes, wk, st);
+	case 2: return launch_tile_v2_opt<2, 4>(P, d_planes, wk, st);
+	case 4: return launch_tile_v2_opt<3, 5>(P, d_planes, wk, st);
+	case 7: return launch_tile_v2_opt<7, 4>(P, d_planes, wk, st);
+	default: return launch_tile_v2_opt<3, 4>(P, d_planes, wk, st);
 	}
 }
 

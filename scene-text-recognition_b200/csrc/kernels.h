@@ -9,10 +9,11 @@ namespace ert {
 struct alignas(64) TileTensorMap { uint64_t opaque[16]; };
 
 struct ExtractWork {
-	uint32_t *par;          // [n_planes][N] keyed forest
-	NodeAttr *attr;         // [n_planes][N] node attributes (sparse)
-	uint32_t *node_list;    // [n_planes][N] keys of tile-local nodes
-	uint32_t *node_count;   // [n_planes]
+	uint32_t *par;          // [n_planes][node_cap] keyed forest over node slots
+	NodeAttr *attr;         // [n_planes][node_cap] node attributes
+	uint32_t *node_key;     // [n_planes][node_cap] level << 26 | pixel index of the node's level root (its largest own-level pixel)
+	uint32_t *node_count;   // [n_planes] slots handed out
+	uint32_t *start_key;    // [n_planes][4] keys (level, slot) of the nodes holding the flood's start candidates: pixels 0, 1, W
 	uint32_t *reach_root;   // [n_planes]
 	int32_t *lone_level;    // [n_planes]
 	KeptRec *kept;          // [n_planes][kept_cap]
@@ -22,12 +23,14 @@ struct ExtractWork {
 	int tile_cfg;           // index into the tile configuration table
 	unsigned long long *prof;   // optional [16] per-phase cycle sums of k_tile_build (debug)
 	uint32_t *ring_rec;     // [n_planes][tiles][2*(TW+TH)] root keys on the tile sides (seam records)
+	int seam_list;          // 1: k_seam_link_list (compacted edge list per CTA, converged drain); 0: k_seam_link_rec (one thread per seam position)
+	int node_cap;           // slots per plane
 	TileTensorMap tmap;     // (x, y, source plane) view of the plane buffer for k_tile_build2's haloed TMA box
 };
 
 struct NmsParams {
 	int W, H;
-	size_t N;
+	size_t N;               // stride of the per-plane node attribute array (slots per plane)
 	int kept_cap, pool_cap;
 	int min_area, max_area, stability_t;
 	double overlap_coef;
@@ -46,6 +49,18 @@ struct CascadeDev {
 	const int *stage_len;
 	const int *stage_thr;
 	int n_stages;
+	// compact tables for u8 histograms (built at load time): {cp, cn} and dim | ceil(thr) << 16 per stump
+	const double2 *cpcn;
+	const uint32_t *dimthr;
+};
+
+// scratch of the warp-per-(region, stage) cascade kernel: stage sums, per-region arrival counters (self-resetting: zero
+// between launches), first region of every plane
+struct CascadeScratch {
+	double *stage_sum;      // [rows][32]
+	uint32_t *done;         // [rows]
+	int32_t *pool_prefix;   // [planes + 1]
+	int rows_cap, planes_cap;
 };
 
 struct SvmDev {
@@ -53,6 +68,8 @@ struct SvmDev {
 	double gamma;
 	const double *sv;        // [l][dims] dense support vectors
 	const double *coef;      // [nr_class-1][l]
+	const double *coefT;     // [l][nr_class-1] the same table SV-major (a class block's coefficients are contiguous)
+	int legacy_prob;         // 1: k_svm_prob (one warp per vector, A/B); 0: k_svm_decide_prob
 	const double *rho, *probA, *probB;   // [nr_class*(nr_class-1)/2]
 	const int *label, *nsv, *start;      // [nr_class]
 	// tensor-core tables (u8 features): j = round(255 v) and e = round(S (v - j/255)), padded [2048][1920]; |sv|^2
@@ -100,20 +117,24 @@ int launch_tile_v2(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 int tile_config_count();
 size_t ring_words_per_plane(int W, int H);
 int launch_channels(const uint8_t *d_bgr, size_t frame_stride, int row_stride, int W, int H, int n_frames, uint8_t *d_ycc, int pitch, cudaStream_t st);
+int launch_resize_planes(const PlaneSrc *d_src_planes, int n_planes, int sw, int sh, int spitch, uint8_t *d_dst, int dw, int dh, int dpitch, size_t dplane,
+                         cudaStream_t st);
 int launch_unpack_planes(const uint8_t *d_ycc, int pitch, int W, int H, uint8_t *d_out6, cudaStream_t st);
-int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, int local_union, cudaStream_t st,
+int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork &wk, cudaStream_t st,
                    cudaEvent_t ev_tile_begin = nullptr, cudaEvent_t ev_tile_end = nullptr, cudaStream_t st_post = nullptr);
 
 size_t nms_scratch_stride(int kept_cap);
 int launch_nms(const NmsParams &P, int n_planes, const KeptRec *kept, const uint32_t *kept_count, const NodeAttr *attr,
                const uint32_t *reach_root, const int32_t *lone_level, const OutNode *in_nodes, const int32_t *in_offsets,
                uint8_t *scratch, size_t scratch_stride, OutNode *out_nodes, int32_t *out_pool, int32_t *out_counts,
-               uint32_t *status, cudaStream_t st);
+               uint32_t *status, cudaStream_t st, int32_t *order_sens = nullptr);
 
+// first region of every plane: pool_prefix[p] = sum over q < p of min(pool count of plane q, pool_cap)
+int launch_pool_prefix(const int32_t *counts, int n_planes, int pool_cap, int32_t *pool_prefix, cudaStream_t st);
 int launch_lbp_hist(const ClassifyParams &P, int n_planes, const PlaneSrc *planes, const OutNode *nodes, const int32_t *pool,
-                    const int32_t *counts, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st, uint8_t *codes_out = nullptr);
-int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const int32_t *counts, int pool_cap, const CascadeDev &strong,
-                      const CascadeDev &weak, int n_strong, int n_weak, int32_t *label, double *sscore, double *wscore, cudaStream_t st);
+                    const int32_t *pool_prefix, const uint8_t *aran_tbl, uint8_t *hist_out, cudaStream_t st, uint8_t *codes_out = nullptr);
+int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const int32_t *pool_prefix, int n_planes, int pool_cap, const CascadeDev &strong,
+                      const CascadeDev &weak, int32_t *label, double *sscore, double *wscore, const CascadeScratch &sc, cudaStream_t st);
 int launch_cascade_f64(const double *fv, size_t row_stride, int n_rows, const CascadeDev &strong, const CascadeDev &weak,
                        int32_t *label, double *sscore, double *wscore, cudaStream_t st);
 

@@ -5,8 +5,8 @@
 //
 //   k_svm_kvalue : K[n][s] = exp(-gamma * sum_d (x[n][d] - sv[s][d])^2) as a register-tiled FP64
 //                  "distance GEMM" (64x64 output tile per CTA, 4x4 per thread, operands staged in
-//                  shared memory).  FP64 keeps the parsed support-vector values exact; the integer
-//                  tensor-core formulation (u8 x u8 -> s32) is the planned fast path.
+//                  shared memory).  FP64 keeps the parsed support-vector values exact: the audit path and the path for
+//                  arbitrary double inputs; u8 features take k_svm_kvalue_tc below (tcgen05, two integer GEMMs).
 //   k_svm_prob   : one warp per vector: 2080 pairwise decision values (per-pair order of the reference),
 //                  Platt sigmoid, clamp, and the Wu-Lin-Weng coupling iteration with p / Qp in registers,
 //                  shuffle broadcasts and one reciprocal per Gauss-Seidel step (last-bit differences only).
@@ -242,39 +242,11 @@ __device__ __forceinline__ double sigmoid_predict_dev(double dec, double A, doub
 	return 1.0 / (1.0 + exp(f));
 }
 
-__global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const double *__restrict__ kv, int n, double *__restrict__ label_out,
-                                                              double *__restrict__ prob_out)
-{
-	extern __shared__ __align__(16) double dsm[];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int k = m.nr_class;
-	const int tri = k * (k + 1) / 2;                          // upper triangle incl. diagonal: idx(a<=b) = a*k - a*(a-1)/2 + b - a
-	double *Q = dsm + (size_t)warp * ((size_t)tri + MAXK);    // first r[i][j] (i<j; r[j][i] = 1 - r[i][j]), then Q in place
-	double *ps = Q + tri;                                     // p, shared copy for the matrix-vector product
 #define QIDX(a, b) ((a) * k - (a) * ((a) - 1) / 2 + (b) - (a))
-	const int v = blockIdx.x * PROB_WARPS + warp;
-	if (v >= n) return;
-	const double *kvv = kv + (size_t)v * m.l;
-
-	// pairwise decision values (svm_predict_values, src/svm.cpp:2527-2551, same summation order per pair)
-	// -> sigmoid_predict -> clamp [1e-7, 1-1e-7]
-	for (int i = 0; i < k; i++) {
-		for (int j = i + 1 + lane; j < k; j += 32) {
-			const int pidx = i * k - i * (i + 1) / 2 + (j - i - 1);
-			const double *c1 = m.coef + (size_t)(j - 1) * m.l, *c2 = m.coef + (size_t)i * m.l;
-			const int si = m.start[i], sj = m.start[j], ci = m.nsv[i], cj = m.nsv[j];
-			double sum = 0.0;
-			for (int q = 0; q < ci; q++) sum = fma(c1[si + q], kvv[si + q], sum);
-			for (int q = 0; q < cj; q++) sum = fma(c2[sj + q], kvv[sj + q], sum);
-			sum -= m.rho[pidx];
-			double pr = sigmoid_predict_dev(sum, m.probA[pidx], m.probB[pidx]);
-			const double lo = 1e-7;
-			pr = fmin(fmax(pr, lo), 1.0 - lo);
-			Q[QIDX(i, j)] = pr;
-		}
-	}
-	__syncwarp();
-
+// One warp: pairwise probabilities r[i][j] (i < j) in Q's upper triangle -> multiclass_probability -> prob_out / label_out.
+__device__ __forceinline__ void svm_couple_warp(const SvmDev &m, double *Q, double *ps, int k, int lane, int v, double *__restrict__ label_out,
+                                                double *__restrict__ prob_out)
+{
 	// multiclass_probability (src/svm.cpp:1829-1890): Q[t][t] = sum_{j != t} r[j][t]^2, Q[t][j] = -r[j][t] r[t][j].
 	// p and Qp live in registers (3 slots per lane: t = lane, lane+32, lane+64); the Gauss-Seidel sweep broadcasts
 	// Qp[t] by shuffle, so the inner loop has no shared-memory writes and no barriers; 1/(1+diff) is computed once
@@ -352,6 +324,109 @@ __global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const do
 		for (int t = 1; t < k; t++) if (ps[t] > ps[best]) best = t;
 		label_out[v] = (double)m.label[best];
 	}
+}
+#undef QIDX
+
+__global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const double *__restrict__ kv, int n, double *__restrict__ label_out,
+                                                              double *__restrict__ prob_out)
+{
+	extern __shared__ __align__(16) double dsm[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int k = m.nr_class;
+	const int tri = k * (k + 1) / 2;                          // upper triangle incl. diagonal: idx(a<=b) = a*k - a*(a-1)/2 + b - a
+	double *Q = dsm + (size_t)warp * ((size_t)tri + MAXK);    // first r[i][j] (i<j; r[j][i] = 1 - r[i][j]), then Q in place
+	double *ps = Q + tri;                                     // p, shared copy for the matrix-vector product
+#define QIDX(a, b) ((a) * k - (a) * ((a) - 1) / 2 + (b) - (a))
+	const int v = blockIdx.x * PROB_WARPS + warp;
+	if (v >= n) return;
+	const double *kvv = kv + (size_t)v * m.l;
+
+	// pairwise decision values (svm_predict_values, src/svm.cpp:2527-2551, same summation order per pair)
+	// -> sigmoid_predict -> clamp [1e-7, 1-1e-7]
+	for (int i = 0; i < k; i++) {
+		for (int j = i + 1 + lane; j < k; j += 32) {
+			const int pidx = i * k - i * (i + 1) / 2 + (j - i - 1);
+			const double *c1 = m.coef + (size_t)(j - 1) * m.l, *c2 = m.coef + (size_t)i * m.l;
+			const int si = m.start[i], sj = m.start[j], ci = m.nsv[i], cj = m.nsv[j];
+			double sum = 0.0;
+			for (int q = 0; q < ci; q++) sum = fma(c1[si + q], kvv[si + q], sum);
+			for (int q = 0; q < cj; q++) sum = fma(c2[sj + q], kvv[sj + q], sum);
+			sum -= m.rho[pidx];
+			double pr = sigmoid_predict_dev(sum, m.probA[pidx], m.probB[pidx]);
+			const double lo = 1e-7;
+			pr = fmin(fmax(pr, lo), 1.0 - lo);
+			Q[QIDX(i, j)] = pr;
+		}
+	}
+	__syncwarp();
+
+	svm_couple_warp(m, Q, ps, k, lane, v, label_out, prob_out);
+#undef QIDX
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_svm_decide_prob : decision values + probabilities for SVP_V vectors per CTA.
+// The pairwise decision value of (i, j) is S_i[j'] + S_j[i'] - rho with S_c[o'] = sum over the support vectors s of class c
+// of coef[o'][s] * K[s]  (svm_predict_values, src/svm.cpp:2527-2551; o' = the row of sv_coef that faces the other class).
+// Per class block that is a small matrix product [SVP_V vectors x nsv_c] x [nsv_c x (k-1)], so the CTA walks the 65 class
+// blocks once: the block's coefficients (SV-major copy, contiguous) and the vectors' kernel values go to shared memory,
+// every thread owns two (vector, row) outputs, and the sums land in the pair's slot of the vector's upper triangle.
+// k_svm_prob reads 2 x 2080 x ~30 coefficients per VECTOR through L2, uncoalesced (8 MB of sectors per vector); here the
+// table is read once per 8 vectors, coalesced.  Then one warp per vector: Platt sigmoid, clamp, Wu-Lin-Weng coupling.
+// ---------------------------------------------------------------------------------------------
+constexpr int SVP_V = 8, SVP_CHUNK = 64;
+
+__global__ void __launch_bounds__(SVP_V * 32, 1) k_svm_decide_prob(SvmDev m, const double *__restrict__ kv, int n, double *__restrict__ label_out,
+                                                                 double *__restrict__ prob_out)
+{
+	extern __shared__ __align__(16) double dsm[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+	const int k = m.nr_class, k1 = k - 1;
+	const int tri = k * (k + 1) / 2;
+	double *Qall = dsm;                                          // [SVP_V][tri + MAXK]
+	double *Ks = Qall + (size_t)SVP_V * ((size_t)tri + MAXK);    // [SVP_V][SVP_CHUNK]
+	double *Cs = Ks + SVP_V * SVP_CHUNK;                         // [SVP_CHUNK][k1]
+	double *Q = Qall + (size_t)warp * ((size_t)tri + MAXK);
+	double *ps = Q + tri;
+#define QIDX(a, b) ((a) * k - (a) * ((a) - 1) / 2 + (b) - (a))
+	const int v0 = blockIdx.x * SVP_V;
+	const int v = v0 + warp;
+	for (int i = lane; i < tri; i += 32) Q[i] = 0.0;
+	__syncthreads();
+	for (int c = 0; c < k; c++) {
+		const int sc = m.start[c], nc = m.nsv[c];
+		for (int q0 = 0; q0 < nc; q0 += SVP_CHUNK) {
+			const int nq = min(SVP_CHUNK, nc - q0);
+			for (int i = tid; i < SVP_V * nq; i += SVP_V * 32) {
+				const int vv = i / nq, q = i - vv * nq;
+				Ks[vv * SVP_CHUNK + q] = (v0 + vv < n) ? kv[(size_t)(v0 + vv) * m.l + sc + q0 + q] : 0.0;
+			}
+			const double *ct = m.coefT + (size_t)(sc + q0) * k1;
+			for (int i = tid; i < nq * k1; i += SVP_V * 32) Cs[i] = ct[i];
+			__syncthreads();
+			const double *kr = Ks + warp * SVP_CHUNK;
+			for (int o1 = lane; o1 < k1; o1 += 32) {
+				double sum = 0.0;
+				for (int q = 0; q < nq; q++) sum = fma(Cs[q * k1 + o1], kr[q], sum);
+				const int o = (o1 >= c) ? o1 + 1 : o1;           // the other class of the pair
+				const int a = min(c, o), b = max(c, o);
+				Q[QIDX(a, b)] += sum;                            // exactly one thread per (vector, pair) and block
+			}
+			__syncthreads();
+		}
+	}
+	if (v >= n) return;
+	// sigmoid_predict -> clamp [1e-7, 1-1e-7]  (src/svm.cpp:2606-2611)
+	for (int i = 0; i < k; i++)
+		for (int j = i + 1 + lane; j < k; j += 32) {
+			const int pidx = i * k - i * (i + 1) / 2 + (j - i - 1);
+			const double dec = Q[QIDX(i, j)] - m.rho[pidx];
+			double pr = sigmoid_predict_dev(dec, m.probA[pidx], m.probB[pidx]);
+			const double lo = 1e-7;
+			Q[QIDX(i, j)] = fmin(fmax(pr, lo), 1.0 - lo);
+		}
+	__syncwarp();
+	svm_couple_warp(m, Q, ps, k, lane, v, label_out, prob_out);
 #undef QIDX
 }
 
@@ -373,6 +448,16 @@ int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8
 	} else if (x_u8) k_svm_kvalue<uint8_t><<<grid, 256, 0, st>>>(m, x_u8, n, kvalue_ws);
 	else k_svm_kvalue<double><<<grid, 256, 0, st>>>(m, x_f64, n, kvalue_ws);
 	ERT_CUDA_CHECK(cudaGetLastError());
+	{
+		const size_t tri = (size_t)m.nr_class * (m.nr_class + 1) / 2;
+		const size_t smem2 = ((size_t)SVP_V * (tri + MAXK) + (size_t)SVP_V * SVP_CHUNK + (size_t)SVP_CHUNK * (m.nr_class - 1)) * sizeof(double);
+		if (m.coefT && smem2 <= 220 * 1024 && !m.legacy_prob) {
+			ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_decide_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+			k_svm_decide_prob<<<(n + SVP_V - 1) / SVP_V, SVP_V * 32, smem2, st>>>(m, kvalue_ws, n, label, prob);
+			ERT_CUDA_CHECK(cudaGetLastError());
+			return 0;
+		}
+	}
 	const size_t smem = (size_t)PROB_WARPS * ((size_t)m.nr_class * (m.nr_class + 1) / 2 + MAXK) * sizeof(double);
 		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	k_svm_prob<<<(n + PROB_WARPS - 1) / PROB_WARPS, PROB_WARPS * 32, smem, st>>>(m, kvalue_ws, n, label, prob);

@@ -31,7 +31,8 @@ class ErtResult(C.Structure):
     _fields_ = [("n_planes", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("node_offset", _i32p), ("nodes", _i32p), ("pool_offset", _i32p), ("pool_node", _i32p),
                 ("pool_label", _i32p), ("pool_strong_score", _f64p), ("pool_weak_score", _f64p),
-                ("pool_hist", _u8p), ("status", C.c_uint32), ("stage_ms", C.c_double * 8)]
+                ("pool_hist", _u8p), ("status", C.c_uint32), ("stage_ms", C.c_double * 8),
+                ("plane_order_sensitive", _i32p), ("order_sensitive_total", C.c_int32)]
 
 
 class ErtTracked(C.Structure):
@@ -84,14 +85,14 @@ class OcrResult:
 EXPORTS = [
     "ert_set_tile_fifo", "ert_set_nms_sequential", "ert_host_alloc", "ert_host_free", "ert_batch_done", "ert_er_track", "ert_er_track_regions", "ert_ocr_chain_run_batch", "ert_ocr_chain_run_plane", "ert_ocr_features_plane",
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
-    "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
+    "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_config", "ert_set_node_capacity", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
     "ert_load_svm", "ert_svm_nr_class", "ert_set_svm_tensor_cores", "ert_svm_dims", "ert_detect_classify", "ert_enqueue_host", "ert_detect_classify_device",
     "ert_fetch_result", "ert_compute_channels", "ert_planes_detect", "ert_enqueue_planes", "ert_nms_nodes", "ert_classify_regions", "ert_lbp_hist",
     "ert_cascade_predict_batch", "ert_cascade_classify_u8", "ert_svm_predict_probability_batch",
     "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
     "ert_bench_cascade_u8", "ert_bench_svm_u8",
     "ert_set_params", "ert_set_cascade", "ert_cascade_stage_info", "ert_svm_total_sv", "ert_svm_labels", "ert_svm_gamma", "ert_calc_lbp",
-    "ert_er_track_regions_ycc", "ert_set_stream_split",
+    "ert_er_track_regions_ycc", "ert_set_stream_split", "ert_set_seam_list", "ert_enqueue_pyramid_level", "ert_set_planes_per_frame", "ert_set_svm_legacy_prob",
     "ert_dist_unique_id", "ert_dist_create", "ert_dist_destroy", "ert_gather_regions_enqueue", "ert_gather_regions_collect", "ert_gather_regions_outstanding",
 ]
 
@@ -112,14 +113,17 @@ def load_library():
     L.ert_create.restype = C.c_void_p
     L.ert_create.argtypes = [C.POINTER(ErtParams), C.c_int]
     L.ert_destroy.argtypes = [C.c_void_p]
-    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_local_union", "ert_set_tile_config", "ert_set_tile_fifo", "ert_set_nms_sequential", "ert_set_stream_split"):
+    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_config", "ert_set_node_capacity", "ert_set_tile_fifo", "ert_set_nms_sequential", "ert_set_stream_split", "ert_set_seam_list"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_int]
     L.ert_set_capacity.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ert_enqueue_pyramid_level.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.ert_set_planes_per_frame.argtypes = [C.c_void_p, C.c_int]
     L.ert_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
     L.ert_load_cascade.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.ert_load_svm.argtypes = [C.c_void_p, C.c_char_p]
     L.ert_svm_nr_class.argtypes = [C.c_void_p]
     L.ert_set_svm_tensor_cores.argtypes = [C.c_void_p, C.c_int]
+    L.ert_set_svm_legacy_prob.argtypes = [C.c_void_p, C.c_int]
     L.ert_svm_dims.argtypes = [C.c_void_p]
     RP = C.POINTER(C.POINTER(ErtResult))
     L.ert_detect_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, RP]
@@ -237,8 +241,8 @@ class ErText:
     def set_return_hist(self, on):
         self._check(self.L.ert_set_return_hist(self.ctx, int(on)))
 
-    def set_tile_local_union(self, on):
-        self._check(self.L.ert_set_tile_local_union(self.ctx, int(on)))
+    def set_node_capacity(self, slots_per_plane):
+        self._check(self.L.ert_set_node_capacity(self.ctx, int(slots_per_plane)))
 
     def set_nms_sequential(self, on):
         self._check(self.L.ert_set_nms_sequential(self.ctx, int(on)))
@@ -248,6 +252,16 @@ class ErText:
 
     def set_stream_split(self, on):
         self._check(self.L.ert_set_stream_split(self.ctx, int(on)))
+
+    def set_planes_per_frame(self, n):
+        self._check(self.L.ert_set_planes_per_frame(self.ctx, int(n)))
+
+    def enqueue_pyramid_level(self, src, div, upto=STAGE_CLASSIFY):
+        """this context <- the planes of `src`'s batch in flight, resized by 1/div on the device; collect with fetch()"""
+        self._check(self.L.ert_enqueue_pyramid_level(self.ctx, src.ctx, int(div), upto))
+
+    def set_seam_list(self, on):
+        self._check(self.L.ert_set_seam_list(self.ctx, int(on)))
 
     def set_tile_config(self, i):
         self._check(self.L.ert_set_tile_config(self.ctx, i))
@@ -287,7 +301,10 @@ class ErText:
             a, b = int(poff[p]), int(poff[p + 1])
             planes.append(PlaneResult(nodes[noff[p]:noff[p + 1]], pool[a:b], label[a:b], ss[a:b], ws[a:b],
                                       hist[a:b] if hist is not None else None))
-        return BatchResult(planes, int(r.status), list(r.stage_ms), r.width, r.height, (noff, nodes, poff, pool, label))
+        br = BatchResult(planes, int(r.status), list(r.stage_ms), r.width, r.height, (noff, nodes, poff, pool, label))
+        br.order_sensitive = np.ctypeslib.as_array(r.plane_order_sensitive, shape=(r.n_planes,)).copy() if r.plane_order_sensitive else None
+        br.order_sensitive_total = int(r.order_sensitive_total)
+        return br
 
     # ---- the batched hot path ------------------------------------------------------------------
     def detect_classify(self, bgr, upto=STAGE_CLASSIFY):
@@ -309,6 +326,15 @@ class ErText:
 
     def enqueue_host(self, host_ptr, f, w, h, stride, upto=STAGE_CLASSIFY):
         self._check(self.L.ert_enqueue_host(self.ctx, host_ptr, f, w, h, stride, upto))
+
+    def enqueue_host_array(self, bgr, upto=STAGE_CLASSIFY):
+        """enqueue one frame [H, W, 3] or a batch [F, H, W, 3] held in a numpy array (kept alive until fetch)"""
+        a = np.ascontiguousarray(bgr, dtype=np.uint8)
+        if a.ndim == 3:
+            a = a[None]
+        self._keep = a
+        f, h, w, _ = a.shape
+        self._check(self.L.ert_enqueue_host(self.ctx, a.ctypes.data, f, w, h, w * 3, upto))
 
     def enqueue_device(self, dev_ptr, f, w, h, stride, upto=STAGE_CLASSIFY):
         self._check(self.L.ert_detect_classify_device(self.ctx, dev_ptr, f, w, h, stride, upto))
@@ -484,6 +510,9 @@ class ErText:
         op = C.POINTER(ErtOcrResult)()
         self._check(self.L.ert_ocr_chain_run_batch(self.ctx, reg.ctypes.data, len(reg), C.byref(op)))
         return self._unpack_ocr(op)
+
+    def set_svm_legacy_prob(self, on):
+        self._check(self.L.ert_set_svm_legacy_prob(self.ctx, int(on)))
 
     def set_svm_tensor_cores(self, on):
         self._check(self.L.ert_set_svm_tensor_cores(self.ctx, int(on)))

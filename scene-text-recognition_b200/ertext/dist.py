@@ -30,11 +30,19 @@ def pack_records(batch_result, frame_ids):
     return out
 
 
-def gather_records(records, device, max_rows=4096):
-    """all_gather of variable-length record lists: one fixed-size buffer per rank (count in row 0)."""
+def gather_records(records, device, max_rows=None):
+    """all_gather of variable-length record lists through torch.distributed (host-side reference of the library's gather,
+    used by the gloo tests): the counts are gathered first and the payload is sized from the largest one, so nothing is
+    ever dropped.  max_rows, if given, is a hard limit: exceeding it raises instead of truncating."""
     world = dist.get_world_size()
+    n = len(records)
+    if max_rows is not None and n > max_rows:
+        raise ValueError("%d region records on this rank exceed max_rows = %d" % (n, max_rows))
+    cnt = torch.tensor([n], dtype=torch.int32, device=device)
+    cnts = torch.empty((world,), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(cnts, cnt)
+    max_rows = int(cnts.max().item())
     buf = torch.zeros((max_rows + 1, REC_COLS), dtype=torch.int32)
-    n = min(len(records), max_rows)
     buf[0, 0] = n
     if n:
         buf[1:n + 1] = torch.from_numpy(records[:n])
@@ -81,7 +89,9 @@ class RegionGatherer:
     def submit(self, records):
         slot = self.n % self.depth
         self._finish(slot)                       # the collective issued `depth` submits ago
-        n = min(len(records), self.max_rows)
+        if len(records) > self.max_rows:
+            raise ValueError("%d region records on this rank exceed max_rows = %d (nothing is dropped silently)" % (len(records), self.max_rows))
+        n = len(records)
         h = self.host[slot]
         h[0, 0] = n
         if n:
@@ -95,3 +105,78 @@ class RegionGatherer:
             self._finish((self.n + k) % self.depth)
         res, self.done = self.done, []
         return res
+
+
+# ---------------------------------------------------------------------------------------------
+# the library's own gather (csrc/dist.cu): packed on the device, NCCL inside libertext.so, pipelined
+# ---------------------------------------------------------------------------------------------
+import ctypes as _C
+
+
+class _Rec(_C.Structure):
+    _fields_ = [(n, _C.c_int32) for n in ("frame", "plane", "level", "area", "x", "y", "w", "h", "label", "pool_index")]
+
+
+class _GatherResult(_C.Structure):
+    _fields_ = [("world", _C.c_int32), ("n_records", _C.c_int32), ("rank_offset", _C.POINTER(_C.c_int32)), ("records", _C.POINTER(_Rec)),
+                ("sequence", _C.c_longlong)]
+
+
+REC_DTYPE = np.dtype([(n, np.int32) for n in ("frame", "plane", "level", "area", "x", "y", "w", "h", "label", "pool_index")])
+
+
+class LibraryGather:
+    """ert_dist_* of include/ertext.h.  The NCCL unique id travels through torch.distributed (any backend); everything
+    else -- device-side packing, count all-gather, exact-size grouped send / recv, pinned-host landing -- happens inside
+    libertext.so on its own side stream."""
+
+    def __init__(self, device_index, rank, world, max_records_per_rank=16384):
+        import ertext
+        self.L = ertext.load_library()
+        L = self.L
+        L.ert_dist_create.restype = _C.c_void_p
+        L.ert_dist_create.argtypes = [_C.c_int, _C.c_int, _C.c_int, _C.c_void_p, _C.c_int]
+        L.ert_dist_destroy.argtypes = [_C.c_void_p]
+        L.ert_dist_unique_id.argtypes = [_C.c_void_p]
+        L.ert_gather_regions_enqueue.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int]
+        L.ert_gather_regions_collect.argtypes = [_C.c_void_p, _C.POINTER(_C.POINTER(_GatherResult))]
+        L.ert_gather_regions_outstanding.argtypes = [_C.c_void_p]
+        idbuf = (_C.c_ubyte * 128)()
+        if world > 1:
+            if rank == 0 and L.ert_dist_unique_id(idbuf):
+                raise ertext.ErtError(L.ert_last_error().decode())
+            t = torch.tensor(list(idbuf), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda(device_index)
+            dist.broadcast(t, 0)
+            idbuf = (_C.c_ubyte * 128)(*t.cpu().tolist())
+        self.h = L.ert_dist_create(device_index, rank, world, idbuf if world > 1 else None, max_records_per_rank)
+        if not self.h:
+            raise ertext.ErtError(L.ert_last_error().decode())
+        self.world = world
+
+    def enqueue(self, ctx, frame_ids):
+        import ertext
+        ids = np.ascontiguousarray(frame_ids, dtype=np.int32)
+        if self.L.ert_gather_regions_enqueue(self.h, ctx.ctx, ids.ctypes.data, len(ids)):
+            raise ertext.ErtError(self.L.ert_last_error().decode())
+
+    def outstanding(self):
+        return self.L.ert_gather_regions_outstanding(self.h)
+
+    def collect(self):
+        """-> (records as a structured array copied out of the pinned buffer, rank offsets [world + 1], sequence number)"""
+        import ertext
+        rp = _C.POINTER(_GatherResult)()
+        if self.L.ert_gather_regions_collect(self.h, _C.byref(rp)):
+            raise ertext.ErtError(self.L.ert_last_error().decode())
+        r = rp.contents
+        n = r.n_records
+        off = np.ctypeslib.as_array(r.rank_offset, shape=(r.world + 1,)).copy()
+        rec = np.frombuffer((_C.c_char * (n * REC_DTYPE.itemsize)).from_address(_C.addressof(r.records.contents)), dtype=REC_DTYPE).copy() if n else np.zeros(0, REC_DTYPE)
+        return rec, off, int(r.sequence)
+
+    def close(self):
+        if self.h:
+            self.L.ert_dist_destroy(self.h)
+            self.h = None

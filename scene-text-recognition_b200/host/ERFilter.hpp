@@ -10,8 +10,7 @@
 //   struct ER with level/area/bound/parent/child/next/done/stability                     inc/ER.h:42-80
 //   er_track(strong, weak, tracked, ...) incl. calc_color                                 inc/ER.h:129, src/ER.cpp:532-609
 //   OCR(svm_file, img_L, feature_L), chain_run(src, thresh, slope)                        inc/OCR.h:31-35, src/OCR.cpp:67-140
-//   struct Text, er_grouping(all_er, text, overlap_sup, inner_sup) + suppressions + slope  inc/ER.h:84-97,130; src/ER.cpp:612-692,893-964,1362-1389
-//   er_ocr up to the confidence filter (duplicate removal, chain_run per ER, MIN_OCR_PROB)  src/ER.cpp:695-745
+//   struct Text                                                                          inc/ER.h:84-97
 // Downstream CPU stages of the reference (er_track, er_grouping, er_ocr) consume the ER* trees
 // this facade rebuilds from the device results.  With -DERT_WITH_OPENCV the cv::Mat / cv::Rect types
 // are used directly; otherwise minimal stand-ins with the same member names are provided.
@@ -88,159 +87,11 @@ struct Text {
 	std::string word;
 };
 
-// ---- er_grouping and what it calls: small-N, order-dependent host logic (SURVEY 8f rank 3 keeps it on the CPU).
-// A restatement of the reference's semantics (same comparisons, same integer / double conversions, std::sort with the
-// same comparator on the same sequence), checked against the reference's own code in tests/test_grouping_cpu.py. ----
-namespace detail {
-inline int rect_area(const Rect &r) { return r.width * r.height; }
-inline Rect rect_isect(const Rect &a, const Rect &b)
-{
-	const int x1 = std::max(a.x, b.x), y1 = std::max(a.y, b.y);
-	const int x2 = std::min(a.x + a.width, b.x + b.width), y2 = std::min(a.y + a.height, b.y + b.height);
-	if (x2 <= x1 || y2 <= y1) return Rect(0, 0, 0, 0);
-	return Rect(x1, y1, x2 - x1, y2 - y1);
-}
-inline Rect rect_union(const Rect &a, const Rect &b)
-{
-	if (a.width <= 0 || a.height <= 0) return b;
-	if (b.width <= 0 || b.height <= 0) return a;
-	const int x1 = std::min(a.x, b.x), y1 = std::min(a.y, b.y);
-	const int x2 = std::max(a.x + a.width, b.x + b.width), y2 = std::max(a.y + a.height, b.y + b.height);
-	return Rect(x1, y1, x2 - x1, y2 - y1);
-}
-inline double center_dist(const ER *a, const ER *b)
-{
-	const double dx = (double)(a->center.x - b->center.x), dy = (double)(a->center.y - b->center.y);
-	return std::sqrt(dx * dx + dy * dy);
-}
-inline bool by_center_x(ER *a, ER *b) { return a->center.x < b->center.x; }
-} // namespace detail
-
-// ERFilter::overlap_suppression (src/ER.cpp:928-964): an ER absorbs every later ER whose bound overlaps its own by more
-// than half of the union; the survivor's bound becomes the mean box (truncating) and its centre follows.
-inline void overlap_suppression(ERs &pool)
-{
-	std::vector<bool> merged(pool.size(), false);
-	for (size_t i = 0; i < pool.size(); i++) {
-		for (size_t j = i + 1; j < pool.size(); j++) {
-			if (merged[j]) continue;
-			ER *a = pool[i], *b = pool[j];
-			const Rect ov = detail::rect_isect(a->bound, b->bound), un = detail::rect_union(a->bound, b->bound);
-			if ((double)detail::rect_area(ov) / (double)detail::rect_area(un) > 0.5) {
-				merged[j] = true;
-				const int x = (int)((a->bound.x + b->bound.x) * 0.5), y = (int)((a->bound.y + b->bound.y) * 0.5);
-				const int w = (int)((a->bound.width + b->bound.width) * 0.5), h = (int)((a->bound.height + b->bound.height) * 0.5);
-				a->bound.x = x; a->bound.y = y; a->bound.height = h; a->bound.width = w;
-				a->center.x = (int)(x + a->bound.width * 0.5);
-				a->center.y = (int)(y + a->bound.height * 0.5);
-			}
-		}
-	}
-	for (int i = (int)pool.size() - 1; i >= 0; i--) if (merged[(size_t)i]) pool.erase(pool.begin() + i);
-}
-
-// ERFilter::inner_suppression (src/ER.cpp:893-925): drop an ER that sits inside another one more than twice its size
-// whose centre is close (0.2 of the outer one's larger side).
-inline void inner_suppression(ERs &pool)
-{
-	std::vector<bool> drop(pool.size(), false);
-	for (size_t i = 0; i < pool.size(); i++) {
-		for (size_t j = 0; j < pool.size(); j++) {
-			const ER *o = pool[i], *n = pool[j];
-			if (detail::center_dist(o, n) < 0.2 * std::max(o->bound.width, o->bound.height)) {
-				if (o->bound.x <= n->bound.x && o->bound.y <= n->bound.y && o->bound.x + o->bound.width >= n->bound.x + n->bound.width &&
-				    o->bound.y + o->bound.height >= n->bound.y + n->bound.height &&
-				    (double)detail::rect_area(o->bound) / (double)detail::rect_area(n->bound) > 2.0)
-					drop[j] = true;
-			}
-		}
-	}
-	for (int i = (int)pool.size() - 1; i >= 0; i--) if (drop[(size_t)i]) pool.erase(pool.begin() + i);
-}
-
-// fitline_avgslope (src/ER.cpp:1362-1389) on (x, y) points: per consecutive triple the mean of the three pairwise slopes
-// when they agree within 0.07, else the one of smallest magnitude (none if there is a tie); averaged over the triples.
-inline double fitline_avgslope(const std::vector<Point> &p)
-{
-	if (p.size() <= 2) return 0;
-	const double epsilon = 0.07;
-	double slope = .0;
-	for (size_t i = 0; i + 2 < p.size(); i++) {
-		const double s12 = (double)(p[i].y - p[i + 1].y) / (p[i].x - p[i + 1].x);
-		const double s23 = (double)(p[i + 1].y - p[i + 2].y) / (p[i + 1].x - p[i + 2].x);
-		const double s13 = (double)(p[i].y - p[i + 2].y) / (p[i].x - p[i + 2].x);
-		if (std::fabs(s12 - s23) < epsilon && std::fabs(s23 - s13) < epsilon && std::fabs(s12 - s13) < epsilon) slope += (s12 + s23 + s13) / 3;
-		else if (std::fabs(s12) < std::fabs(s23) && std::fabs(s12) < std::fabs(s13)) slope += s12;
-		else if (std::fabs(s23) < std::fabs(s12) && std::fabs(s23) < std::fabs(s13)) slope += s23;
-		else if (std::fabs(s13) < std::fabs(s12) && std::fabs(s13) < std::fabs(s23)) slope += s13;
-	}
-	slope /= (p.size() - 2);
-	return slope;
-}
-
-// ERFilter::er_grouping (src/ER.cpp:612-692).  `text` is expected empty, as every caller of the reference passes it.
-inline void er_grouping(ERs &all_er, std::vector<Text> &text, bool overlap_sup = false, bool inner_sup = false)
-{
-	std::sort(all_er.begin(), all_er.end(), detail::by_center_x);
-	if (overlap_sup) overlap_suppression(all_er);
-	if (inner_sup) inner_suppression(all_er);
-	std::vector<int> group(all_er.size(), -1);
-	int index = 0;
-	for (size_t i = 0; i < all_er.size(); i++) {
-		ER *a = all_er[i];
-		for (size_t j = i + 1; j < all_er.size(); j++) {
-			ER *b = all_er[j];
-			const int hmin = std::min(a->bound.height, b->bound.height);
-			const bool near =
-			    std::abs(a->center.x - b->center.x) < std::max(a->bound.width, b->bound.width) * 3.0 &&
-			    std::abs(a->center.y - b->center.y) < (a->bound.height + b->bound.height) * 0.25 &&
-			    std::abs(a->bound.height - b->bound.height) < hmin &&
-			    std::abs(a->bound.width - b->bound.width) < std::min(a->bound.height, b->bound.height * 2) &&
-			    std::fabs(a->color1 - b->color1) < 25 && std::fabs(a->color2 - b->color2) < 25 && std::fabs(a->color3 - b->color3) < 25 &&
-			    std::abs(a->area - b->area) < std::min(a->area, b->area) * 4;
-			if (!near) continue;
-			if (group[i] == -1 && group[j] == -1) {
-				group[i] = group[j] = index;
-				text.push_back(Text());
-				text[(size_t)index].ers.push_back(a);
-				text[(size_t)index].ers.push_back(b);
-				index++;
-			} else if (group[j] != -1) {           // also taken when BOTH already have a group: a joins b's as well
-				group[i] = group[j];
-				text[(size_t)group[i]].ers.push_back(a);
-			} else {
-				group[j] = group[i];
-				text[(size_t)group[j]].ers.push_back(b);
-			}
-		}
-	}
-	for (size_t t = 0; t < text.size(); t++) {
-		std::sort(text[t].ers.begin(), text[t].ers.end(), detail::by_center_x);
-		ERs tmp(text[t].ers.begin(), text[t].ers.end());
-		overlap_suppression(tmp);                  // edits the shared ERs' bounds in place, as the reference does
-		inner_suppression(tmp);
-		std::vector<Point> pts;
-		for (ER *e : tmp) { Point q; q.x = e->bound.x + e->bound.width; q.y = e->bound.y + e->bound.height; pts.push_back(q); }
-		text[t].slope = fitline_avgslope(pts);
-	}
-}
-
-// the duplicate removal at the head of ERFilter::er_ocr's loop body (src/ER.cpp:702-724)
-inline void er_ocr_remove_duplicates(Text &t)
-{
-	std::vector<bool> del(t.ers.size(), false);
-	for (size_t m = 0; m < t.ers.size(); m++) {
-		for (size_t n = m + 1; n < t.ers.size(); n++) {
-			const double ov = detail::rect_area(detail::rect_isect(t.ers[m]->bound, t.ers[n]->bound));
-			const double un = detail::rect_area(detail::rect_union(t.ers[m]->bound, t.ers[n]->bound));
-			if (ov / un > 0.95) {
-				if (detail::rect_area(t.ers[m]->bound) > detail::rect_area(t.ers[n]->bound)) del[n] = true;
-				else del[m] = true;
-			}
-		}
-	}
-	for (int j = (int)t.ers.size() - 1; j >= 0; j--) if (del[(size_t)j]) t.ers.erase(t.ers.begin() + j);
-}
+// er_grouping / overlap_suppression / inner_suppression / fitline_avgslope / er_ocr (src/ER.cpp:612-786, 893-964,
+// 1362-1389) are NOT part of this facade: they are small-N, order-dependent host logic that the reference keeps (SURVEY 8f
+// rank 3).  A program that needs them links the reference's own definitions -- either against the reference's unmodified
+// headers with host/dropin/erfilter_dropin.cpp underneath (the tested route), or compiled
+// against this header's ER / Text, whose members carry the reference's names.
 
 inline void throw_last(const char *what) { throw std::runtime_error(std::string(what) + ": " + ert_last_error()); }
 
@@ -330,8 +181,11 @@ private:
 
 class ERFilter {
 public:
-	ERFilter(int thresh_step = 2, int min_area = 100, int max_area = 100000, int stability_t = 2, double overlap_coef = 0.7,
-	         double min_ocr_prob = 0.01, int device = 0)
+	// Defaults: the values every hot-path caller of the reference passes (src/main.cpp:22, inc/utils.h:6-11).  The reference's
+	// header default THRESH_STEP = 2 (inc/ER.h:113) is outside the device path's range: thresh_step must be 5..255 (levels are
+	// bytes with 255 reserved for walls and 6 bits in the global keys; steps 1..4 give up to 256 levels) -- ert_create fails loudly.
+	ERFilter(int thresh_step = 8, int min_area = 120, int max_area = 900000, int stability_t = 2, double overlap_coef = 0.7,
+	         double min_ocr_prob = 0.15, int device = 0)
 	    : dev_(make_params(thresh_step, min_area, max_area, stability_t, overlap_coef, min_ocr_prob), device), min_ocr_prob_(min_ocr_prob) {}
 	~ERFilter() {}
 
@@ -341,47 +195,6 @@ public:
 
 	void set_thresh_step(int t) { if (ert_set_thresh_step(dev_.ctx(), t)) throw_last("set_thresh_step"); }
 	void set_min_area(int m) { ert_set_min_area(dev_.ctx(), m); }
-
-	// er_grouping(ERs &all_er, vector<Text> &text, bool overlap_sup, bool inner_sup)  (inc/ER.h:130)
-	void er_grouping(ERs &all_er, std::vector<Text> &text, bool overlap_sup = false, bool inner_sup = false)
-	{
-		ertx::er_grouping(all_er, text, overlap_sup, inner_sup);
-	}
-
-	// er_ocr(all_er, channel, text) up to and including the confidence filter (src/ER.cpp:695-745): per text (last to
-	// first) remove duplicates, chain_run every ER, drop ERs below MIN_OCR_PROB, drop texts left with < 2 ERs.  ALL
-	// chain_run calls of the frame go to the device as ONE batch against the planes text_detect left there.  What
-	// follows in the reference (word graph, feedback_verify, spell check, src/ER.cpp:747-785) is string post-processing
-	// and stays in the reference's code.
-	void er_ocr_letters(std::vector<Text> &text, OCR &ocr)
-	{
-		(void)ocr;   // the model lives in the device context; the parameter documents the dependency (ocr.loaded())
-		std::vector<ert_ocr_region> regs;
-		std::vector<size_t> first(text.size(), 0);
-		for (int i = (int)text.size() - 1; i >= 0; i--) {
-			er_ocr_remove_duplicates(text[(size_t)i]);
-			first[(size_t)i] = regs.size();
-			for (ER *e : text[(size_t)i].ers) {
-				ert_ocr_region r; r.frame = 0; r.plane = e->ch; r.x = e->bound.x; r.y = e->bound.y; r.w = e->bound.width; r.h = e->bound.height;
-				r.slope = text[(size_t)i].slope;
-				regs.push_back(r);
-			}
-		}
-		const ert_ocr_result *o = nullptr;
-		if (!regs.empty() && ert_ocr_chain_run_batch(dev_.ctx(), regs.data(), (int)regs.size(), &o)) throw_last("er_ocr");
-		// an ER can sit in several texts (with different slopes): as in the reference, every text is filtered with the
-		// result of ITS OWN chain_run, and the ER keeps what the text processed last (the lowest index) wrote
-		for (int i = (int)text.size() - 1; i >= 0; i--) {
-			ERs &ers = text[(size_t)i].ers;
-			for (size_t j = 0; j < ers.size(); j++) {
-				const double result = o->value[first[(size_t)i] + j];
-				ers[j]->letter = (char)floor(result);          // src/ER.cpp:733-734
-				ers[j]->prob = result - floor(result);
-			}
-			for (int j = (int)ers.size() - 1; j >= 0; j--) if (ers[(size_t)j]->prob < min_ocr_prob_) ers.erase(ers.begin() + j);
-			if (ers.size() < 2) text.erase(text.begin() + i);    // min_pass_ocr (src/ER.cpp:698,744)
-		}
-	}
 
 	// ERFilter::text_detect up to classify (src/ER.cpp:33-60).  src: 8UC3 BGR.  times[0..2] = extract, nms, classify
 	// seconds (device time), times[6] = wall seconds, like the reference's return value.

@@ -82,16 +82,6 @@ int main(int argc, char **argv)
 					const double result = ocr->chain_run(chn(e->bound), e->level * 8, 0.0);    // src/ER.cpp:732
 					printf("OCR %c %.6f\n", (char)floor(result), result - floor(result));
 				}
-				// the rest of text_detect through the facade: er_grouping (host) -> er_ocr up to the confidence filter
-				// (src/ER.cpp:68-70, 695-745), all chain_run calls of the frame as one device batch
-				std::vector<Text> text;
-				er_filter->er_grouping(tracked2, text, false, true);
-				er_filter->er_ocr_letters(text, *ocr);
-				for (size_t t = 0; t < text.size(); t++) {
-					printf("TXT %.17g", text[t].slope);
-					for (ER *e : text[t].ers) printf(" %d:%d:%d:%d:%d:%c:%.6f", e->ch, e->bound.x, e->bound.y, e->bound.width, e->bound.height, e->letter, e->prob);
-					printf("\n");
-				}
 				delete ocr;
 			}
 			for (int p = 0; p < 6; p++) er_filter->er_delete(root2[(size_t)p]);

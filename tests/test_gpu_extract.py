@@ -20,10 +20,8 @@ KINDS = ["noise", "smooth", "blobs", "walls", "wall0", "wall01", "allwall", "fla
 SIZES = [(1, 1), (1, 9), (7, 1), (31, 33), (32, 64), (33, 65), (64, 128), (100, 130), (257, 191)]
 
 
-@pytest.mark.parametrize("local_union", [1, 0])
 @pytest.mark.parametrize("kind", KINDS)
-def test_planes_match_oracle(ert, port, kind, local_union):
-    ert.set_tile_local_union(local_union)
+def test_planes_match_oracle(ert, port, kind):
     try:
         for si, (h, w) in enumerate(SIZES):
             img = make_plane(si, h, w, kind)
@@ -32,9 +30,9 @@ def test_planes_match_oracle(ert, port, kind, local_union):
                 exp = port.plane(img, scores=True, canonical_order=True)
                 got = ert.planes_detect(img)
                 assert got.status == 0
-                _check(got.planes[0], exp, (kind, h, w, ma, local_union))
+                _check(got.planes[0], exp, (kind, h, w, ma))
     finally:
-        ert.set_tile_local_union(1); ert.set_min_area(120); port.params["min_area"] = 120
+        ert.set_min_area(120); port.params["min_area"] = 120
 
 
 @pytest.mark.parametrize("step", [5, 8, 13, 16, 32])
@@ -59,18 +57,19 @@ def test_batch_of_planes_is_independent_of_position(ert, port):
 
 
 def test_full_hd_plane_and_mode_equivalence(ert, port):
-    """1080p: oracle parity on one natural-like and one noise plane; shared-memory tile pass == all-global pass."""
+    """1080p: oracle parity on one natural-like and one noise plane; the seam kernels (compacted lists / one thread per
+    seam position) agree."""
     for kind in ("blobs", "noise"):
         img = make_plane(42, 1080, 1920, kind)
         exp = port.plane(img, scores=True, canonical_order=True)
         got = ert.planes_detect(img)
         assert got.status == 0
         _check(got.planes[0], exp, kind)
-        ert.set_tile_local_union(0)
+        ert.set_seam_list(0)
         try:
             got0 = ert.planes_detect(img)
         finally:
-            ert.set_tile_local_union(1)
+            ert.set_seam_list(1)
         assert (got0.planes[0].nodes == got.planes[0].nodes).all() and (got0.planes[0].pool == got.planes[0].pool).all()
         root = got.planes[0].nodes[0]
         assert root[6] == -1 and root[1] > 1080 * 1920 - (img >= 252).sum()   # area = pixels + nodes (Q2)
@@ -87,6 +86,17 @@ def test_kept_capacity_overflow_is_reported(ert):
         ert.set_capacity(16384, 2048); ert.set_min_area(120)
 
 
+def test_node_capacity_overflow_is_reported(ert):
+    """more tile-local nodes leave their tiles than the plane's node array holds: flagged, and fine again with the default"""
+    img = make_plane(1, 300, 300, "noise")
+    ert.set_node_capacity(64)
+    try:
+        assert ert.planes_detect(img).status & 16
+    finally:
+        ert.set_node_capacity(0)
+    assert ert.planes_detect(img).status == 0
+
+
 def test_status_word_belongs_to_one_batch(ert):
     """an overflow reported for one batch must not poison the next batch on the same context (the status word is per batch)"""
     img = make_plane(1, 300, 300, "noise")
@@ -101,9 +111,10 @@ def test_status_word_belongs_to_one_batch(ert):
         ert.set_capacity(16384, 2048); ert.set_min_area(120)
 
 
-@pytest.mark.parametrize("cfg", [1, 2])
-def test_tile_kernel_generations_agree(ert, cfg):
-    """the round-1 tile kernels (kept for A/B) and k_tile_build2 produce byte-identical results"""
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+def test_tile_kernel_variants_agree(ert, cfg):
+    """the A/B variants of the tile kernel (per-level fold / arrival counters, with / without the horizontal edge skip)
+    produce byte-identical results"""
     imgs = [make_plane(7, 257, 191, k) for k in ("noise", "blobs", "walls", "checker")] 
     base = [ert.planes_detect(im) for im in imgs]
     ert.set_tile_config(cfg)

@@ -201,35 +201,6 @@ def test_cpp_facade_like_the_reference_callers(ert, port, golden_frames, tmp_pat
     assert len(ocr) == len(sel)
     for i, l in enumerate(ocr):
         assert l[1] == chr(int(np.floor(r.value[i]))) and abs(float(l[2]) - (r.value[i] - np.floor(r.value[i]))) < 1e-6
-    # text_detect -> er_grouping -> er_ocr letters through the facade == the same chain on the reference's own code
-    try:
-        from oracle.refbind import RefOracle
-        ref = RefOracle(with_svm=True)
-    except (FileNotFoundError, OSError):
-        return
-    cand = ft.cand[ft.tracked]
-    rows = np.stack([cand[k].astype(np.float64) for k in ("plane", "x", "y", "w", "h", "area", "center_x", "center_y", "color1", "color2", "color3")], axis=1)
-    g = ref.er_grouping(rows, False, True, dedupe=True)
-    exp = []
-    for slope, members in g["texts"]:
-        ers = []
-        for m in members:
-            ch = int(rows[m, 0]); x, y, w, h = [int(v) for v in g["bounds"][m, :4]]
-            v = ref.chain_run(planes[ch][y:y + h, x:x + w], 0, slope)
-            if v - np.floor(v) >= 0.15:
-                ers.append((ch, x, y, w, h, chr(int(np.floor(v))), v - np.floor(v)))
-        if len(ers) >= 2:
-            exp.append((slope, ers))
-    got = []
-    for l in lines:
-        if l.startswith("TXT"):
-            t = l.split()
-            got.append((float(t[1]), [tuple(e.split(":")) for e in t[2:]]))
-    assert len(got) == len(exp) and len(exp) >= 1
-    for (s1, e1), (s2, e2) in zip(got, exp):
-        assert s1 == s2 and len(e1) == len(e2)
-        for a, b in zip(e1, e2):
-            assert tuple(int(v) for v in a[:5]) == b[:5] and a[5] == b[5] and abs(float(a[6]) - b[6]) <= 1e-4 * b[6] + 1e-6
 
 
 def test_4k_three_plane_four_scale_pyramid(ert, port):
@@ -250,6 +221,75 @@ def test_4k_three_plane_four_scale_pyramid(ert, port):
             assert got.nodes.shape == exp["nodes"].shape and (got.nodes == exp["nodes"]).all(), (s, k)
             assert (got.pool == exp["pool"]).all() and (got.label == exp["label"]).all(), (s, k)
             assert (got.strong_score == exp["strong_score"]).all() and (got.weak_score == exp["weak_score"]).all(), (s, k)
+
+
+def test_device_pyramid_levels_match_cv2_and_oracle(port):
+    """BASELINE configs 2 / 4 on the device: one BGR frame goes up once; the levels 1/2 (exact-2x area path), 1/3 and 1/4
+    (fixed-point bilinear) are resized ON THE DEVICE from its planes (ert_enqueue_pyramid_level) and run through the same
+    path.  Every level must equal the oracle on the cv2.resize'd plane -- which pins the device resize against cv2."""
+    import ertext
+    cv2 = pytest.importorskip("cv2")
+    from ertext import synth
+    frame = synth.s_text_frame(55, 1280, 720, n_glyphs=80)
+    planes = port.channels(frame)
+    for ppf in (6, 3):
+        src = ertext.ErText()
+        src.set_planes_per_frame(ppf)
+        levels = [(d, ertext.ErText()) for d in (2, 3, 4)]
+        src.enqueue_host_array(frame)
+        for d, c in levels:
+            c.enqueue_pyramid_level(src, d)
+        r0 = src.fetch()
+        assert r0.status == 0 and len(r0.planes) == ppf
+        for d, c in levels:
+            r = c.fetch()
+            assert r.status == 0 and len(r.planes) == ppf and (r.width, r.height) == (1280 // d, 720 // d)
+            for k in range(ppf):
+                lvl = cv2.resize(planes[k], (1280 // d, 720 // d), interpolation=cv2.INTER_LINEAR)     # inverted channels are inverted first
+                exp = port.plane(lvl, scores=True, canonical_order=True)
+                got = r.planes[k]
+                assert got.nodes.shape == exp["nodes"].shape and (got.nodes == exp["nodes"]).all(), (ppf, d, k)
+                assert (got.pool == exp["pool"]).all() and (got.label == exp["label"]).all(), (ppf, d, k)
+                assert (got.strong_score == exp["strong_score"]).all(), (ppf, d, k)
+        # the source context can take its next batch at once: the device orders it behind the levels' reads
+        src.enqueue_host_array(frame[::-1].copy())
+        for d, c in levels[:1]:
+            c.enqueue_pyramid_level(src, d)
+        src.fetch(); levels[0][1].fetch()
+        for _, c in levels:
+            c.close()
+        src.close()
+
+
+def test_svm_probability_kernels_agree(ert):
+    """k_svm_decide_prob (8 vectors per CTA, class-block products from shared memory) == the round-1 one-warp-per-vector
+    kernel: same labels, probabilities equal to rounding (the summation order of a decision value differs in the last bits)"""
+    from ertext import synth
+    x = synth.svm_features_u8(3, 523)                   # not a multiple of 8: exercises the partial last CTA
+    lab, prob = ert.svm_predict_probability(x)
+    ert.set_svm_legacy_prob(1)
+    try:
+        lab0, prob0 = ert.svm_predict_probability(x)
+    finally:
+        ert.set_svm_legacy_prob(0)
+    assert (lab == lab0).all()
+    assert np.allclose(prob, prob0, rtol=1e-9, atol=1e-15)
+    assert np.allclose(prob.sum(1), 1.0, atol=1e-9)
+
+
+def test_order_sensitive_counter_is_reported(ert, golden_frames):
+    """ert_result.plane_order_sensitive: how many nodes had two or more sibling chains able to continue into them (the only
+    place the canonical sibling order can matter).  Small on real frames; -1 from the sequential audit walk."""
+    res = ert.detect_classify(golden_frames)
+    assert res.order_sensitive is not None and len(res.order_sensitive) == len(res.planes)
+    assert (res.order_sensitive >= 0).all() and res.order_sensitive_total == int(res.order_sensitive.sum())
+    pooled = sum(len(p.pool) for p in res.planes)
+    assert res.order_sensitive_total <= max(8, pooled)          # rare: a handful per frame
+    ert.set_nms_sequential(1)
+    try:
+        assert ert.detect_classify(golden_frames[:1]).order_sensitive_total == -1
+    finally:
+        ert.set_nms_sequential(0)
 
 
 def test_noise_full_hd_worst_case(ert, port):
@@ -295,7 +335,7 @@ def test_batch_equals_frame_by_frame_and_all_tile_shapes_agree(ert):
             assert (one.planes[k].pool == batch.planes[f * 6 + k].pool).all()
     sig = [(p.nodes.tobytes(), p.pool.tobytes(), p.label.tobytes()) for p in batch.planes]
     try:
-        for cfg in (1, 2, 3, 4):
+        for cfg in (1, 2, 3):
             ert.set_tile_config(cfg)
             r = ert.detect_classify(frames)
             assert [(p.nodes.tobytes(), p.pool.tobytes(), p.label.tobytes()) for p in r.planes] == sig, cfg

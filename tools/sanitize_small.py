@@ -12,7 +12,7 @@ print("bgr", sum(len(p.nodes) for p in r.planes), r.status)
 for kind in ("noise", "walls", "allwall", "flat"):
     r = e.planes_detect(np.stack([make_plane(1, 70, 131, kind), make_plane(2, 70, 131, "smooth")]))
     print(kind, [len(p.nodes) for p in r.planes], r.status)
-e.set_tile_local_union(0); r = e.planes_detect(make_plane(3, 40, 70, "smooth")); e.set_tile_local_union(1)
+e.set_seam_list(0); r = e.planes_detect(make_plane(3, 40, 70, "smooth")); e.set_seam_list(1)
 pl = make_plane(4, 90, 120, "blobs")
 print(e.classify_regions(pl, np.array([[3, 4, 40, 50], [10, 10, 26, 52]], np.int32))[0])
 print(e.lbp_hist(pl, np.array([[0, 0, 30, 30]], np.int32)).sum())

@@ -1,5 +1,5 @@
 """A/B of the tile-build kernels (ert_set_tile_config): outputs must be byte-identical between configurations on a
-ladder of planes (configuration 1 = the round-1 kernel, oracle-validated by the test-suite), then the bench workload
+ladder of planes (ert_set_tile_config 0..3 = variants of k_tile_build2; the default is oracle-validated by the test-suite), then the bench workload
 (8 synthetic 1080p frames = 48 planes) is timed per configuration with the library's CUDA events around the tile
 kernel, plus the per-phase cycle sums of ert_debug_phase_cycles.   python tools/tile_ab.py [--cfgs 0,1] [--quick]
 """
@@ -32,8 +32,8 @@ def same(a, b):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cfgs", default="0,1")
-    ap.add_argument("--base", type=int, default=1)
+    ap.add_argument("--cfgs", default="0,1,2,3")
+    ap.add_argument("--base", type=int, default=0)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--iters", type=int, default=12)
     a = ap.parse_args()
