@@ -207,43 +207,59 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_cascade_stage(const uint8_t *
                                                                  int32_t *__restrict__ label, double *__restrict__ sscore, double *__restrict__ wscore,
                                                                  double *__restrict__ stage_sum, uint32_t *__restrict__ done)
 {
-	const int lane = threadIdx.x & 31;
-	const int gw = blockIdx.x * CS_WARPS + (threadIdx.x >> 5), nw_total = gridDim.x * CS_WARPS;
+	__shared__ double s_v[CS_WARPS][32];            // the 32 selected values of a chunk, re-read by broadcast
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int gw = blockIdx.x * CS_WARPS + wib, nw_total = gridDim.x * CS_WARPS;
 	const int ns = strong.n_stages, nw = weak.n_stages, nst = ns + nw;
 	const int total = pool_prefix ? pool_prefix[n_planes] : n_rows;
 	const long long items = (long long)total * nst;
+	double *sv = s_v[wib];
 	for (long long it = gw; it < items; it += nw_total) {
+		__syncwarp();                                 // lane 0 may still be in the previous item's epilogue
 		const int r = (int)(it / nst), s2 = (int)(it % nst);
 		size_t idx = (size_t)r;
 		if (pool_prefix) {
 			const int plane = plane_of_region(pool_prefix, n_planes, r);
 			idx = (size_t)plane * pool_cap + (size_t)(r - pool_prefix[plane]);
 		}
-		const CascadeDev &c = (s2 < ns) ? strong : weak;
-		const int sl = (s2 < ns) ? s2 : s2 - ns;
+		const bool in_strong = s2 < ns;
+		const int sl = in_strong ? s2 : s2 - ns;
+		const int *slen = in_strong ? strong.stage_len : weak.stage_len;
+		const double2 *cpcn = in_strong ? strong.cpcn : weak.cpcn;
+		const uint32_t *dimthr = in_strong ? strong.dimthr : weak.dimthr;
 		int off = 0;
-		for (int q = 0; q < sl; q++) off += c.stage_len[q];
-		const int len = c.stage_len[sl];
+		for (int q = 0; q < sl; q++) off += slen[q];
+		const int len = slen[sl];
 		const uint8_t *hs = hist + idx * 1024;
 		double score = 0.0;
-		// software pipeline: the next chunk's table entries are in flight while this chunk's 32 adds retire
+		// All lanes execute the same instruction stream (indices clamped, values selected): the warp stays converged, the
+		// next chunk's table entries are in flight while this chunk's 32 adds retire, and the 32 selected values travel
+		// through shared memory (one store, broadcast reads) so the add chain is the only dependent sequence.
+		int jc = max(min(lane, len - 1), 0);
 		double2 cc = make_double2(0.0, 0.0);
 		uint32_t dt = 0;
-		if (lane < len) { cc = __ldg(c.cpcn + off + lane); dt = __ldg(c.dimthr + off + lane); }
+		if (len > 0) { cc = __ldg(cpcn + off + jc); dt = __ldg(dimthr + off + jc); }      // warp-uniform condition
 		for (int c0 = 0; c0 < len; c0 += 32) {
 			const int j = c0 + lane;
-			double v = 0.0;
-			if (j < len) v = ((uint32_t)__ldg(hs + (dt & 0xFFFFu)) < (dt >> 16)) ? cc.x : cc.y;
-			const int jn = j + 32;
-			if (jn < len) { cc = __ldg(c.cpcn + off + jn); dt = __ldg(c.dimthr + off + jn); }
+			const uint32_t h = (uint32_t)__ldg(hs + (dt & 0xFFFFu));
+			const double v = (j < len) ? ((h < (dt >> 16)) ? cc.x : cc.y) : 0.0;
+			jc = min(j + 32, len - 1);
+			cc = __ldg(cpcn + off + jc);
+			dt = __ldg(dimthr + off + jc);
+			sv[lane] = v;
+			__syncwarp();
 			const int m = min(32, len - c0);
 			if (m == 32) {
-				// full chunk, unrolled: the 32 broadcasts do not depend on the running sum and pipeline ahead of the add chain
 #pragma unroll
-				for (int i = 0; i < 32; i++) score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, v, i));
+				for (int i = 0; i < 32; i += 2) {
+					const double2 p = *reinterpret_cast<const double2 *>(sv + i);
+					score = __dadd_rn(score, p.x);
+					score = __dadd_rn(score, p.y);
+				}
 			} else {
-				for (int i = 0; i < m; i++) score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, v, i));
+				for (int i = 0; i < m; i++) score = __dadd_rn(score, sv[i]);
 			}
+			__syncwarp();
 		}
 		uint32_t arrived = 0;
 		if (lane == 0) {

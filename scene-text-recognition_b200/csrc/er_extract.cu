@@ -412,7 +412,7 @@ int extract_pitch(int W) { return (W + 127) / 128 * 128; }
 
 // tile-kernel variants selectable at run time for A/B (ert_set_tile_config): 0 = default (both options of er_tile.cu),
 // 1 = neither, 2 = arrival-counter fold only, 3 = horizontal edge skip only, 4 = as 0 with 48 registers
-int tile_config_count() { return 6; }
+int tile_config_count() { return 5; }
 size_t ring_words_per_plane(int W, int H) { return (size_t)((W + 63) / 64) * ((H + 31) / 32) * 2 * (64 + 32); }
 
 __global__ void k_unpack_planes(const uint8_t *__restrict__ ycc, int pitch, int W, int H, uint8_t *__restrict__ out6)
@@ -451,8 +451,8 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	ERT_CUDA_CHECK(cudaMemsetAsync(wk.node_count, 0, sizeof(uint32_t) * P.n_planes, st));
 	ERT_CUDA_CHECK(cudaMemsetAsync(wk.kept_count, 0, sizeof(uint32_t) * P.n_planes, st));
 	if (ev_tile_begin) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_begin, st));
-	static const int opt_of_cfg[6] = {3, 0, 1, 2, 4, 7};  // 4: as 0, register allocation for 5 CTAs per SM (48 registers); 5: + warp-combined counting
-	if (launch_tile_v2(P, d_planes, wk, st, opt_of_cfg[(wk.tile_cfg >= 0 && wk.tile_cfg < 6) ? wk.tile_cfg : 0])) return -1;
+	static const int opt_of_cfg[5] = {3, 0, 1, 2, 4};     // 4: as 0, register allocation for 5 CTAs per SM (48 registers)
+	if (launch_tile_v2(P, d_planes, wk, st, opt_of_cfg[(wk.tile_cfg >= 0 && wk.tile_cfg < 5) ? wk.tile_cfg : 0])) return -1;
 	if (ev_tile_end) ERT_CUDA_CHECK(cudaEventRecord(ev_tile_end, st));
 	if (st_post && st_post != st) {
 		// everything after the SM-filling tile kernel runs on the context's high-priority stream: its narrow, latency-bound

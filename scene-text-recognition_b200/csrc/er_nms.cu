@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT) k_nms(NmsParams P, const KeptRec *__restri
 		if (tid == 0) { out_counts[2 * plane] = 0; out_counts[2 * plane + 1] = 0; }
 		return;
 	}
-	int n2 = 1;
+	int n2 = 4;                       // at least 4: the per-node byte arrays are also accessed as 32-bit words
 	while (n2 < n) n2 <<= 1;
 	uint8_t *base = (n2 <= smem_cap) ? nms_smem : (scratch + (size_t)plane * scratch_stride);
 	NmsView v = make_view(base, n2);

@@ -68,7 +68,6 @@ __device__ __forceinline__ bool lvl_differs(uint32_t q, uint32_t k) { return (q 
 
 // OPT bit 0: fold interior subtrees with arrival counters (two CTA barriers) instead of one CTA barrier per level
 // OPT bit 1: skip a horizontal edge whose pixel pair repeats the pair right above it (joined through two same-level vertical pairs)
-// OPT bit 2: combine the runs of one node inside a warp before the shared-memory reductions of the counting pass
 // MINB: resident CTAs per SM the register allocation aims at (shared memory allows 4; 5 caps the kernel at 48 registers,
 // which leaves room for two small CTAs of the other stages beside four tile CTAs)
 template <int OPT, int MINB>
@@ -355,20 +354,7 @@ k_tile_build2(const __grid_constant__ CUtensorMap tmap, ExtractParams P, const P
 			}
 			const uint32_t r = k & 0xFFFFu;
 			const bool isroot = live && (r == e);
-			if (OPT & 4) {
-				// runs of one node that sit in the same warp (a smooth region spans many rows) are combined first: one set of
-				// shared-memory reductions per distinct node instead of one per run (same-address atomics serialise)
-				const uint32_t grp = __match_any_sync(FULL, live ? r : (0x10000u + (uint32_t)lane));
-				const uint32_t g_cnt = __reduce_add_sync(grp, live ? xe - xs + 1u + (isroot ? ACC_NODE : 0u) : 0u);
-				const uint32_t g_mn = __reduce_min_sync(grp, xs), g_mx = __reduce_max_sync(grp, xe), g_ym = __reduce_or_sync(grp, 1u << y);
-				if (live && (uint32_t)lane == (uint32_t)(__ffs(grp) - 1)) {
-					const uint32_t ar = attr_s + (r << 2);
-					reds_add(ar, g_cnt);
-					reds_min(ar + TPX * 4, g_mn);
-					reds_max(ar + 2 * TPX * 4, g_mx);
-					reds_or(ar + 3 * TPX * 4, g_ym);
-				}
-			} else if (live) {
+			if (live) {
 				const uint32_t ar = attr_s + (r << 2);
 				reds_add(ar, xe - xs + 1u + (isroot ? ACC_NODE : 0u));
 				reds_min(ar + TPX * 4, xs);
@@ -672,7 +658,6 @@ int launch_tile_v2(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	case 1: return launch_tile_v2_opt<1, 4>(P, d_planes, wk, st);
 	case 2: return launch_tile_v2_opt<2, 4>(P, d_planes, wk, st);
 	case 4: return launch_tile_v2_opt<3, 5>(P, d_planes, wk, st);
-	case 7: return launch_tile_v2_opt<7, 4>(P, d_planes, wk, st);
 	default: return launch_tile_v2_opt<3, 4>(P, d_planes, wk, st);
 	}
 }

@@ -261,6 +261,35 @@ def test_device_pyramid_levels_match_cv2_and_oracle(port):
         src.close()
 
 
+def test_library_region_gather_single_rank(golden_frames):
+    """ert_gather_regions_* at world size 1 (no NCCL): the records packed on the device and landed in pinned memory ==
+    the labelled regions of the result, pipelined over more gathers than the library has slots"""
+    import ertext
+    from ertext import dist as edist
+    g = edist.LibraryGather(0, 0, 1, max_records_per_rank=4096)
+    ctxs = [ertext.ErText(), ertext.ErText()]
+    exp = []
+    for s in range(6):
+        ids = [10 * s + i for i in range(len(golden_frames))]
+        c = ctxs[s % 2]
+        c.enqueue_host_array(golden_frames if s % 2 == 0 else golden_frames[::-1].copy())
+        g.enqueue(c, ids)
+        exp.append(edist.pack_records(c.fetch(), ids))
+        if g.outstanding() >= 3:
+            rec, off, seq = g.collect()
+            got = sorted((int(r["frame"]), int(r["plane"]), int(r["level"]), int(r["area"]), int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"]), int(r["label"])) for r in rec)
+            assert got == sorted(tuple(int(v) for v in row) for row in exp[seq]) and list(off) == [0, len(rec)]
+    n = 0
+    while g.outstanding():
+        rec, off, seq = g.collect()
+        assert len(rec) == len(exp[seq])
+        n += 1
+    assert n >= 2 and len(exp[0]) > 10
+    g.close()
+    for c in ctxs:
+        c.close()
+
+
 def test_svm_probability_kernels_agree(ert):
     """k_svm_decide_prob (8 vectors per CTA, class-block products from shared memory) == the round-1 one-warp-per-vector
     kernel: same labels, probabilities equal to rounding (the summation order of a decision value differs in the last bits)"""
