@@ -302,8 +302,8 @@ def run_ours(a, rank, local_rank, world):
                 ctxs[k].enqueue_host(host_batches[i % NB].data_ptr(), fpg, W, H, W * 3, upto=a.upto)
             pending[k] = True
             if gather is not None and a.upto >= 3:
-                if gather.outstanding() >= 3:
-                    take_gather(record)              # the gather enqueued three steps ago: finished long since
+                if gather.outstanding() >= 6:
+                    take_gather(record)              # the gather enqueued six steps ago: finished long since
                 gather.enqueue(ctxs[k], my_ids)      # packs on the device, NCCL on the library's side stream; returns at once
         for j in range(NC):
             k = (n_steps + j) % NC
@@ -333,6 +333,8 @@ def run_ours(a, rank, local_rank, world):
             dist.barrier()
         return max(start.elapsed_time(e) for e in ends), wall, n
 
+    brackets = {}
+
     def reduce_max(ms):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -343,6 +345,7 @@ def run_ours(a, rank, local_rank, world):
         # every context allocates its workspace on first use: W warm-up steps, but at least one per context
         run_loop(max(a.warmup, NC), resident, False)
         ms, wall, _ = bracket(lambda: run_loop(a.steps, resident, True))
+        brackets["resident" if resident else "e2e"] = {"device_ms_per_step": ms / a.steps, "host_wall_ms_per_step": wall / a.steps}
         # the host-side result collection of the last batches happens after the last kernel: the step ends when the
         # result is in host memory, so take the larger of the device bracket and the host bracket
         return reduce_max(max(ms, wall) if not resident else ms)
@@ -428,7 +431,8 @@ def run_ours(a, rank, local_rank, world):
                    "pipelining": "%d contexts / streams used round-robin; post-tile stages on a high-priority stream per context" % NC,
                    "numa": numa},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fpg * W * H * 3, "d2h_bytes_per_step": int(stats["d2h"] / max(stats["steps"], 1)),
-                "ms_per_step": ms_e2e / a.steps, "h2d_ceiling": ceiling, "fraction_of_h2d_ceiling": e2e / ceiling["frames_per_s"]},
+                "ms_per_step": ms_e2e / a.steps, "h2d_ceiling": ceiling, "fraction_of_h2d_ceiling": e2e / ceiling["frames_per_s"],
+                "rank0_brackets": brackets},
         "gpu_launches": int(res_stats["launches"]),
         "roofline": {"bound": "hbm", "kernel": "k_tile_build2 (64x32 tile + halo per TMA box, 256 threads, 4 px per lane)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,

@@ -6,9 +6,9 @@
 //   enqueue(batch s) : k_pack_regions compacts the batch's strong / weak regions into a send buffer ON THE DEVICE (the
 //                      batch's own high-priority stream, right behind its result compaction), then on the gather's side
 //                      stream: ncclAllGather of the per-rank counts -> pinned host;
-//                      for batch s-1 (counts now known on the host without waiting): ONE grouped exchange of EXACTLY the
-//                      records each rank holds (ncclSend / ncclRecv per peer, ncclGroupStart / End), records -> pinned host
-//   collect()        : the oldest finished gather (normally batch s-2): pointers into pinned host memory.
+//                      for batch s-4 (its counts reached the host long ago, nothing waits): ONE grouped exchange of EXACTLY
+//                      the records each rank holds (ncclSend / ncclRecv per peer, ncclGroupStart / End), records -> pinned host
+//   collect()        : the oldest outstanding gather: pointers into pinned host memory.
 // No padding travels, nothing on the host touches the records, no stream of the data path is ever synchronised.
 // NCCL is bound at run time (dlopen of the libnccl.so.2 the process already has, else the system one): libertext.so
 // has no link-time NCCL dependency and single-GPU users never load it.
@@ -109,7 +109,8 @@ static NcclApi *nccl_api()
 using namespace ert;
 
 namespace {
-constexpr int DEPTH = 4;
+constexpr int DEPTH = 8;       // gathers in flight
+constexpr int LAG = 4;         // the exact-size exchange of batch s - LAG is issued when batch s is enqueued (same order on every rank)
 enum SlotState { FREE = 0, PACKED = 1, EXCHANGED = 2 };
 struct Slot {
 	int state = FREE;
@@ -260,9 +261,11 @@ int ert_gather_regions_enqueue(ert_dist *d, ert_ctx *c, const int32_t *frame_ids
 	ERT_CUDA_CHECK(cudaEventRecord(s.ev_counts, d->stream));
 	s.state = PACKED;
 	d->n_enqueued++;
-	// (3) the exact-size exchange of the PREVIOUS batch: its counts reached the host long ago
-	if (d->n_enqueued >= 2) {
-		Slot &p = d->slot[(d->n_enqueued - 2) % DEPTH];
+	// (3) the exact-size exchange of the batch enqueued LAG calls ago: with a few batches in flight (the data path runs
+	// several contexts round-robin) that batch has long finished, so its counts are on the host and nothing waits.  The lag
+	// is a constant, not a poll: every rank issues its NCCL calls in the same order.
+	if (d->n_enqueued > LAG) {
+		Slot &p = d->slot[(d->n_enqueued - 1 - LAG) % DEPTH];
 		if (p.state == PACKED) { const int rc = exchange_slot(d, p); if (rc) return rc; }
 	}
 	return 0;
