@@ -183,9 +183,10 @@ ERT_API int ert_svm_nr_class(ert_ctx *ctx);   /* svm_get_nr_class (inc/svm.h:81)
 ERT_API int ert_svm_total_sv(ert_ctx *ctx);   /* svm_get_nr_sv (inc/svm.h:84) */
 ERT_API int ert_svm_labels(ert_ctx *ctx, int *label);   /* svm_get_labels (inc/svm.h:82); returns nr_class */
 ERT_API double ert_svm_gamma(ert_ctx *ctx);   /* model->param.gamma */
-/* u8 features: 1 (default) = RBF distances as two exact-integer tcgen05 GEMMs (kind::i8); 0 = FP64 CUDA-core kernel */
+/* u8 features: 1 (default) = RBF distances as two integer tcgen05 GEMMs (kind::i8; TMA ring, TMEM double-buffered);
+ * 2 = the same GEMMs through the round-1 single-stage kernel (A-B); 0 = FP64 CUDA-core kernel */
 ERT_API int ert_set_svm_tensor_cores(ert_ctx *ctx, int on);
-/* A-B: 1 = the round-1 probability kernel (one warp per vector walks the coefficient table); 0 (default) = k_svm_decide_prob */
+/* A-B: 1 = the round-1 probability kernel (one warp per vector walks the coefficient table); 0 (default) = k_svm_decide + k_svm_couple */
 ERT_API int ert_set_svm_legacy_prob(ert_ctx *ctx, int on);
 ERT_API int ert_svm_dims(ert_ctx *ctx);
 

@@ -587,7 +587,7 @@ int ert_load_svm(ert_ctx *c, const char *path)
 	SvmHost &m = c->svm;
 	{
 		// a reload replaces the model: release the previous device tables, keep the caller's tensor-core choice
-		const bool keep_tc = m.use_tc;
+		const int keep_tc = m.use_tc;
 		cudaFree(m.d_sv); cudaFree(m.d_coef); cudaFree(m.d_coefT); cudaFree(m.d_rho); cudaFree(m.d_probA); cudaFree(m.d_probB);
 		cudaFree(m.d_label); cudaFree(m.d_nsv); cudaFree(m.d_start); cudaFree(m.d_svj); cudaFree(m.d_sve); cudaFree(m.d_ss);
 		m = SvmHost();
@@ -725,7 +725,7 @@ int ert_svm_labels(ert_ctx *c, int *label)
 	return c->svm.nr_class;
 }
 double ert_svm_gamma(ert_ctx *c) { return c->svm.loaded ? c->svm.gamma : 0.0; }
-int ert_set_svm_tensor_cores(ert_ctx *c, int on) { c->svm.use_tc = on != 0; return 0; }
+int ert_set_svm_tensor_cores(ert_ctx *c, int on) { if (!c || on < 0 || on > 2) { set_error("bad arguments"); return -1; } c->svm.use_tc = on; return 0; }
 int ert_set_svm_legacy_prob(ert_ctx *c, int on) { c->svm.legacy_prob = on ? 1 : 0; return 0; }
 int ert_svm_dims(ert_ctx *c) { return c->svm.loaded ? c->svm.dims : -1; }
 
@@ -1040,7 +1040,7 @@ static int svm_common(ert_ctx *c, const double *xf, const uint8_t *xu, int n, do
 	cudaStream_t st = c->stream;
 	const SvmHost &m = c->svm;
 	const size_t xb = xf ? sizeof(double) * (size_t)n * m.dims : (size_t)n * m.dims;
-	if (c->s0.ensure(xb) || c->s1.ensure(sizeof(double) * (size_t)n * m.l) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
+	if (c->s0.ensure(xb) || c->s1.ensure(svm_ws_bytes(m.dev(), n)) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, xf ? (const void *)xf : (const void *)xu, xb, cudaMemcpyHostToDevice, st));
 	double *d_label = (double *)c->s3.p, *d_prob = d_label + n;
 	uint8_t *tcws = nullptr;
@@ -1049,7 +1049,7 @@ static int svm_common(ert_ctx *c, const double *xf, const uint8_t *xu, int n, do
 	if (label) ERT_CUDA_CHECK(cudaMemcpyAsync(label, d_label, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
 	if (prob) ERT_CUDA_CHECK(cudaMemcpyAsync(prob, d_prob, sizeof(double) * (size_t)n * m.nr_class, cudaMemcpyDeviceToHost, st));
 	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
-	return 0;
+	return svm_gemm_flag_check(tcws, n);
 }
 
 int ert_svm_predict_probability_batch(ert_ctx *c, const double *x, int n, double *label, double *prob) { return svm_common(c, x, nullptr, n, label, prob); }
@@ -1087,7 +1087,7 @@ int ert_bench_svm_u8(ert_ctx *c, const uint8_t *x, int n, int iters, double *ms_
 	ERT_CUDA_CHECK(cudaSetDevice(c->device));
 	cudaStream_t st = c->stream;
 	const SvmHost &m = c->svm;
-	if (c->s0.ensure((size_t)n * m.dims) || c->s1.ensure(sizeof(double) * (size_t)n * m.l) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
+	if (c->s0.ensure((size_t)n * m.dims) || c->s1.ensure(svm_ws_bytes(m.dev(), n)) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
 	ERT_CUDA_CHECK(cudaMemcpyAsync(c->s0.p, x, (size_t)n * m.dims, cudaMemcpyHostToDevice, st));
 	double *d_label = (double *)c->s3.p, *d_prob = d_label + n;
 	uint8_t *tcws = nullptr;
@@ -1101,7 +1101,7 @@ int ert_bench_svm_u8(ert_ctx *c, const uint8_t *x, int n, int iters, double *ms_
 	float ms = 0;
 	ERT_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
 	*ms_per_iter = (double)ms / iters;
-	return 0;
+	return svm_gemm_flag_check(tcws, n);
 }
 
 } // extern "C"

@@ -129,7 +129,7 @@ int run_ocr(ert_ctx *c, const std::vector<OcrJob> &jobs, bool with_svm, const er
 	if (with_svm) {
 		const SvmHost &m = c->svm;
 		if (m.dims != 1800) { set_error("the loaded SVM has %d dimensions, OCR features have 1800", m.dims); return -1; }
-		if (c->s1.ensure(sizeof(double) * (size_t)n * m.l) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
+		if (c->s1.ensure(svm_ws_bytes(m.dev(), n)) || c->s3.ensure(sizeof(double) * (size_t)n * (m.nr_class + 1))) return -1;
 		d_label = (double *)c->s3.p; d_prob = d_label + n;
 		uint8_t *tcws = nullptr;
 		if (m.use_tc && m.d_svj) { if (c->s4.ensure(svm_tc_ws_bytes(n))) return -1; tcws = (uint8_t *)c->s4.p; }
@@ -146,6 +146,7 @@ int run_ocr(ert_ctx *c, const std::vector<OcrJob> &jobs, bool with_svm, const er
 		ERT_CUDA_CHECK(cudaMemcpyAsync(c->ocr_prob.data(), d_prob, sizeof(double) * (size_t)n * c->svm.nr_class, cudaMemcpyDeviceToHost, st));
 	}
 	ERT_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (with_svm && c->svm.use_tc && c->svm.d_svj && svm_gemm_flag_check((uint8_t *)c->s4.p, n)) return -1;
 	float ms = 0.f;
 	cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]);
 	r.ocr_ms = (double)ms;

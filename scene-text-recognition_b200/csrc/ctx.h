@@ -39,15 +39,25 @@ struct SvmHost {
 	std::vector<uint8_t> svj; std::vector<int8_t> sve; std::vector<double> ss;
 	uint8_t *d_svj = nullptr; int8_t *d_sve = nullptr; double *d_ss = nullptr;
 	double inv_s255 = 0;
-	bool use_tc = true;
+	int use_tc = 1;          // 0 FP64 distance kernel, 1 TMA-pipelined tcgen05 GEMM, 2 round-1 single-stage tcgen05 GEMM
 	SvmDev dev() const
 	{
-		SvmDev m; m.nr_class = nr_class; m.l = l; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef; m.coefT = d_coefT; m.legacy_prob = legacy_prob;
+		SvmDev m; m.nr_class = nr_class; m.l = l; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef; m.coefT = d_coefT; m.legacy_prob = legacy_prob; m.tc_variant = use_tc;
 		m.rho = d_rho; m.probA = d_probA; m.probB = d_probB; m.label = d_label; m.nsv = d_nsv; m.start = d_start;
 		m.svj = use_tc ? d_svj : nullptr; m.sve = d_sve; m.ss = d_ss; m.inv_s255 = inv_s255;
 		return m;
 	}
 };
+
+// after the stream has been synchronised: did an mbarrier wait in the tensor-core GEMM give up? (bounded waits, svm_gemm.cu)
+static inline int svm_gemm_flag_check(uint8_t *tcws, int n)
+{
+	if (!tcws) return 0;
+	uint32_t f = 0;
+	ERT_CUDA_CHECK(cudaMemcpy(&f, svm_tc_flag(tcws, n), sizeof f, cudaMemcpyDeviceToHost));
+	if (f) { set_error("svm: the tensor-core GEMM pipeline timed out (flag %u); results are invalid", f); return -1; }
+	return 0;
+}
 
 template <typename T>
 static int dev_upload(T **dptr, const std::vector<T> &v)

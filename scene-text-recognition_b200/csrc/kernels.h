@@ -69,7 +69,8 @@ struct SvmDev {
 	const double *sv;        // [l][dims] dense support vectors
 	const double *coef;      // [nr_class-1][l]
 	const double *coefT;     // [l][nr_class-1] the same table SV-major (a class block's coefficients are contiguous)
-	int legacy_prob;         // 1: k_svm_prob (one warp per vector, A/B); 0: k_svm_decide_prob
+	int legacy_prob;         // 1: k_svm_prob (one warp per vector, A/B); 0: k_svm_decide + k_svm_couple
+	int tc_variant;          // u8 features: 1 = k_svm_kvalue_tma (TMA ring, double-buffered TMEM), 2 = round-1 single-stage tcgen05 kernel (A/B)
 	const double *rho, *probA, *probB;   // [nr_class*(nr_class-1)/2]
 	const int *label, *nsv, *start;      // [nr_class]
 	// tensor-core tables (u8 features): j = round(255 v) and e = round(S (v - j/255)), padded [2048][1920]; |sv|^2
@@ -138,9 +139,13 @@ int launch_cascade_u8(const uint8_t *hist, size_t row_stride, int n_rows, const 
 int launch_cascade_f64(const double *fv, size_t row_stride, int n_rows, const CascadeDev &strong, const CascadeDev &weak,
                        int32_t *label, double *sscore, double *wscore, cudaStream_t st);
 
-int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *kvalue_ws, double *label, double *prob,
+// ws: svm_ws_bytes(m, n) bytes (kernel values + the two decision-term arrays of one pass of at most 32768 vectors)
+size_t svm_ws_bytes(const SvmDev &m, int n);
+int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *ws, double *label, double *prob,
                        cudaStream_t st, uint8_t *tc_ws = nullptr);
 size_t svm_tc_ws_bytes(int n);
+uint32_t *svm_tc_flag(uint8_t *tc_ws, int n);   // device word after the workspace: nonzero = an mbarrier wait in the GEMM gave up
+int launch_svm_kvalue_tma(const SvmDev &m, const uint8_t *xp, const uint32_t *xx, int n_rows, int row0, int n, double *kv, uint32_t *flag, cudaStream_t st);
 int svm_tc_kpad();
 int svm_tc_npad();
 

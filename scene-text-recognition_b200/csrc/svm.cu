@@ -242,6 +242,18 @@ __device__ __forceinline__ double sigmoid_predict_dev(double dec, double A, doub
 	return 1.0 / (1.0 + exp(f));
 }
 
+// 1 / x to within an ulp or two: hardware seed (>= 20 bits) + two Newton steps.  The Gauss-Seidel sweep below is one long
+// dependency chain per vector, and the IEEE division sequence was most of its length.
+__device__ __forceinline__ double rcp_newton(double x)
+{
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	double e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-x, r, 1.0);
+	return fma(r, e, r);
+}
+
 #define QIDX(a, b) ((a) * k - (a) * ((a) - 1) / 2 + (b) - (a))
 // One warp: pairwise probabilities r[i][j] (i < j) in Q's upper triangle -> multiclass_probability -> prob_out / label_out.
 __device__ __forceinline__ void svm_couple_warp(const SvmDev &m, double *Q, double *ps, int k, int lane, int v, double *__restrict__ label_out,
@@ -249,15 +261,16 @@ __device__ __forceinline__ void svm_couple_warp(const SvmDev &m, double *Q, doub
 {
 	// multiclass_probability (src/svm.cpp:1829-1890): Q[t][t] = sum_{j != t} r[j][t]^2, Q[t][j] = -r[j][t] r[t][j].
 	// p and Qp live in registers (3 slots per lane: t = lane, lane+32, lane+64); the Gauss-Seidel sweep broadcasts
-	// Qp[t] by shuffle, so the inner loop has no shared-memory writes and no barriers; 1/(1+diff) is computed once
-	// per step instead of dividing every element (results differ from libsvm's in the last bits only).
-	double qtt[3], pr_[3], qp[3];
+	// Qp[t] by shuffle, so the inner loop has no shared-memory writes and no barriers; 1/Q[t][t] is computed once per
+	// vector and 1/(1+diff) once per step (Newton reciprocal) instead of dividing every element (results differ from
+	// libsvm's in the last bits only).
+	double qtt[3], iqt[3], pr_[3], qp[3];
 #pragma unroll
 	for (int sl = 0; sl < 3; sl++) {
 		const int t = lane + 32 * sl;
 		double q = 0.0;
 		if (t < k) for (int j = 0; j < k; j++) if (j != t) { const double rjt = (j < t) ? Q[QIDX(j, t)] : 1.0 - Q[QIDX(t, j)]; q = fma(rjt, rjt, q); }
-		qtt[sl] = q; pr_[sl] = (t < k) ? 1.0 / k : 0.0; qp[sl] = 0.0;
+		qtt[sl] = q; iqt[sl] = (t < k) ? 1.0 / q : 0.0; pr_[sl] = (t < k) ? 1.0 / k : 0.0; qp[sl] = 0.0;
 	}
 	__syncwarp();
 	for (int i = 0; i < k; i++)
@@ -297,8 +310,9 @@ __device__ __forceinline__ void svm_couple_warp(const SvmDev &m, double *Q, doub
 			const int sl_t = t >> 5, owner = t & 31;
 			const double qpt = __shfl_sync(0xFFFFFFFFu, sl_t == 0 ? qp[0] : (sl_t == 1 ? qp[1] : qp[2]), owner);
 			const double qt = __shfl_sync(0xFFFFFFFFu, sl_t == 0 ? qtt[0] : (sl_t == 1 ? qtt[1] : qtt[2]), owner);
-			const double diff = (pQp - qpt) / qt;
-			const double inv = 1.0 / (1.0 + diff);
+			const double iq = __shfl_sync(0xFFFFFFFFu, sl_t == 0 ? iqt[0] : (sl_t == 1 ? iqt[1] : iqt[2]), owner);
+			const double diff = (pQp - qpt) * iq;
+			const double inv = rcp_newton(1.0 + diff);
 			pQp = (pQp + diff * fma(diff, qt, 2.0 * qpt)) * inv * inv;
 #pragma unroll
 			for (int sl = 0; sl < 3; sl++) {
@@ -327,8 +341,8 @@ __device__ __forceinline__ void svm_couple_warp(const SvmDev &m, double *Q, doub
 }
 #undef QIDX
 
-__global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const double *__restrict__ kv, int n, double *__restrict__ label_out,
-                                                              double *__restrict__ prob_out)
+__global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const double *__restrict__ kv, int n, int v_out0,
+                                                              double *__restrict__ label_out, double *__restrict__ prob_out)
 {
 	extern __shared__ __align__(16) double dsm[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -360,112 +374,296 @@ __global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const do
 	}
 	__syncwarp();
 
-	svm_couple_warp(m, Q, ps, k, lane, v, label_out, prob_out);
+	svm_couple_warp(m, Q, ps, k, lane, v_out0 + v, label_out, prob_out);
 #undef QIDX
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_svm_decide_prob : decision values + probabilities for SVP_V vectors per CTA.
-// The pairwise decision value of (i, j) is S_i[j'] + S_j[i'] - rho with S_c[o'] = sum over the support vectors s of class c
-// of coef[o'][s] * K[s]  (svm_predict_values, src/svm.cpp:2527-2551; o' = the row of sv_coef that faces the other class).
-// Per class block that is a small matrix product [SVP_V vectors x nsv_c] x [nsv_c x (k-1)], so the CTA walks the 65 class
-// blocks once: the block's coefficients (SV-major copy, contiguous) and the vectors' kernel values go to shared memory,
-// every thread owns two (vector, row) outputs, and the sums land in the pair's slot of the vector's upper triangle.
-// k_svm_prob reads 2 x 2080 x ~30 coefficients per VECTOR through L2, uncoalesced (8 MB of sectors per vector); here the
-// table is read once per 8 vectors, coalesced.  Then one warp per vector: Platt sigmoid, clamp, Wu-Lin-Weng coupling.
+// k_svm_decide + k_svm_couple : decision values and probabilities, two kernels.
+// The pairwise decision value of (i, j), i < j, is S_i[j'] + S_j[i'] - rho with S_c[o'] = sum over the support vectors s of
+// class c of coef[o'][s] * K[s]  (svm_predict_values, src/svm.cpp:2527-2551; o' = the row of sv_coef that faces the other
+// class).  Per class block that is a small matrix product [vectors x nsv_c] x [nsv_c x (k-1)]:
+//   k_svm_decide : CTA = 64 vectors x one class block, 4 x 4 outputs per thread from shared memory (coefficients from the
+//                  SV-major copy, contiguous per block).  The block of class c owns the FIRST term of the pairs (c, o > c)
+//                  and the SECOND term of the pairs (o < c, c): it writes them to two packed-triangle arrays R and C
+//                  ([vectors][k(k-1)/2]), every element exactly once -- no atomics, no zero fill.
+//   k_svm_couple : one warp per vector: dec = R + C - rho (coalesced), Platt sigmoid, clamp, Wu-Lin-Weng coupling.
+// (k_svm_prob, one warp per vector for everything, reads 2 x 2080 x ~30 coefficients per VECTOR through L2, uncoalesced;
+//  a fused 8-vectors-per-CTA variant was latency-bound at one CTA per SM: 430 us per CTA whatever the grid, profiles/README.)
 // ---------------------------------------------------------------------------------------------
-constexpr int SVP_V = 8, SVP_CHUNK = 64;
+constexpr int DEC_V = 64, DEC_Q = 32, DEC_O = 64, DEC_CG = 5;
+constexpr int DEC_KS = DEC_Q * (DEC_V + 2), DEC_CS = DEC_Q * DEC_O;          // doubles per stage
+constexpr size_t DEC_SMEM = 2 * (size_t)(DEC_KS + DEC_CS) * sizeof(double);   // two stages
 
-__global__ void __launch_bounds__(SVP_V * 32, 1) k_svm_decide_prob(SvmDev m, const double *__restrict__ kv, int n, double *__restrict__ label_out,
-                                                                 double *__restrict__ prob_out)
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// grid (class groups, vector tiles, output tiles): the CTAs of one vector tile are neighbours in launch order, so a vector's
+// kernel values (contiguous over the group's classes) and its R / C rows are touched together (L2).  A CTA walks its
+// DEC_CG classes in chunks of DEC_Q support vectors through a two-stage cp.async ring: the next chunk is in flight
+// while this one is multiplied; one barrier per chunk.
+__global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *__restrict__ kv, int n, double *__restrict__ R, double *__restrict__ C)
 {
 	extern __shared__ __align__(16) double dsm[];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-	const int k = m.nr_class, k1 = k - 1;
-	const int tri = k * (k + 1) / 2;
-	double *Qall = dsm;                                          // [SVP_V][tri + MAXK]
-	double *Ks = Qall + (size_t)SVP_V * ((size_t)tri + MAXK);    // [SVP_V][SVP_CHUNK]
-	double *Cs = Ks + SVP_V * SVP_CHUNK;                         // [SVP_CHUNK][k1]
-	double *Q = Qall + (size_t)warp * ((size_t)tri + MAXK);
-	double *ps = Q + tri;
-#define QIDX(a, b) ((a) * k - (a) * ((a) - 1) / 2 + (b) - (a))
-	const int v0 = blockIdx.x * SVP_V;
-	const int v = v0 + warp;
-	for (int i = lane; i < tri; i += 32) Q[i] = 0.0;
-	__syncthreads();
-	for (int c = 0; c < k; c++) {
-		const int sc = m.start[c], nc = m.nsv[c];
-		for (int q0 = 0; q0 < nc; q0 += SVP_CHUNK) {
-			const int nq = min(SVP_CHUNK, nc - q0);
-			for (int i = tid; i < SVP_V * nq; i += SVP_V * 32) {
-				const int vv = i / nq, q = i - vv * nq;
-				Ks[vv * SVP_CHUNK + q] = (v0 + vv < n) ? kv[(size_t)(v0 + vv) * m.l + sc + q0 + q] : 0.0;
-			}
-			const double *ct = m.coefT + (size_t)(sc + q0) * k1;
-			for (int i = tid; i < nq * k1; i += SVP_V * 32) Cs[i] = ct[i];
-			__syncthreads();
-			const double *kr = Ks + warp * SVP_CHUNK;
-			for (int o1 = lane; o1 < k1; o1 += 32) {
-				double sum = 0.0;
-				for (int q = 0; q < nq; q++) sum = fma(Cs[q * k1 + o1], kr[q], sum);
-				const int o = (o1 >= c) ? o1 + 1 : o1;           // the other class of the pair
-				const int a = min(c, o), b = max(c, o);
-				Q[QIDX(a, b)] += sum;                            // exactly one thread per (vector, pair) and block
-			}
-			__syncthreads();
+	const int tid = threadIdx.x, tv = tid >> 4, to = tid & 15;
+	const int k = m.nr_class, k1 = k - 1, np = k * k1 / 2;
+	const int c_begin = blockIdx.x * DEC_CG, c_end = min(k, c_begin + DEC_CG), o0 = blockIdx.z * DEC_O;
+	const int v0 = blockIdx.y * DEC_V;
+
+	auto issue = [&](int c, int q0, int buf) {
+		double *Ks = dsm + (size_t)buf * (DEC_KS + DEC_CS), *Cs = Ks + DEC_KS;
+		const int nq = min(DEC_Q, m.nsv[c] - q0), sq = m.start[c] + q0;
+#pragma unroll
+		for (int i = 0; i < DEC_V * DEC_Q / 256; i++) {
+			const int idx = tid + i * 256, vv = idx >> 5, q = idx & 31;
+			if (q < nq) cp_async8(&Ks[q * (DEC_V + 2) + vv], kv + (size_t)min(v0 + vv, n - 1) * m.l + sq + q);
 		}
+#pragma unroll
+		for (int i = 0; i < DEC_Q * DEC_O / 256; i++) {
+			const int idx = tid + i * 256, q = idx >> 6, o = idx & 63;
+			if (q < nq) cp_async8(&Cs[q * DEC_O + o], m.coefT + (size_t)(sq + q) * k1 + min(o0 + o, k1 - 1));
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+
+	double acc[4][4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+	int c = c_begin, q0 = 0, buf = 0;
+	if (c < c_end) issue(c, 0, 0);
+	while (c < c_end) {
+		const int ncls = m.nsv[c];
+		const int nq = min(DEC_Q, ncls - q0);
+		const bool last_chunk = q0 + DEC_Q >= ncls;
+		const int c_next = last_chunk ? c + 1 : c, q_next = last_chunk ? 0 : q0 + DEC_Q;
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads();                                     // this chunk has landed; everybody is done with the other stage
+		if (c_next < c_end) issue(c_next, q_next, buf ^ 1);
+		const double *Ks = dsm + (size_t)buf * (DEC_KS + DEC_CS), *Cs = Ks + DEC_KS;
+#pragma unroll 4
+		for (int q = 0; q < nq; q++) {
+			const double2 a01 = *reinterpret_cast<const double2 *>(&Ks[q * (DEC_V + 2) + tv * 4]), a23 = *reinterpret_cast<const double2 *>(&Ks[q * (DEC_V + 2) + tv * 4 + 2]);
+			const double2 b01 = *reinterpret_cast<const double2 *>(&Cs[q * DEC_O + to * 4]), b23 = *reinterpret_cast<const double2 *>(&Cs[q * DEC_O + to * 4 + 2]);
+			const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+		}
+		if (last_chunk) {
+			// class c is complete: first term of the pairs (c, o > c) -> R, second term of the pairs (o < c, c) -> C
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const int v = v0 + tv * 4 + i;
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const int o1 = o0 + to * 4 + j;
+					if (v < n && o1 < k1) {
+						const int o = (o1 >= c) ? o1 + 1 : o1;      // the other class of the pair
+						if (c < o) R[(size_t)v * np + (c * k - c * (c + 1) / 2 + (o - c - 1))] = acc[i][j];
+						else       C[(size_t)v * np + (o * k - o * (o + 1) / 2 + (c - o - 1))] = acc[i][j];
+					}
+					acc[i][j] = 0.0;
+				}
+			}
+		}
+		c = c_next; q0 = q_next; buf ^= 1;
 	}
-	if (v >= n) return;
-	// sigmoid_predict -> clamp [1e-7, 1-1e-7]  (src/svm.cpp:2606-2611)
-	for (int i = 0; i < k; i++)
-		for (int j = i + 1 + lane; j < k; j += 32) {
-			const int pidx = i * k - i * (i + 1) / 2 + (j - i - 1);
-			const double dec = Q[QIDX(i, j)] - m.rho[pidx];
-			double pr = sigmoid_predict_dev(dec, m.probA[pidx], m.probB[pidx]);
-			const double lo = 1e-7;
-			Q[QIDX(i, j)] = fmin(fmax(pr, lo), 1.0 - lo);
-		}
-	__syncwarp();
-	svm_couple_warp(m, Q, ps, k, lane, v, label_out, prob_out);
-#undef QIDX
 }
 
-int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *kvalue_ws, double *label, double *prob,
+// One warp per vector.  Shared memory per warp: the strict upper triangle in rho order (pair (i, j), i < j, at
+// i*k - i*(i+1)/2 + j - i - 1 =: rb(i) + j), then p and 1/Q[t][t].  The diagonal of Q lives in registers only.
+//   1. r = clamp(sigmoid((R + C - rho) * A + B))       flat over the pairs, coalesced, no index arithmetic
+//   2. Q[t][t] = sum_{j != t} r[j][t]^2 ;  Q[i][j] = -r[i][j] (1 - r[i][j]) in place
+//   3. Wu-Lin-Weng iteration (multiclass_probability, src/svm.cpp:1829-1890): Qp from scratch, convergence test, then the
+//      Gauss-Seidel sweep.  The sweep is one dependency chain of k steps; per step: one shuffle (Qp[t] from its owner),
+//      one broadcast load (1/Q[t][t]), a Newton reciprocal, and per lane three fused updates whose Q index is
+//      (j < t ? rb(j) + t : rb(t) + j) -- rb(j) is a lane constant, rb(t) warp-uniform.  diff * Q[t][t] is replaced by the
+//      numerator it came from (pQp - Qp[t]); with the reciprocals this differs from libsvm in the last bits only.
+__global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_couple(SvmDev m, const double *__restrict__ R, const double *__restrict__ C, int n, int v_out0,
+                                                                double *__restrict__ label_out, double *__restrict__ prob_out)
+{
+	extern __shared__ __align__(16) double dsm[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int k = m.nr_class, np = k * (k - 1) / 2, kp = (k + 7) & ~7;
+	double *Q = dsm + (size_t)warp * ((size_t)np + 2 * kp);
+	double *ps = Q + np, *iqs = ps + kp;
+	const int v = blockIdx.x * PROB_WARPS + warp;
+	if (v >= n) return;
+	const double *Rv = R + (size_t)v * np, *Cv = C + (size_t)v * np;
+#pragma unroll 4
+	for (int p = lane; p < np; p += 32) {
+		const double dec = (Rv[p] + Cv[p]) - m.rho[p];
+		const double f = __dadd_rn(__dmul_rn(dec, m.probA[p]), m.probB[p]);   // sigmoid_predict, src/svm.cpp:1818-1826
+		const double e = exp(-fabs(f));
+		const double r1 = rcp_newton(1.0 + e);
+		const double pr = (f >= 0) ? e * r1 : r1;
+		Q[p] = fmin(fmax(pr, 1e-7), 1.0 - 1e-7);                               // src/svm.cpp:2606-2611
+	}
+	__syncwarp();
+
+	int tt[3], rbl[3];
+	double qtt[3], pr_[3], qp[3];
+#pragma unroll
+	for (int sl = 0; sl < 3; sl++) {
+		const int t = lane + 32 * sl;
+		tt[sl] = min(t, k - 1);                                  // lanes past k compute on the last class and are masked out
+		rbl[sl] = tt[sl] * k - tt[sl] * (tt[sl] + 1) / 2 - tt[sl] - 1;
+		qtt[sl] = 0.0; qp[sl] = 0.0;
+		pr_[sl] = (t < k) ? 1.0 / k : 0.0;
+	}
+	{
+		int rbj = -1;
+		for (int j = 0; j < k; j++) {
+#pragma unroll
+			for (int sl = 0; sl < 3; sl++) {
+				const int t = tt[sl];
+				const double rv = Q[(j < t) ? rbj + t : rbl[sl] + max(j, t + 1)];
+				const double rjt = (j < t) ? rv : 1.0 - rv;
+				if (j != t) qtt[sl] = fma(rjt, rjt, qtt[sl]);
+			}
+			rbj += k - j - 2;
+		}
+	}
+	__syncwarp();
+#pragma unroll 4
+	for (int p = lane; p < np; p += 32) { const double sij = Q[p]; Q[p] = -((1.0 - sij) * sij); }
+#pragma unroll
+	for (int sl = 0; sl < 3; sl++) { const int t = lane + 32 * sl; if (t < k) { ps[t] = pr_[sl]; iqs[t] = 1.0 / qtt[sl]; } }
+	__syncwarp();
+
+	const int max_iter = max(100, k);
+	const double eps = 0.005 / k;
+	for (int iter = 0; iter < max_iter; iter++) {
+		double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+		{
+			int rbj = -1;
+			for (int j = 0; j < k; j++) {
+				const double pj = ps[j];
+				const double q0 = (j == tt[0]) ? qtt[0] : Q[(j < tt[0]) ? rbj + tt[0] : rbl[0] + max(j, tt[0] + 1)];
+				const double q1 = (j == tt[1]) ? qtt[1] : Q[(j < tt[1]) ? rbj + tt[1] : rbl[1] + max(j, tt[1] + 1)];
+				const double q2 = (j == tt[2]) ? qtt[2] : Q[(j < tt[2]) ? rbj + tt[2] : rbl[2] + max(j, tt[2] + 1)];
+				s0 = fma(q0, pj, s0); s1 = fma(q1, pj, s1); s2 = fma(q2, pj, s2);
+				rbj += k - j - 2;
+			}
+		}
+		qp[0] = s0; qp[1] = s1; qp[2] = s2;
+		double pQp = fma(pr_[2], s2, fma(pr_[1], s1, pr_[0] * s0));
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) pQp += __shfl_xor_sync(0xFFFFFFFFu, pQp, o);
+		double err = 0.0;
+#pragma unroll
+		for (int sl = 0; sl < 3; sl++) if (lane + 32 * sl < k) err = fmax(err, fabs(qp[sl] - pQp));
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) err = fmax(err, __shfl_xor_sync(0xFFFFFFFFu, err, o));
+		if (err < eps) break;
+#pragma unroll
+		for (int SL = 0; SL < 3; SL++) {
+			const int t_end = min(k, 32 * SL + 32);
+			int rbt = (32 * SL) * k - (32 * SL) * (32 * SL + 1) / 2 - 32 * SL - 1;
+			for (int t = 32 * SL; t < t_end; t++) {
+				const double qpt = __shfl_sync(0xFFFFFFFFu, qp[SL], t - 32 * SL);
+				const double num = pQp - qpt;
+				const double diff = num * iqs[t];
+				const double inv = rcp_newton(1.0 + diff);
+				pQp = (pQp + diff * (num + 2.0 * qpt)) * inv * inv;
+				if (lane == t - 32 * SL) pr_[SL] += diff;
+#pragma unroll
+				for (int sl = 0; sl < 3; sl++) {
+					const int j = tt[sl];
+					const double qv = Q[(j < t) ? rbl[sl] + t : rbt + max(j, t + 1)];
+					const double qtj = (j == t) ? qtt[sl] : qv;
+					qp[sl] = fma(diff, qtj, qp[sl]) * inv;
+					pr_[sl] *= inv;
+				}
+				rbt += k - t - 2;
+			}
+		}
+#pragma unroll
+		for (int sl = 0; sl < 3; sl++) { const int t = lane + 32 * sl; if (t < k) ps[t] = pr_[sl]; }
+		__syncwarp();
+	}
+	// argmax, first maximum wins (svm_predict_probability, src/svm.cpp:2620-2626)
+	double bv = -1.0; int bi = 0;
+#pragma unroll
+	for (int sl = 0; sl < 3; sl++) {
+		const int t = lane + 32 * sl;
+		if (t < k) { prob_out[(size_t)(v_out0 + v) * k + t] = pr_[sl]; if (pr_[sl] > bv) { bv = pr_[sl]; bi = t; } }
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+		const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+		if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+	}
+	if (lane == 0) label_out[v_out0 + v] = (double)m.label[bi];
+}
+
+// vectors per pass: bounds the workspace (K, R, C: ~48 KB per vector for OCR.model) whatever the batch
+constexpr int SVM_PASS = 32768;
+
+size_t svm_ws_bytes(const SvmDev &m, int n)
+{
+	const size_t c = (size_t)min(n, SVM_PASS), np = (size_t)m.nr_class * (m.nr_class - 1) / 2;
+	return sizeof(double) * c * ((size_t)m.l + 2 * np) + 1024;
+}
+
+int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *ws, double *label, double *prob,
                        cudaStream_t st, uint8_t *tc_ws)
 {
 	if (n <= 0) return 0;
 	if (m.nr_class > MAXK) { set_error("svm: nr_class %d > %d unsupported", m.nr_class, MAXK); return -1; }
-	dim3 grid((m.l + KT - 1) / KT, (n + KT - 1) / KT);
-	if (x_u8 && m.svj && tc_ws && m.dims <= TC_KPAD && m.l <= TC_NPAD) {
-		uint8_t *xp = tc_ws;
-		uint32_t *xx = reinterpret_cast<uint32_t *>(tc_ws + (((size_t)n * TC_KPAD + 255) / 256) * 256);
+	const size_t np = (size_t)m.nr_class * (m.nr_class - 1) / 2;
+	const size_t tri = (size_t)m.nr_class * (m.nr_class + 1) / 2;
+	const bool tc = x_u8 && m.svj && tc_ws && m.dims <= TC_KPAD && m.l <= TC_NPAD;
+	uint8_t *xp = tc_ws;
+	uint32_t *xx = tc ? reinterpret_cast<uint32_t *>(tc_ws + (((size_t)n * TC_KPAD + 255) / 256) * 256) : nullptr;
+	if (tc) {
+		ERT_CUDA_CHECK(cudaMemsetAsync(svm_tc_flag(tc_ws, n), 0, sizeof(uint32_t), st));
 		k_svm_prep_x<<<(n + 3) / 4, 128, 0, st>>>(x_u8, n, m.dims, xp, xx);
 		ERT_CUDA_CHECK(cudaGetLastError());
-		const size_t smem = 16384 + 2 * 32768;
-		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_kvalue_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		dim3 g2(TC_NPAD / TC_N, (n + TC_M - 1) / TC_M);
-		k_svm_kvalue_tc<<<g2, 128, smem, st>>>(xp, xx, n, m.svj, m.sve, m.ss, m.l, m.gamma, m.inv_s255, kvalue_ws);
-	} else if (x_u8) k_svm_kvalue<uint8_t><<<grid, 256, 0, st>>>(m, x_u8, n, kvalue_ws);
-	else k_svm_kvalue<double><<<grid, 256, 0, st>>>(m, x_f64, n, kvalue_ws);
-	ERT_CUDA_CHECK(cudaGetLastError());
-	{
-		const size_t tri = (size_t)m.nr_class * (m.nr_class + 1) / 2;
-		const size_t smem2 = ((size_t)SVP_V * (tri + MAXK) + (size_t)SVP_V * SVP_CHUNK + (size_t)SVP_CHUNK * (m.nr_class - 1)) * sizeof(double);
-		if (m.coefT && smem2 <= 220 * 1024 && !m.legacy_prob) {
-			ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_decide_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-			k_svm_decide_prob<<<(n + SVP_V - 1) / SVP_V, SVP_V * 32, smem2, st>>>(m, kvalue_ws, n, label, prob);
-			ERT_CUDA_CHECK(cudaGetLastError());
-			return 0;
-		}
 	}
-	const size_t smem = (size_t)PROB_WARPS * ((size_t)m.nr_class * (m.nr_class + 1) / 2 + MAXK) * sizeof(double);
-		ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-	k_svm_prob<<<(n + PROB_WARPS - 1) / PROB_WARPS, PROB_WARPS * 32, smem, st>>>(m, kvalue_ws, n, label, prob);
-	ERT_CUDA_CHECK(cudaGetLastError());
+	const size_t smem_tc = 16384 + 2 * 32768;
+	const size_t smem_q = (size_t)PROB_WARPS * (tri + MAXK) * sizeof(double);
+	const size_t smem_c = (size_t)PROB_WARPS * (np + 2 * (size_t)((m.nr_class + 7) & ~7)) * sizeof(double);
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_kvalue_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_couple, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM));
+	const int cap = min(n, SVM_PASS);
+	double *kv = ws, *R = ws + (size_t)cap * m.l, *C = R + (size_t)cap * np;
+	for (int v0 = 0; v0 < n; v0 += SVM_PASS) {
+		const int nc = min(SVM_PASS, n - v0);
+		if (tc && m.tc_variant != 2) {
+			if (launch_svm_kvalue_tma(m, xp, xx, n, v0, nc, kv, svm_tc_flag(tc_ws, n), st)) return -1;
+		} else if (tc) {
+			dim3 g2(TC_NPAD / TC_N, (nc + TC_M - 1) / TC_M);
+			k_svm_kvalue_tc<<<g2, 128, smem_tc, st>>>(xp + (size_t)v0 * TC_KPAD, xx + v0, nc, m.svj, m.sve, m.ss, m.l, m.gamma, m.inv_s255, kv);
+		} else {
+			dim3 grid((m.l + KT - 1) / KT, (nc + KT - 1) / KT);
+			if (x_u8) k_svm_kvalue<uint8_t><<<grid, 256, 0, st>>>(m, x_u8 + (size_t)v0 * m.dims, nc, kv);
+			else k_svm_kvalue<double><<<grid, 256, 0, st>>>(m, x_f64 + (size_t)v0 * m.dims, nc, kv);
+		}
+		ERT_CUDA_CHECK(cudaGetLastError());
+		if (m.coefT && !m.legacy_prob) {
+			dim3 g3((m.nr_class + DEC_CG - 1) / DEC_CG, (nc + DEC_V - 1) / DEC_V, (m.nr_class - 1 + DEC_O - 1) / DEC_O);
+			k_svm_decide<<<g3, 256, DEC_SMEM, st>>>(m, kv, nc, R, C);
+			ERT_CUDA_CHECK(cudaGetLastError());
+			k_svm_couple<<<(nc + PROB_WARPS - 1) / PROB_WARPS, PROB_WARPS * 32, smem_c, st>>>(m, R, C, nc, v0, label, prob);
+		} else {
+			k_svm_prob<<<(nc + PROB_WARPS - 1) / PROB_WARPS, PROB_WARPS * 32, smem_q, st>>>(m, kv, nc, v0, label, prob);
+		}
+		ERT_CUDA_CHECK(cudaGetLastError());
+	}
 	return 0;
 }
 
 size_t svm_tc_ws_bytes(int n) { return (((size_t)n * TC_KPAD + 255) / 256) * 256 + (size_t)n * 4 + 256; }
+uint32_t *svm_tc_flag(uint8_t *tc_ws, int n) { return reinterpret_cast<uint32_t *>(tc_ws + (((size_t)n * TC_KPAD + 255) / 256) * 256) + n; }
 int svm_tc_kpad() { return TC_KPAD; }
 int svm_tc_npad() { return TC_NPAD; }
 

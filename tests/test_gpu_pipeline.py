@@ -101,6 +101,13 @@ def test_svm_batch_vs_reference_golden(ert, golden_svm):
         ert.set_svm_tensor_cores(1)
     assert (label3 == label).all()
     assert (np.abs(prob3 - prob) / np.maximum(prob3, 1e-300)).max() < 1e-6
+    # the TMA-pipelined GEMM (default) and the round-1 single-stage tcgen05 kernel compute the same integer sums: identical results
+    ert.set_svm_tensor_cores(2)
+    try:
+        label4, prob4 = ert.svm_predict_probability(golden_svm["x_u8"])
+    finally:
+        ert.set_svm_tensor_cores(1)
+    assert (label4 == label).all() and (prob4 == prob).all()
 
 
 def test_device_resident_entry_and_async_pair(ert, golden_frames):
@@ -328,10 +335,11 @@ def test_library_region_gather_single_rank(golden_frames):
 
 
 def test_svm_probability_kernels_agree(ert):
-    """k_svm_decide_prob (8 vectors per CTA, class-block products from shared memory) == the round-1 one-warp-per-vector
-    kernel: same labels, probabilities equal to rounding (the summation order of a decision value differs in the last bits)"""
+    """k_svm_decide + k_svm_couple (class-block products, 64 vectors per CTA, then one warp per vector) == the round-1
+    one-warp-per-vector kernel: same labels, probabilities equal to rounding (the summation order of a decision value and
+    the Newton reciprocal in the sweep differ in the last bits)"""
     from ertext import synth
-    x = synth.svm_features_u8(3, 523)                   # not a multiple of 8: exercises the partial last CTA
+    x = synth.svm_features_u8(3, 523)                   # not a multiple of 64: exercises the partial last CTA
     lab, prob = ert.svm_predict_probability(x)
     ert.set_svm_legacy_prob(1)
     try:
@@ -341,6 +349,33 @@ def test_svm_probability_kernels_agree(ert):
     assert (lab == lab0).all()
     assert np.allclose(prob, prob0, rtol=1e-9, atol=1e-15)
     assert np.allclose(prob.sum(1), 1.0, atol=1e-9)
+
+
+def test_svm_gemm_variants_bit_identical_on_ragged_batches(ert):
+    """k_svm_kvalue_tma (persistent, TMA ring, TMEM double buffer) against the single-stage kernel on batch sizes that leave
+    partial tiles, one tile, and many tiles per CTA: same integer accumulators, so the probabilities are bit-identical."""
+    from ertext import synth
+    for n in (1, 127, 129, 1000, 20001):
+        x = synth.svm_features_u8(100 + n, n)
+        lab, prob = ert.svm_predict_probability(x)
+        ert.set_svm_tensor_cores(2)
+        try:
+            lab2, prob2 = ert.svm_predict_probability(x)
+        finally:
+            ert.set_svm_tensor_cores(1)
+        assert (lab == lab2).all() and (prob == prob2).all(), n
+
+
+def test_svm_batches_larger_than_one_pass(ert):
+    """The scorer walks a batch in passes of 32768 vectors (bounded workspace): rows of a 40000-vector batch made of a
+    repeated block must repeat exactly, across the pass boundary too."""
+    from ertext import synth
+    base = synth.svm_features_u8(11, 500)
+    x = np.tile(base, (80, 1))
+    lab, prob = ert.svm_predict_probability(x)
+    lab0, prob0 = ert.svm_predict_probability(base)
+    assert (lab.reshape(80, 500) == lab0[None]).all()
+    assert (prob.reshape(80, 500, -1) == prob0[None]).all()
 
 
 def test_order_sensitive_counter_is_reported(ert, golden_frames):
