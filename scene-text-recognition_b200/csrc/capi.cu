@@ -421,7 +421,7 @@ void ert_destroy(ert_ctx *c)
 	cudaFree(c->d_bgr); cudaFree(c->d_aran_tbl);
 	for (int k = 0; k < 2; k++) { cudaFree(c->casc[k].d_stumps); cudaFree(c->casc[k].d_len); cudaFree(c->casc[k].d_thr); cudaFree(c->casc[k].d_cpcn); cudaFree(c->casc[k].d_dimthr); }
 	cudaFree(c->csc.stage_sum); cudaFree(c->csc.done); cudaFree(c->csc.pool_prefix);
-	cudaFree(c->svm.d_sv); cudaFree(c->svm.d_coef); cudaFree(c->svm.d_coefT); cudaFree(c->svm.d_rho); cudaFree(c->svm.d_probA); cudaFree(c->svm.d_probB);
+	cudaFree(c->svm.d_sv); cudaFree(c->svm.d_coef); cudaFree(c->svm.d_coefT); cudaFree(c->svm.d_pair_ij); cudaFree(c->svm.d_rho); cudaFree(c->svm.d_probA); cudaFree(c->svm.d_probB);
 	cudaFree(c->svm.d_label); cudaFree(c->svm.d_nsv); cudaFree(c->svm.d_start);
 	cudaFree(c->svm.d_svj); cudaFree(c->svm.d_sve); cudaFree(c->svm.d_ss);
 	c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
@@ -588,7 +588,7 @@ int ert_load_svm(ert_ctx *c, const char *path)
 	{
 		// a reload replaces the model: release the previous device tables, keep the caller's tensor-core choice
 		const int keep_tc = m.use_tc;
-		cudaFree(m.d_sv); cudaFree(m.d_coef); cudaFree(m.d_coefT); cudaFree(m.d_rho); cudaFree(m.d_probA); cudaFree(m.d_probB);
+		cudaFree(m.d_sv); cudaFree(m.d_coef); cudaFree(m.d_coefT); cudaFree(m.d_pair_ij); m.d_pair_ij = nullptr; cudaFree(m.d_rho); cudaFree(m.d_probA); cudaFree(m.d_probB);
 		cudaFree(m.d_label); cudaFree(m.d_nsv); cudaFree(m.d_start); cudaFree(m.d_svj); cudaFree(m.d_sve); cudaFree(m.d_ss);
 		m = SvmHost();
 		m.use_tc = keep_tc;
@@ -670,7 +670,7 @@ int ert_load_svm(ert_ctx *c, const char *path)
 	// tensor-core tables: v = j/255 + eps with j = round(255 v); e = round(S * eps), S = 127 / max|eps|
 	if (m.dims <= svm_tc_kpad() && m.l <= svm_tc_npad()) {
 		const int KP = svm_tc_kpad(), NP = svm_tc_npad();
-		m.svj.assign((size_t)NP * KP, 0); m.sve.assign((size_t)NP * KP, 0); m.ss.assign((size_t)m.l, 0.0);
+		m.svj.assign((size_t)NP * KP, 0); m.sve.assign((size_t)NP * KP, 0); m.ss.assign((size_t)NP, 0.0);
 		double maxeps = 0;
 		bool ok = true;
 		for (int i = 0; i < m.l && ok; i++)
@@ -701,6 +701,9 @@ int ert_load_svm(ert_ctx *c, const char *path)
 	m.coefT.assign((size_t)m.l * k1, 0.0);
 	for (int j = 0; j < k1; j++) for (int i = 0; i < m.l; i++) m.coefT[(size_t)i * k1 + j] = m.coef[(size_t)j * m.l + i];
 	if (dev_upload(&m.d_coefT, m.coefT)) return -1;
+	m.pair_ij.clear();
+	for (int i = 0; i < m.nr_class; i++) for (int j = i + 1; j < m.nr_class; j++) m.pair_ij.push_back((uint16_t)(i << 8 | j));
+	if (dev_upload(&m.d_pair_ij, m.pair_ij)) return -1;
 	if (dev_upload(&m.d_sv, m.sv) || dev_upload(&m.d_coef, m.coef) || dev_upload(&m.d_rho, m.rho) || dev_upload(&m.d_probA, m.probA) ||
 	    dev_upload(&m.d_probB, m.probB) || dev_upload(&m.d_label, m.label) || dev_upload(&m.d_nsv, m.nsv) || dev_upload(&m.d_start, m.start)) return -1;
 	m.loaded = true;

@@ -34,6 +34,7 @@ struct SvmHost {
 	std::vector<int> label, nsv, start;
 	double *d_sv = nullptr, *d_coef = nullptr, *d_rho = nullptr, *d_probA = nullptr, *d_probB = nullptr;
 	std::vector<double> coefT; double *d_coefT = nullptr;
+	std::vector<uint16_t> pair_ij; uint16_t *d_pair_ij = nullptr;   // pair p of the rho order -> i << 8 | j
 	int legacy_prob = 0;
 	int *d_label = nullptr, *d_nsv = nullptr, *d_start = nullptr;
 	std::vector<uint8_t> svj; std::vector<int8_t> sve; std::vector<double> ss;
@@ -42,7 +43,7 @@ struct SvmHost {
 	int use_tc = 1;          // 0 FP64 distance kernel, 1 TMA-pipelined tcgen05 GEMM, 2 round-1 single-stage tcgen05 GEMM
 	SvmDev dev() const
 	{
-		SvmDev m; m.nr_class = nr_class; m.l = l; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef; m.coefT = d_coefT; m.legacy_prob = legacy_prob; m.tc_variant = use_tc;
+		SvmDev m; m.nr_class = nr_class; m.l = l; m.ldk = (l + 127) & ~127; m.dims = dims; m.gamma = gamma; m.sv = d_sv; m.coef = d_coef; m.coefT = d_coefT; m.pair_ij = d_pair_ij; m.legacy_prob = legacy_prob; m.tc_variant = use_tc;
 		m.rho = d_rho; m.probA = d_probA; m.probB = d_probB; m.label = d_label; m.nsv = d_nsv; m.start = d_start;
 		m.svj = use_tc ? d_svj : nullptr; m.sve = d_sve; m.ss = d_ss; m.inv_s255 = inv_s255;
 		return m;

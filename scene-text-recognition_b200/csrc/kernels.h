@@ -65,10 +65,12 @@ struct CascadeScratch {
 
 struct SvmDev {
 	int nr_class, l, dims;
+	int ldk;                 // row stride of the kernel-value matrix K[vectors][ldk]: l rounded up to 128 (whole tiles, 16-byte stores)
 	double gamma;
 	const double *sv;        // [l][dims] dense support vectors
 	const double *coef;      // [nr_class-1][l]
 	const double *coefT;     // [l][nr_class-1] the same table SV-major (a class block's coefficients are contiguous)
+	const uint16_t *pair_ij; // [nr_class*(nr_class-1)/2] classes of pair p (rho order): i << 8 | j
 	int legacy_prob;         // 1: k_svm_prob (one warp per vector, A/B); 0: k_svm_decide + k_svm_couple
 	int tc_variant;          // u8 features: 1 = k_svm_kvalue_tma (TMA ring, double-buffered TMEM), 2 = round-1 single-stage tcgen05 kernel (A/B)
 	const double *rho, *probA, *probB;   // [nr_class*(nr_class-1)/2]

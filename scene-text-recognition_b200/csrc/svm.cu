@@ -12,6 +12,7 @@
 //                  shuffle broadcasts and one reciprocal per Gauss-Seidel step (last-bit differences only).
 #include "common.cuh"
 #include "kernels.h"
+#include "svm_math.cuh"
 
 namespace ert {
 
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) k_svm_kvalue(SvmDev m, const XT *__restri
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
 			const int r = n0 + ty * 4 + i, s = s0 + tx * 4 + j;
-			if (r < n && s < m.l) kv[(size_t)r * m.l + s] = exp(-m.gamma * acc[i][j]);
+			if (r < n && s < m.l) kv[(size_t)r * m.ldk + s] = exp(-m.gamma * acc[i][j]);
 		}
 }
 
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(128) k_svm_prep_x(const uint8_t *__restrict__ 
 
 __global__ void __launch_bounds__(128, 1) k_svm_kvalue_tc(const uint8_t *__restrict__ xp, const uint32_t *__restrict__ xx, int n,
                                                          const uint8_t *__restrict__ svj, const int8_t *__restrict__ sve,
-                                                         const double *__restrict__ ss, int l, double gamma, double inv_s255,
+                                                         const double *__restrict__ ss, int l, int ldk, double gamma, double inv_s255,
                                                          double *__restrict__ kv)
 {
 	extern __shared__ __align__(1024) uint8_t tsm[];
@@ -220,9 +221,9 @@ __global__ void __launch_bounds__(128, 1) k_svm_kvalue_tc(const uint8_t *__restr
 			for (int j = 0; j < 16; ++j) {
 				const int s = s0 + c0 + j;
 				if (s < l) {
-					const double dot = (double)(int32_t)rj[j] / 65025.0 + (double)(int32_t)re[j] * inv_s255;
+					const double dot = fma((double)(int32_t)rj[j], 1.0 / 65025.0, (double)(int32_t)re[j] * inv_s255);   // no division: its slow-path call would serialise the 16 chains
 					const double d2 = xxr + ss[s] - 2.0 * dot;
-					kv[(size_t)row * l + s] = exp(-gamma * d2);
+					kv[(size_t)row * ldk + s] = exp_nonpos(-gamma * fmax(d2, 0.0));
 				}
 			}
 		}
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const do
 #define QIDX(a, b) ((a) * k - (a) * ((a) - 1) / 2 + (b) - (a))
 	const int v = blockIdx.x * PROB_WARPS + warp;
 	if (v >= n) return;
-	const double *kvv = kv + (size_t)v * m.l;
+	const double *kvv = kv + (size_t)v * m.ldk;
 
 	// pairwise decision values (svm_predict_values, src/svm.cpp:2527-2551, same summation order per pair)
 	// -> sigmoid_predict -> clamp [1e-7, 1-1e-7]
@@ -415,12 +416,12 @@ __global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *_
 	auto issue = [&](int c, int q0, int buf) {
 		double *Ks = dsm + (size_t)buf * (DEC_KS + DEC_CS), *Cs = Ks + DEC_KS;
 		const int nq = min(DEC_Q, m.nsv[c] - q0), sq = m.start[c] + q0;
-#pragma unroll
+#pragma unroll 2
 		for (int i = 0; i < DEC_V * DEC_Q / 256; i++) {
 			const int idx = tid + i * 256, vv = idx >> 5, q = idx & 31;
-			if (q < nq) cp_async8(&Ks[q * (DEC_V + 2) + vv], kv + (size_t)min(v0 + vv, n - 1) * m.l + sq + q);
+			if (q < nq) cp_async8(&Ks[q * (DEC_V + 2) + vv], kv + (size_t)min(v0 + vv, n - 1) * m.ldk + sq + q);
 		}
-#pragma unroll
+#pragma unroll 2
 		for (int i = 0; i < DEC_Q * DEC_O / 256; i++) {
 			const int idx = tid + i * 256, q = idx >> 6, o = idx & 63;
 			if (q < nq) cp_async8(&Cs[q * DEC_O + o], m.coefT + (size_t)(sq + q) * k1 + min(o0 + o, k1 - 1));
@@ -433,6 +434,9 @@ __global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *_
 	for (int i = 0; i < 4; i++)
 #pragma unroll
 		for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+	int rbo[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++) { const int o = min(o0 + to * 4 + j, k1 - 1); rbo[j] = o * k - o * (o + 1) / 2 - o - 1; }
 	int c = c_begin, q0 = 0, buf = 0;
 	if (c < c_end) issue(c, 0, 0);
 	while (c < c_end) {
@@ -455,17 +459,19 @@ __global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *_
 				for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
 		}
 		if (last_chunk) {
-			// class c is complete: first term of the pairs (c, o > c) -> R, second term of the pairs (o < c, c) -> C
+			// class c is complete: first term of the pairs (c, o > c) -> R, second term of the pairs (o < c, c) -> C.
+			// pair (a, b), a < b, sits at rb(a) + b with rb(a) = a*k - a*(a+1)/2 - a - 1: rb(c) is CTA-uniform, rb(o) a thread constant.
+			const int rbc = c * k - c * (c + 1) / 2 - c - 1;
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
 				const int v = v0 + tv * 4 + i;
+				double *Rrow = R + (size_t)v * np + rbc + 1, *Crow = C + (size_t)v * np + c;
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					const int o1 = o0 + to * 4 + j;
 					if (v < n && o1 < k1) {
-						const int o = (o1 >= c) ? o1 + 1 : o1;      // the other class of the pair
-						if (c < o) R[(size_t)v * np + (c * k - c * (c + 1) / 2 + (o - c - 1))] = acc[i][j];
-						else       C[(size_t)v * np + (o * k - o * (o + 1) / 2 + (c - o - 1))] = acc[i][j];
+						if (o1 >= c) Rrow[o1] = acc[i][j];          // o = o1 + 1 > c
+						else Crow[rbo[j]] = acc[i][j];              // o = o1 < c
 					}
 					acc[i][j] = 0.0;
 				}
@@ -475,81 +481,79 @@ __global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *_
 	}
 }
 
-// One warp per vector.  Shared memory per warp: the strict upper triangle in rho order (pair (i, j), i < j, at
-// i*k - i*(i+1)/2 + j - i - 1 =: rb(i) + j), then p and 1/Q[t][t].  The diagonal of Q lives in registers only.
-//   1. r = clamp(sigmoid((R + C - rho) * A + B))       flat over the pairs, coalesced, no index arithmetic
-//   2. Q[t][t] = sum_{j != t} r[j][t]^2 ;  Q[i][j] = -r[i][j] (1 - r[i][j]) in place
-//   3. Wu-Lin-Weng iteration (multiclass_probability, src/svm.cpp:1829-1890): Qp from scratch, convergence test, then the
-//      Gauss-Seidel sweep.  The sweep is one dependency chain of k steps; per step: one shuffle (Qp[t] from its owner),
-//      one broadcast load (1/Q[t][t]), a Newton reciprocal, and per lane three fused updates whose Q index is
-//      (j < t ? rb(j) + t : rb(t) + j) -- rb(j) is a lane constant, rb(t) warp-uniform.  diff * Q[t][t] is replaced by the
-//      numerator it came from (pQp - Qp[t]); with the reciprocals this differs from libsvm in the last bits only.
-__global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_couple(SvmDev m, const double *__restrict__ R, const double *__restrict__ C, int n, int v_out0,
-                                                                double *__restrict__ label_out, double *__restrict__ prob_out)
+// One warp per vector, two warps per CTA.  Shared memory per warp: the FULL symmetric matrix Q (row stride ks odd: a lane
+// walking its own row and 32 lanes reading one row are both conflict-free), then p and 1/Q[t][t].
+//   1. r[i][j] = clamp(sigmoid((R + C - rho) * A + B)), r[j][i] = 1 - r[i][j]    flat over the pairs, coalesced
+//   2. Q[t][t] = sum_{j != t} r[j][t]^2 (column t, libsvm's order);  Q[i][j] = Q[j][i] = -r[i][j] r[j][i] in place
+//   3. Wu-Lin-Weng iteration (multiclass_probability, src/svm.cpp:1829-1890): Qp from scratch (each lane its rows),
+//      convergence test, then the Gauss-Seidel sweep.  The sweep is one dependency chain of k steps; per step: one shuffle
+//      (Qp[t] from its owner), one broadcast load (1/Q[t][t]), a Newton reciprocal, and per lane three fused updates from
+//      row t.  diff * Q[t][t] is replaced by the numerator it came from (pQp - Qp[t]); with the reciprocals this differs
+//      from libsvm in the last bits only.
+// (The packed triangle of the previous version held twelve vectors per SM instead of six but spent 2/3 of its instructions
+//  on index selects: 41 k warp instructions per vector against ~15 k here; profiles/README.)
+constexpr int CPL_WARPS = 2;
+
+__global__ void __launch_bounds__(CPL_WARPS * 32) k_svm_couple(SvmDev m, const double *__restrict__ R, const double *__restrict__ C, int n, int v_out0,
+                                                               double *__restrict__ label_out, double *__restrict__ prob_out)
 {
 	extern __shared__ __align__(16) double dsm[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int k = m.nr_class, np = k * (k - 1) / 2, kp = (k + 7) & ~7;
-	double *Q = dsm + (size_t)warp * ((size_t)np + 2 * kp);
-	double *ps = Q + np, *iqs = ps + kp;
-	const int v = blockIdx.x * PROB_WARPS + warp;
+	const int k = m.nr_class, np = k * (k - 1) / 2, kp = (k + 7) & ~7, ks = k | 1;
+	double *Q = dsm + (size_t)warp * ((size_t)ks * k + 2 * kp);
+	double *ps = Q + (size_t)ks * k, *iqs = ps + kp;
+	const int v = blockIdx.x * CPL_WARPS + warp;
 	if (v >= n) return;
 	const double *Rv = R + (size_t)v * np, *Cv = C + (size_t)v * np;
 #pragma unroll 4
 	for (int p = lane; p < np; p += 32) {
 		const double dec = (Rv[p] + Cv[p]) - m.rho[p];
 		const double f = __dadd_rn(__dmul_rn(dec, m.probA[p]), m.probB[p]);   // sigmoid_predict, src/svm.cpp:1818-1826
-		const double e = exp(-fabs(f));
+		const double e = exp_nonpos(-fabs(f));
 		const double r1 = rcp_newton(1.0 + e);
-		const double pr = (f >= 0) ? e * r1 : r1;
-		Q[p] = fmin(fmax(pr, 1e-7), 1.0 - 1e-7);                               // src/svm.cpp:2606-2611
+		const double pr = fmin(fmax((f >= 0) ? e * r1 : r1, 1e-7), 1.0 - 1e-7);   // src/svm.cpp:2606-2611
+		const int ij = m.pair_ij[p], i = ij >> 8, j = ij & 255;
+		Q[i * ks + j] = pr;
+		Q[j * ks + i] = 1.0 - pr;
 	}
-	__syncwarp();
-
-	int tt[3], rbl[3];
+	int tt[3];
 	double qtt[3], pr_[3], qp[3];
 #pragma unroll
 	for (int sl = 0; sl < 3; sl++) {
 		const int t = lane + 32 * sl;
-		tt[sl] = min(t, k - 1);                                  // lanes past k compute on the last class and are masked out
-		rbl[sl] = tt[sl] * k - tt[sl] * (tt[sl] + 1) / 2 - tt[sl] - 1;
+		tt[sl] = min(t, k - 1);                                  // lanes past k shadow the last class and are masked out
+		if (t < k) Q[t * ks + t] = 0.0;
 		qtt[sl] = 0.0; qp[sl] = 0.0;
 		pr_[sl] = (t < k) ? 1.0 / k : 0.0;
 	}
-	{
-		int rbj = -1;
-		for (int j = 0; j < k; j++) {
-#pragma unroll
-			for (int sl = 0; sl < 3; sl++) {
-				const int t = tt[sl];
-				const double rv = Q[(j < t) ? rbj + t : rbl[sl] + max(j, t + 1)];
-				const double rjt = (j < t) ? rv : 1.0 - rv;
-				if (j != t) qtt[sl] = fma(rjt, rjt, qtt[sl]);
-			}
-			rbj += k - j - 2;
-		}
+	__syncwarp();
+	for (int j = 0; j < k; j++) {
+		const double *row = Q + j * ks;
+		const double r0 = row[tt[0]], r1 = row[tt[1]], r2 = row[tt[2]];   // the diagonal holds 0: j == t adds nothing
+		qtt[0] = fma(r0, r0, qtt[0]); qtt[1] = fma(r1, r1, qtt[1]); qtt[2] = fma(r2, r2, qtt[2]);
 	}
 	__syncwarp();
 #pragma unroll 4
-	for (int p = lane; p < np; p += 32) { const double sij = Q[p]; Q[p] = -((1.0 - sij) * sij); }
+	for (int p = lane; p < np; p += 32) {
+		const int ij = m.pair_ij[p], i = ij >> 8, j = ij & 255;
+		const double sij = Q[i * ks + j];
+		const double qv = -((1.0 - sij) * sij);
+		Q[i * ks + j] = qv;
+		Q[j * ks + i] = qv;
+	}
 #pragma unroll
-	for (int sl = 0; sl < 3; sl++) { const int t = lane + 32 * sl; if (t < k) { ps[t] = pr_[sl]; iqs[t] = 1.0 / qtt[sl]; } }
+	for (int sl = 0; sl < 3; sl++) { const int t = lane + 32 * sl; if (t < k) { Q[t * ks + t] = qtt[sl]; ps[t] = pr_[sl]; iqs[t] = 1.0 / qtt[sl]; } }
 	__syncwarp();
 
 	const int max_iter = max(100, k);
 	const double eps = 0.005 / k;
+	const double *row0 = Q + tt[0] * ks, *row1 = Q + tt[1] * ks, *row2 = Q + tt[2] * ks;
 	for (int iter = 0; iter < max_iter; iter++) {
 		double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-		{
-			int rbj = -1;
-			for (int j = 0; j < k; j++) {
-				const double pj = ps[j];
-				const double q0 = (j == tt[0]) ? qtt[0] : Q[(j < tt[0]) ? rbj + tt[0] : rbl[0] + max(j, tt[0] + 1)];
-				const double q1 = (j == tt[1]) ? qtt[1] : Q[(j < tt[1]) ? rbj + tt[1] : rbl[1] + max(j, tt[1] + 1)];
-				const double q2 = (j == tt[2]) ? qtt[2] : Q[(j < tt[2]) ? rbj + tt[2] : rbl[2] + max(j, tt[2] + 1)];
-				s0 = fma(q0, pj, s0); s1 = fma(q1, pj, s1); s2 = fma(q2, pj, s2);
-				rbj += k - j - 2;
-			}
+#pragma unroll 5
+		for (int j = 0; j < k; j++) {
+			const double pj = ps[j];
+			s0 = fma(row0[j], pj, s0); s1 = fma(row1[j], pj, s1); s2 = fma(row2[j], pj, s2);
 		}
 		qp[0] = s0; qp[1] = s1; qp[2] = s2;
 		double pQp = fma(pr_[2], s2, fma(pr_[1], s1, pr_[0] * s0));
@@ -564,23 +568,17 @@ __global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_couple(SvmDev m, const 
 #pragma unroll
 		for (int SL = 0; SL < 3; SL++) {
 			const int t_end = min(k, 32 * SL + 32);
-			int rbt = (32 * SL) * k - (32 * SL) * (32 * SL + 1) / 2 - 32 * SL - 1;
 			for (int t = 32 * SL; t < t_end; t++) {
 				const double qpt = __shfl_sync(0xFFFFFFFFu, qp[SL], t - 32 * SL);
+				const double *rowt = Q + t * ks;
+				const double q0 = rowt[tt[0]], q1 = rowt[tt[1]], q2 = rowt[tt[2]];
 				const double num = pQp - qpt;
 				const double diff = num * iqs[t];
 				const double inv = rcp_newton(1.0 + diff);
 				pQp = (pQp + diff * (num + 2.0 * qpt)) * inv * inv;
 				if (lane == t - 32 * SL) pr_[SL] += diff;
-#pragma unroll
-				for (int sl = 0; sl < 3; sl++) {
-					const int j = tt[sl];
-					const double qv = Q[(j < t) ? rbl[sl] + t : rbt + max(j, t + 1)];
-					const double qtj = (j == t) ? qtt[sl] : qv;
-					qp[sl] = fma(diff, qtj, qp[sl]) * inv;
-					pr_[sl] *= inv;
-				}
-				rbt += k - t - 2;
+				qp[0] = fma(diff, q0, qp[0]) * inv; qp[1] = fma(diff, q1, qp[1]) * inv; qp[2] = fma(diff, q2, qp[2]) * inv;
+				pr_[0] *= inv; pr_[1] *= inv; pr_[2] *= inv;
 			}
 		}
 #pragma unroll
@@ -609,7 +607,7 @@ constexpr int SVM_PASS = 32768;
 size_t svm_ws_bytes(const SvmDev &m, int n)
 {
 	const size_t c = (size_t)min(n, SVM_PASS), np = (size_t)m.nr_class * (m.nr_class - 1) / 2;
-	return sizeof(double) * c * ((size_t)m.l + 2 * np) + 1024;
+	return sizeof(double) * c * ((size_t)m.ldk + 2 * np) + 1024;
 }
 
 int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *ws, double *label, double *prob,
@@ -629,31 +627,31 @@ int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8
 	}
 	const size_t smem_tc = 16384 + 2 * 32768;
 	const size_t smem_q = (size_t)PROB_WARPS * (tri + MAXK) * sizeof(double);
-	const size_t smem_c = (size_t)PROB_WARPS * (np + 2 * (size_t)((m.nr_class + 7) & ~7)) * sizeof(double);
+	const size_t smem_c = (size_t)CPL_WARPS * ((size_t)(m.nr_class | 1) * m.nr_class + 2 * (size_t)((m.nr_class + 7) & ~7)) * sizeof(double);
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_kvalue_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_prob, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_couple, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM));
 	const int cap = min(n, SVM_PASS);
-	double *kv = ws, *R = ws + (size_t)cap * m.l, *C = R + (size_t)cap * np;
+	double *kv = ws, *R = ws + (size_t)cap * m.ldk, *C = R + (size_t)cap * np;
 	for (int v0 = 0; v0 < n; v0 += SVM_PASS) {
 		const int nc = min(SVM_PASS, n - v0);
 		if (tc && m.tc_variant != 2) {
 			if (launch_svm_kvalue_tma(m, xp, xx, n, v0, nc, kv, svm_tc_flag(tc_ws, n), st)) return -1;
 		} else if (tc) {
 			dim3 g2(TC_NPAD / TC_N, (nc + TC_M - 1) / TC_M);
-			k_svm_kvalue_tc<<<g2, 128, smem_tc, st>>>(xp + (size_t)v0 * TC_KPAD, xx + v0, nc, m.svj, m.sve, m.ss, m.l, m.gamma, m.inv_s255, kv);
+			k_svm_kvalue_tc<<<g2, 128, smem_tc, st>>>(xp + (size_t)v0 * TC_KPAD, xx + v0, nc, m.svj, m.sve, m.ss, m.l, m.ldk, m.gamma, m.inv_s255, kv);
 		} else {
 			dim3 grid((m.l + KT - 1) / KT, (nc + KT - 1) / KT);
 			if (x_u8) k_svm_kvalue<uint8_t><<<grid, 256, 0, st>>>(m, x_u8 + (size_t)v0 * m.dims, nc, kv);
 			else k_svm_kvalue<double><<<grid, 256, 0, st>>>(m, x_f64 + (size_t)v0 * m.dims, nc, kv);
 		}
 		ERT_CUDA_CHECK(cudaGetLastError());
-		if (m.coefT && !m.legacy_prob) {
+		if (m.coefT && m.pair_ij && !m.legacy_prob) {
 			dim3 g3((m.nr_class + DEC_CG - 1) / DEC_CG, (nc + DEC_V - 1) / DEC_V, (m.nr_class - 1 + DEC_O - 1) / DEC_O);
 			k_svm_decide<<<g3, 256, DEC_SMEM, st>>>(m, kv, nc, R, C);
 			ERT_CUDA_CHECK(cudaGetLastError());
-			k_svm_couple<<<(nc + PROB_WARPS - 1) / PROB_WARPS, PROB_WARPS * 32, smem_c, st>>>(m, R, C, nc, v0, label, prob);
+			k_svm_couple<<<(nc + CPL_WARPS - 1) / CPL_WARPS, CPL_WARPS * 32, smem_c, st>>>(m, R, C, nc, v0, label, prob);
 		} else {
 			k_svm_prob<<<(nc + PROB_WARPS - 1) / PROB_WARPS, PROB_WARPS * 32, smem_q, st>>>(m, kv, nc, v0, label, prob);
 		}

@@ -16,6 +16,7 @@
 // Every mbarrier wait is bounded; a wait that gives up sets *flag (the caller reports it) instead of hanging the GPU.
 #include "common.cuh"
 #include "kernels.h"
+#include "svm_math.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cstring>
@@ -56,7 +57,7 @@ __device__ __forceinline__ void g2_tma_2d(uint32_t dst, const CUtensorMap *tm, i
 
 __global__ void __launch_bounds__(g2::NT, 1) k_svm_kvalue_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmJ,
                                                              const __grid_constant__ CUtensorMap tmE, const uint32_t *__restrict__ xx, int row0, int n,
-                                                             const double *__restrict__ ss, int l, double gamma, double inv_s255,
+                                                             const double *__restrict__ ss, int l, int ldk, double gamma, double inv_s255,
                                                              double *__restrict__ kv, uint32_t *__restrict__ flag)
 {
 	using namespace g2;
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(g2::NT, 1) k_svm_kvalue_tma(const __grid_const
 			const int row = tm_ * BM + q * 32 + lane;
 			const double xxr = (row < n) ? (double)xx[row0 + row] / 65025.0 : 0.0;
 			const uint32_t tJ = tmem + buf * 256u + ((uint32_t)(q * 32) << 16), tE = tJ + 128u;
-			double *out = kv + (size_t)row * l;
+			double *out = kv + (size_t)row * ldk + tn * BN;      // ldk is a multiple of BN: whole tiles, 16-byte aligned rows
+			const double *sst = ss + tn * BN;                   // |sv|^2, padded to the tile grid
 #pragma unroll 1
 			for (int c0 = 0; c0 < BN; c0 += 16) {
 				uint32_t rj[16], re[16];
@@ -170,16 +172,17 @@ __global__ void __launch_bounds__(g2::NT, 1) k_svm_kvalue_tma(const __grid_const
 				               "=r"(re[8]), "=r"(re[9]), "=r"(re[10]), "=r"(re[11]), "=r"(re[12]), "=r"(re[13]), "=r"(re[14]), "=r"(re[15])
 				             : "r"(tE + (uint32_t)c0) : "memory");
 				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-				if (row < n && ok) {
+				// 16 independent chains, no branches: the compiler interleaves them (columns past l are computed and never read)
+				double kvv[16];
 #pragma unroll
-					for (int j = 0; j < 16; ++j) {
-						const int s = tn * BN + c0 + j;
-						if (s < l) {
-							const double dot = (double)(int32_t)rj[j] / 65025.0 + (double)(int32_t)re[j] * inv_s255;
-							const double d2 = xxr + ss[s] - 2.0 * dot;
-							out[s] = exp(-gamma * d2);
-						}
-					}
+				for (int j = 0; j < 16; ++j) {
+					const double dot = fma((double)(int32_t)rj[j], 1.0 / 65025.0, (double)(int32_t)re[j] * inv_s255);   // no division: its slow-path call would serialise the 16 chains
+					const double d2 = xxr + sst[c0 + j] - 2.0 * dot;
+					kvv[j] = exp_nonpos(-gamma * fmax(d2, 0.0));
+				}
+				if (row < n) {
+#pragma unroll
+					for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2 *>(out + c0 + j) = make_double2(kvv[j], kvv[j + 1]);
 				}
 			}
 			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -228,7 +231,7 @@ int launch_svm_kvalue_tma(const SvmDev &m, const uint8_t *xp, const uint32_t *xx
 	if (g2_make_map(&tmA, xp, (uint64_t)n_rows, g2::BM) || g2_make_map(&tmJ, m.svj, g2::NPAD, g2::BN) || g2_make_map(&tmE, m.sve, g2::NPAD, g2::BN)) return -1;
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_kvalue_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::SMEM_BYTES));
 	const int n_tiles = ((n + g2::BM - 1) / g2::BM) * ((m.l + g2::BN - 1) / g2::BN);
-	k_svm_kvalue_tma<<<min(n_tiles, sm_count), g2::NT, g2::SMEM_BYTES, st>>>(tmA, tmJ, tmE, xx, row0, n, m.ss, m.l, m.gamma, m.inv_s255, kv, flag);
+	k_svm_kvalue_tma<<<min(n_tiles, sm_count), g2::NT, g2::SMEM_BYTES, st>>>(tmA, tmJ, tmE, xx, row0, n, m.ss, m.l, m.ldk, m.gamma, m.inv_s255, kv, flag);
 	ERT_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
