@@ -384,47 +384,69 @@ __global__ void __launch_bounds__(PROB_WARPS * 32) k_svm_prob(SvmDev m, const do
 // The pairwise decision value of (i, j), i < j, is S_i[j'] + S_j[i'] - rho with S_c[o'] = sum over the support vectors s of
 // class c of coef[o'][s] * K[s]  (svm_predict_values, src/svm.cpp:2527-2551; o' = the row of sv_coef that faces the other
 // class).  Per class block that is a small matrix product [vectors x nsv_c] x [nsv_c x (k-1)]:
-//   k_svm_decide : CTA = 64 vectors x one class block, 4 x 4 outputs per thread from shared memory (coefficients from the
-//                  SV-major copy, contiguous per block).  The block of class c owns the FIRST term of the pairs (c, o > c)
-//                  and the SECOND term of the pairs (o < c, c): it writes them to two packed-triangle arrays R and C
-//                  ([vectors][k(k-1)/2]), every element exactly once -- no atomics, no zero fill.
-//   k_svm_couple : one warp per vector: dec = R + C - rho (coalesced), Platt sigmoid, clamp, Wu-Lin-Weng coupling.
+//   k_svm_decide : CTA = 64 vectors x a group of class blocks, 4 x 4 outputs per thread from shared memory (coefficients
+//                  from the SV-major copy, contiguous per block).  Output S[vector][class c][o'] -- the term of every pair
+//                  (c, other) that sums over c's support vectors -- as whole 32-byte sectors; no atomics, no zero fill.
+//   k_svm_couple : one warp per vector: dec(i, j) = S[i][j'] + S[j][i'] - rho, Platt sigmoid, clamp, Wu-Lin-Weng coupling.
 // (k_svm_prob, one warp per vector for everything, reads 2 x 2080 x ~30 coefficients per VECTOR through L2, uncoalesced;
 //  a fused 8-vectors-per-CTA variant was latency-bound at one CTA per SM: 430 us per CTA whatever the grid, profiles/README.)
 // ---------------------------------------------------------------------------------------------
 constexpr int DEC_V = 64, DEC_Q = 32, DEC_O = 64, DEC_CG = 5;
-constexpr int DEC_KS = DEC_Q * (DEC_V + 2), DEC_CS = DEC_Q * DEC_O;          // doubles per stage
+constexpr int DEC_KLD = DEC_Q + 2;                                            // row stride of the K stage (doubles): 16-byte aligned pairs, rows 4 apart on different banks
+constexpr int DEC_KS = DEC_V * DEC_KLD, DEC_CS = DEC_Q * DEC_O;               // doubles per stage
 constexpr size_t DEC_SMEM = 2 * (size_t)(DEC_KS + DEC_CS) * sizeof(double);   // two stages
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 
 // grid (class groups, vector tiles, output tiles): the CTAs of one vector tile are neighbours in launch order, so a vector's
 // kernel values (contiguous over the group's classes) and its R / C rows are touched together (L2).  A CTA walks its
 // DEC_CG classes in chunks of DEC_Q support vectors through a two-stage cp.async ring: the next chunk is in flight
-// while this one is multiplied; one barrier per chunk.
-__global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *__restrict__ kv, int n, double *__restrict__ R, double *__restrict__ C)
+// while this one is multiplied; one barrier per chunk.  Stage layout: K[vector][q] (lanes copy along q: contiguous on both
+// sides) and coef[q][output]; a thread multiplies two q at a time from 16-byte loads (4 x 4 outputs, 8 loads per 32 FMAs).
+__global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *__restrict__ kv, int n, double *__restrict__ S, int so)
 {
 	extern __shared__ __align__(16) double dsm[];
+	__shared__ int s_nsv[DEC_CG], s_start[DEC_CG];
 	const int tid = threadIdx.x, tv = tid >> 4, to = tid & 15;
-	const int k = m.nr_class, k1 = k - 1, np = k * k1 / 2;
+	const int k = m.nr_class, k1 = k - 1;
 	const int c_begin = blockIdx.x * DEC_CG, c_end = min(k, c_begin + DEC_CG), o0 = blockIdx.z * DEC_O;
 	const int v0 = blockIdx.y * DEC_V;
+	if (tid < c_end - c_begin) { s_nsv[tid] = m.nsv[c_begin + tid]; s_start[tid] = m.start[c_begin + tid]; }
+	__syncthreads();
+	const bool wide = (k1 & 1) == 0 && o0 + DEC_O <= k1;     // coefficient rows can be copied 16 bytes at a time
+	// this thread's K rows: vv = (tid >> 5) + 8 i, clamped to the last vector (rows past n are computed and dropped)
+	const double *krow = kv + (size_t)min(v0 + (tid >> 5), n - 1) * m.ldk + (tid & 31);
+	const size_t kstep = (size_t)8 * m.ldk;
+	const int vlast = n - 1 - v0 - (tid >> 5);               // rows i with 8 i > vlast are past the end
 
 	auto issue = [&](int c, int q0, int buf) {
 		double *Ks = dsm + (size_t)buf * (DEC_KS + DEC_CS), *Cs = Ks + DEC_KS;
-		const int nq = min(DEC_Q, m.nsv[c] - q0), sq = m.start[c] + q0;
-#pragma unroll 2
-		for (int i = 0; i < DEC_V * DEC_Q / 256; i++) {
-			const int idx = tid + i * 256, vv = idx >> 5, q = idx & 31;
-			if (q < nq) cp_async8(&Ks[q * (DEC_V + 2) + vv], kv + (size_t)min(v0 + vv, n - 1) * m.ldk + sq + q);
+		const int nq = min(DEC_Q, s_nsv[c - c_begin] - q0), sq = s_start[c - c_begin] + q0;
+		if ((tid & 31) < nq) {
+			double *dst = Ks + (tid >> 5) * DEC_KLD + (tid & 31);
+#pragma unroll
+			for (int i = 0; i < DEC_V / 8; i++) cp_async8(dst + i * 8 * DEC_KLD, (8 * i <= vlast ? krow + i * kstep : krow) + sq);
 		}
+		if (wide) {
+			const double *src = m.coefT + (size_t)sq * k1 + o0;
+#pragma unroll
+			for (int i = 0; i < DEC_Q * DEC_O / 512; i++) {
+				const int idx = tid + i * 256, q = idx >> 5, o2 = (idx & 31) * 2;
+				if (q < nq) cp_async16(&Cs[q * DEC_O + o2], src + (size_t)q * k1 + o2);
+			}
+		} else {
 #pragma unroll 2
-		for (int i = 0; i < DEC_Q * DEC_O / 256; i++) {
-			const int idx = tid + i * 256, q = idx >> 6, o = idx & 63;
-			if (q < nq) cp_async8(&Cs[q * DEC_O + o], m.coefT + (size_t)(sq + q) * k1 + min(o0 + o, k1 - 1));
+			for (int i = 0; i < DEC_Q * DEC_O / 256; i++) {
+				const int idx = tid + i * 256, q = idx >> 6, o = idx & 63;
+				if (q < nq) cp_async8(&Cs[q * DEC_O + o], m.coefT + (size_t)(sq + q) * k1 + min(o0 + o, k1 - 1));
+			}
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
 	};
@@ -434,47 +456,53 @@ __global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *_
 	for (int i = 0; i < 4; i++)
 #pragma unroll
 		for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-	int rbo[4];
-#pragma unroll
-	for (int j = 0; j < 4; j++) { const int o = min(o0 + to * 4 + j, k1 - 1); rbo[j] = o * k - o * (o + 1) / 2 - o - 1; }
 	int c = c_begin, q0 = 0, buf = 0;
 	if (c < c_end) issue(c, 0, 0);
 	while (c < c_end) {
-		const int ncls = m.nsv[c];
+		const int ncls = s_nsv[c - c_begin];
 		const int nq = min(DEC_Q, ncls - q0);
 		const bool last_chunk = q0 + DEC_Q >= ncls;
 		const int c_next = last_chunk ? c + 1 : c, q_next = last_chunk ? 0 : q0 + DEC_Q;
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncthreads();                                     // this chunk has landed; everybody is done with the other stage
 		if (c_next < c_end) issue(c_next, q_next, buf ^ 1);
-		const double *Ks = dsm + (size_t)buf * (DEC_KS + DEC_CS), *Cs = Ks + DEC_KS;
-#pragma unroll 4
-		for (int q = 0; q < nq; q++) {
-			const double2 a01 = *reinterpret_cast<const double2 *>(&Ks[q * (DEC_V + 2) + tv * 4]), a23 = *reinterpret_cast<const double2 *>(&Ks[q * (DEC_V + 2) + tv * 4 + 2]);
-			const double2 b01 = *reinterpret_cast<const double2 *>(&Cs[q * DEC_O + to * 4]), b23 = *reinterpret_cast<const double2 *>(&Cs[q * DEC_O + to * 4 + 2]);
-			const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+		const double *Ks = dsm + (size_t)buf * (DEC_KS + DEC_CS) + tv * 4 * DEC_KLD, *Cs = dsm + (size_t)buf * (DEC_KS + DEC_CS) + DEC_KS + to * 4;
+		int q = 0;
+#pragma unroll 2
+		for (; q + 1 < nq; q += 2) {
+			double2 a[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const double2 *>(Ks + i * DEC_KLD + q);
+			const double2 b01 = *reinterpret_cast<const double2 *>(Cs + q * DEC_O), b23 = *reinterpret_cast<const double2 *>(Cs + q * DEC_O + 2);
+			const double2 d01 = *reinterpret_cast<const double2 *>(Cs + (q + 1) * DEC_O), d23 = *reinterpret_cast<const double2 *>(Cs + (q + 1) * DEC_O + 2);
+			const double b[4] = {b01.x, b01.y, b23.x, b23.y}, d[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
 			for (int i = 0; i < 4; i++)
 #pragma unroll
-				for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+				for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i].y, d[j], fma(a[i].x, b[j], acc[i][j]));
+		}
+		if (q < nq) {
+			const double2 b01 = *reinterpret_cast<const double2 *>(Cs + q * DEC_O), b23 = *reinterpret_cast<const double2 *>(Cs + q * DEC_O + 2);
+			const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const double ai = Ks[i * DEC_KLD + q];
+#pragma unroll
+				for (int j = 0; j < 4; j++) acc[i][j] = fma(ai, b[j], acc[i][j]);
+			}
 		}
 		if (last_chunk) {
-			// class c is complete: first term of the pairs (c, o > c) -> R, second term of the pairs (o < c, c) -> C.
-			// pair (a, b), a < b, sits at rb(a) + b with rb(a) = a*k - a*(a+1)/2 - a - 1: rb(c) is CTA-uniform, rb(o) a thread constant.
-			const int rbc = c * k - c * (c + 1) / 2 - c - 1;
+			// class c is complete: its row of S (the term of every pair (c, other) that sums over c's support vectors), 32 bytes per thread and vector
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
 				const int v = v0 + tv * 4 + i;
-				double *Rrow = R + (size_t)v * np + rbc + 1, *Crow = C + (size_t)v * np + c;
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					const int o1 = o0 + to * 4 + j;
-					if (v < n && o1 < k1) {
-						if (o1 >= c) Rrow[o1] = acc[i][j];          // o = o1 + 1 > c
-						else Crow[rbo[j]] = acc[i][j];              // o = o1 < c
-					}
-					acc[i][j] = 0.0;
+				if (v < n && o0 + to * 4 < so) {
+					double2 *dst = reinterpret_cast<double2 *>(S + ((size_t)v * k + c) * so + o0 + to * 4);
+					dst[0] = make_double2(acc[i][0], acc[i][1]);
+					dst[1] = make_double2(acc[i][2], acc[i][3]);
 				}
+#pragma unroll
+				for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
 			}
 		}
 		c = c_next; q0 = q_next; buf ^= 1;
@@ -483,7 +511,8 @@ __global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *_
 
 // One warp per vector, two warps per CTA.  Shared memory per warp: the FULL symmetric matrix Q (row stride ks odd: a lane
 // walking its own row and 32 lanes reading one row are both conflict-free), then p and 1/Q[t][t].
-//   1. r[i][j] = clamp(sigmoid((R + C - rho) * A + B)), r[j][i] = 1 - r[i][j]    flat over the pairs, coalesced
+//   1. the vector's 65 x 64 decision terms S -> Q (coalesced rows); r[i][j] = clamp(sigmoid((Q[i][j] + Q[j][i] - rho) * A + B)),
+//      r[j][i] = 1 - r[i][j], flat over the pairs
 //   2. Q[t][t] = sum_{j != t} r[j][t]^2 (column t, libsvm's order);  Q[i][j] = Q[j][i] = -r[i][j] r[j][i] in place
 //   3. Wu-Lin-Weng iteration (multiclass_probability, src/svm.cpp:1829-1890): Qp from scratch (each lane its rows),
 //      convergence test, then the Gauss-Seidel sweep.  The sweep is one dependency chain of k steps; per step: one shuffle
@@ -494,7 +523,7 @@ __global__ void __launch_bounds__(256, 3) k_svm_decide(SvmDev m, const double *_
 //  on index selects: 41 k warp instructions per vector against ~15 k here; profiles/README.)
 constexpr int CPL_WARPS = 2;
 
-__global__ void __launch_bounds__(CPL_WARPS * 32) k_svm_couple(SvmDev m, const double *__restrict__ R, const double *__restrict__ C, int n, int v_out0,
+__global__ void __launch_bounds__(CPL_WARPS * 32) k_svm_couple(SvmDev m, const double *__restrict__ S, int so, int n, int v_out0,
                                                                double *__restrict__ label_out, double *__restrict__ prob_out)
 {
 	extern __shared__ __align__(16) double dsm[];
@@ -504,17 +533,37 @@ __global__ void __launch_bounds__(CPL_WARPS * 32) k_svm_couple(SvmDev m, const d
 	double *ps = Q + (size_t)ks * k, *iqs = ps + kp;
 	const int v = blockIdx.x * CPL_WARPS + warp;
 	if (v >= n) return;
-	const double *Rv = R + (size_t)v * np, *Cv = C + (size_t)v * np;
+	// S[v][c][o'] -> Q[c][o]: the two terms of pair (i, j) land at Q[i][j] and Q[j][i] (coalesced rows, one store each)
+	const double *Sv = S + (size_t)v * k * so;
+	// (eight rows = up to 24 independent loads per lane in flight: the sweep is pure latency otherwise)
+	for (int c0 = 0; c0 < k; c0 += 8) {
+		double sv_[8][3];
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+#pragma unroll
+			for (int sl = 0; sl < 3; sl++) {
+				const int c = c0 + u, o1 = lane + 32 * sl;
+				sv_[u][sl] = (c < k && o1 < k - 1) ? Sv[c * so + o1] : 0.0;
+			}
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+#pragma unroll
+			for (int sl = 0; sl < 3; sl++) {
+				const int c = c0 + u, o1 = lane + 32 * sl;
+				if (c < k && o1 < k - 1) Q[c * ks + o1 + (o1 >= c ? 1 : 0)] = sv_[u][sl];
+			}
+	}
+	__syncwarp();
 #pragma unroll 4
 	for (int p = lane; p < np; p += 32) {
-		const double dec = (Rv[p] + Cv[p]) - m.rho[p];
+		const int ij0 = m.pair_ij[p], i0 = ij0 >> 8, j0 = ij0 & 255;
+		const double dec = (Q[i0 * ks + j0] + Q[j0 * ks + i0]) - m.rho[p];
 		const double f = __dadd_rn(__dmul_rn(dec, m.probA[p]), m.probB[p]);   // sigmoid_predict, src/svm.cpp:1818-1826
 		const double e = exp_nonpos(-fabs(f));
 		const double r1 = rcp_newton(1.0 + e);
 		const double pr = fmin(fmax((f >= 0) ? e * r1 : r1, 1e-7), 1.0 - 1e-7);   // src/svm.cpp:2606-2611
-		const int ij = m.pair_ij[p], i = ij >> 8, j = ij & 255;
-		Q[i * ks + j] = pr;
-		Q[j * ks + i] = 1.0 - pr;
+		Q[i0 * ks + j0] = pr;
+		Q[j0 * ks + i0] = 1.0 - pr;
 	}
 	int tt[3];
 	double qtt[3], pr_[3], qp[3];
@@ -606,8 +655,8 @@ constexpr int SVM_PASS = 32768;
 
 size_t svm_ws_bytes(const SvmDev &m, int n)
 {
-	const size_t c = (size_t)min(n, SVM_PASS), np = (size_t)m.nr_class * (m.nr_class - 1) / 2;
-	return sizeof(double) * c * ((size_t)m.ldk + 2 * np) + 1024;
+	const size_t c = (size_t)min(n, SVM_PASS);
+	return sizeof(double) * c * ((size_t)m.ldk + (size_t)m.nr_class * (size_t)((m.nr_class + 2) & ~3)) + 1024;
 }
 
 int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8, int n, double *ws, double *label, double *prob,
@@ -615,7 +664,6 @@ int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8
 {
 	if (n <= 0) return 0;
 	if (m.nr_class > MAXK) { set_error("svm: nr_class %d > %d unsupported", m.nr_class, MAXK); return -1; }
-	const size_t np = (size_t)m.nr_class * (m.nr_class - 1) / 2;
 	const size_t tri = (size_t)m.nr_class * (m.nr_class + 1) / 2;
 	const bool tc = x_u8 && m.svj && tc_ws && m.dims <= TC_KPAD && m.l <= TC_NPAD;
 	uint8_t *xp = tc_ws;
@@ -633,7 +681,8 @@ int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_couple, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	ERT_CUDA_CHECK(cudaFuncSetAttribute(k_svm_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM));
 	const int cap = min(n, SVM_PASS);
-	double *kv = ws, *R = ws + (size_t)cap * m.ldk, *C = R + (size_t)cap * np;
+	const int so = (m.nr_class + 2) & ~3;                  // row length of S: nr_class - 1 rounded up to 4 doubles
+	double *kv = ws, *S = ws + (size_t)cap * m.ldk;
 	for (int v0 = 0; v0 < n; v0 += SVM_PASS) {
 		const int nc = min(SVM_PASS, n - v0);
 		if (tc && m.tc_variant != 2) {
@@ -649,9 +698,9 @@ int launch_svm_predict(const SvmDev &m, const double *x_f64, const uint8_t *x_u8
 		ERT_CUDA_CHECK(cudaGetLastError());
 		if (m.coefT && m.pair_ij && !m.legacy_prob) {
 			dim3 g3((m.nr_class + DEC_CG - 1) / DEC_CG, (nc + DEC_V - 1) / DEC_V, (m.nr_class - 1 + DEC_O - 1) / DEC_O);
-			k_svm_decide<<<g3, 256, DEC_SMEM, st>>>(m, kv, nc, R, C);
+			k_svm_decide<<<g3, 256, DEC_SMEM, st>>>(m, kv, nc, S, so);
 			ERT_CUDA_CHECK(cudaGetLastError());
-			k_svm_couple<<<(nc + CPL_WARPS - 1) / CPL_WARPS, CPL_WARPS * 32, smem_c, st>>>(m, R, C, nc, v0, label, prob);
+			k_svm_couple<<<(nc + CPL_WARPS - 1) / CPL_WARPS, CPL_WARPS * 32, smem_c, st>>>(m, S, so, nc, v0, label, prob);
 		} else {
 			k_svm_prob<<<(nc + PROB_WARPS - 1) / PROB_WARPS, PROB_WARPS * 32, smem_q, st>>>(m, kv, nc, v0, label, prob);
 		}

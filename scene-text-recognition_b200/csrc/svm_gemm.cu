@@ -3,13 +3,13 @@
 // u8 x s8 for the sub-1/255 residue of the model's decimals), [n x 1920] x [1920 x 1920] each, accumulated in TMEM.
 // (replaces Kernel::k_function RBF, src/svm.cpp:325-365, as called per support vector by svm_predict_values :2516-2518)
 //
-// k_svm_kvalue_tma: persistent, warp-specialised, one CTA per SM (192 threads):
+// k_svm_kvalue_tma: persistent, warp-specialised, one CTA per SM (320 threads):
 //   warp 0      TMA producer: per 128-byte K chunk three tensor-map boxes (A 128 rows, B_J and B_E 128 rows each, SWIZZLE_128B)
 //               into a 4-stage ring (48 KB per stage), mbarrier expect_tx / complete_tx
 //   warp 1      MMA issuer: per stage 4 + 4 tcgen05.mma kind::i8 (M 128, N 128, K 32), tcgen05.commit frees the stage;
 //               the two accumulators of a tile are 256 TMEM columns, double-buffered (512 columns), so the next tile's
 //               main loop runs under this tile's epilogue
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns, d^2 = |x|^2 + |sv|^2 - 2 (DJ / 255^2 + DE / (255 S)), exp in
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, 64 columns each): tcgen05.ld 32 lanes x 16 columns, d^2 = |x|^2 + |sv|^2 - 2 (DJ / 255^2 + DE / (255 S)), exp in
 //               FP64, 128-byte row segments to K
 // Tiles: 128 vectors x 128 support vectors, support-vector tile fastest, so the CTAs in flight share a few A tiles and
 // the 7.4 MB of B through L2.  Rows past n are zero-filled by TMA and never stored.
@@ -25,7 +25,7 @@ namespace ert {
 
 namespace g2 {
 constexpr int BM = 128, BN = 128, BK = 128;                 // tile; BK in bytes = one SWIZZLE_128B atom
-constexpr int STAGES = 4, NT = 192;
+constexpr int STAGES = 4, EPI_WARPS = 8, NT = 64 + EPI_WARPS * 32;
 constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + 2 * B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;     // + slack for the 1024-byte alignment SWIZZLE_128B wants
 constexpr int KPAD = 1920, NPAD = 2048;                     // same padding as svm.cu (TC_KPAD, TC_NPAD)
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(g2::NT, 1) k_svm_kvalue_tma(const __grid_const
 		}
 		for (int i = 0; i < 2; i++) {
 			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g2_smem(&bar_tfull[i])), "r"(1u) : "memory");
-			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g2_smem(&bar_tempty[i])), "r"(4u) : "memory");   // one arrival per epilogue warp
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g2_smem(&bar_tempty[i])), "r"((uint32_t)EPI_WARPS) : "memory");   // one arrival per epilogue warp
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -146,8 +146,9 @@ __global__ void __launch_bounds__(g2::NT, 1) k_svm_kvalue_tma(const __grid_const
 			if (!ok) atomicOr(flag, 2u);
 		}
 	} else {
-		// ---------------- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31 ----------------
-		const int q = warp & 3;
+		// ---------------- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31; two warps per lane quarter split the columns ----------------
+		const int q = warp & 3, half = (warp - 2) >> 2;
+		constexpr int CW = BN / (EPI_WARPS / 4);                 // columns per warp
 		bool ok = true;
 		int t = 0;
 		for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(g2::NT, 1) k_svm_kvalue_tma(const __grid_const
 			double *out = kv + (size_t)row * ldk + tn * BN;      // ldk is a multiple of BN: whole tiles, 16-byte aligned rows
 			const double *sst = ss + tn * BN;                   // |sv|^2, padded to the tile grid
 #pragma unroll 1
-			for (int c0 = 0; c0 < BN; c0 += 16) {
+			for (int c0 = half * CW; c0 < half * CW + CW; c0 += 16) {
 				uint32_t rj[16], re[16];
 				asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
 				             : "=r"(rj[0]), "=r"(rj[1]), "=r"(rj[2]), "=r"(rj[3]), "=r"(rj[4]), "=r"(rj[5]), "=r"(rj[6]), "=r"(rj[7]),
