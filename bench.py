@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--sustained-seconds", type=float, default=2.5, help="extra leg of at least this many seconds (clock record, steady-state check)")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--parity-frames", type=int, default=2, help="frames of one step checked against the oracles outside the timed region (0 = skip)")
+    ap.add_argument("--no-gather", action="store_true", help="A/B at N > 1: leave the labelled regions on their rank (no ert_gather_regions_*)")
     ap.add_argument("--contexts", type=int, default=5, help="contexts / streams used round-robin (copy/compute overlap)")
     return ap.parse_args()
 
@@ -267,7 +268,7 @@ def run_ours(a, rank, local_rank, world):
         if a.tile_config:
             c.set_tile_config(a.tile_config)
 
-    gather = edist.LibraryGather(local_rank, rank, world) if world > 1 else None
+    gather = edist.LibraryGather(local_rank, rank, world) if world > 1 and not a.no_gather else None
     stats = {"tile_ms": [], "extract_ms": [], "nms_ms": [], "classify_ms": [], "launches": 0, "d2h": 0, "regions": 0, "kept": 0, "steps": 0,
              "gathered_records": 0, "gathers": 0}
 
@@ -302,8 +303,8 @@ def run_ours(a, rank, local_rank, world):
                 ctxs[k].enqueue_host(host_batches[i % NB].data_ptr(), fpg, W, H, W * 3, upto=a.upto)
             pending[k] = True
             if gather is not None and a.upto >= 3:
-                if gather.outstanding() >= 6:
-                    take_gather(record)              # the gather enqueued six steps ago: finished long since
+                if gather.outstanding() >= 9:
+                    take_gather(record)              # the gather enqueued nine steps ago: finished long since
                 gather.enqueue(ctxs[k], my_ids)      # packs on the device, NCCL on the library's side stream; returns at once
         for j in range(NC):
             k = (n_steps + j) % NC

@@ -109,8 +109,8 @@ static NcclApi *nccl_api()
 using namespace ert;
 
 namespace {
-constexpr int DEPTH = 8;       // gathers in flight
-constexpr int LAG = 4;         // the exact-size exchange of batch s - LAG is issued when batch s is enqueued (same order on every rank)
+constexpr int DEPTH = 12;      // gathers in flight
+constexpr int LAG = 6;         // the exact-size exchange of batch s - LAG is issued when batch s is enqueued (same order on every rank)
 enum SlotState { FREE = 0, PACKED = 1, EXCHANGED = 2 };
 struct Slot {
 	int state = FREE;

@@ -319,7 +319,7 @@ def test_library_region_gather_single_rank(golden_frames):
         c.enqueue_host_array(golden_frames if s % 2 == 0 else golden_frames[::-1].copy())
         g.enqueue(c, ids)
         exp.append(edist.pack_records(c.fetch(), ids))
-        if g.outstanding() >= 6:
+        if g.outstanding() >= 9:
             rec, off, seq = g.collect()
             got = sorted((int(r["frame"]), int(r["plane"]), int(r["level"]), int(r["area"]), int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"]), int(r["label"])) for r in rec)
             assert got == sorted(tuple(int(v) for v in row) for row in exp[seq]) and list(off) == [0, len(rec)]

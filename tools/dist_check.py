@@ -36,7 +36,7 @@ def main():
         allr = [None] * world
         dist.all_gather_object(allr, mine)
         expected.append(np.concatenate(allr))
-        if g.outstanding() >= 6:
+        if g.outstanding() >= 9:
             rec, off, seq = g.collect()
             ok &= check(rec, off, expected[seq], world, rank, seq)
     while g.outstanding():
