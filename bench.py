@@ -74,6 +74,8 @@ def parse():
     ap.add_argument("--sustained-seconds", type=float, default=2.5, help="extra leg of at least this many seconds (clock record, steady-state check)")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--parity-frames", type=int, default=2, help="frames of one step checked against the oracles outside the timed region (0 = skip)")
+    ap.add_argument("--jpeg-seconds", type=float, default=2.0, help="decode-inclusive leg: JPEG bitstreams in, nvJPEG on the device (0 = skip)")
+    ap.add_argument("--jpeg-threads", type=int, default=6, help="host threads (one context each) feeding the decode-inclusive leg")
     ap.add_argument("--no-gather", action="store_true", help="A/B at N > 1: leave the labelled regions on their rank (no ert_gather_regions_*)")
     ap.add_argument("--contexts", type=int, default=5, help="contexts / streams used round-robin (copy/compute overlap)")
     return ap.parse_args()
@@ -368,6 +370,63 @@ def run_ours(a, rank, local_rank, world):
             dist.all_reduce(nt, op=dist.ReduceOp.SUM)      # ranks may fit a different number of chunks into the window
         return {"value": fpg * int(nt.item()) / (ms * 1e-3), "unit": UNIT, "seconds": ms * 1e-3, "steps_all_ranks": int(nt.item())}
 
+    def jpeg_leg(seconds, threads):
+        """decode-inclusive end to end: the same frames as JPEG bitstreams (OpenCV, quality 90, 4:2:0) handed
+        to ert_enqueue_jpeg -- nvJPEG decodes them into device memory, then the hot path; no pixel H2D copy.  One host thread per
+        context (nvJPEG's Huffman stage runs on the calling thread); wall clock between two device synchronisations."""
+        try:
+            import cv2
+        except Exception as ex:                     # no encoder for the synthetic input: say so instead of inventing a number
+            return {"unavailable": "cv2 is needed to JPEG-encode the synthetic frames: %s" % ex}
+        import threading
+        import ertext
+        frames = host_batches[0].numpy()
+        jpegs = [cv2.imencode(".jpg", f, [int(cv2.IMWRITE_JPEG_QUALITY), 90])[1].tobytes() for f in frames]
+        tctx = []
+        try:
+            for _ in range(threads):
+                c = ertext.ErText(device=local_rank)
+                c.enqueue_jpeg(jpegs, W, H, upto=a.upto); c.fetch()          # warm-up: workspace, decoder state
+                tctx.append(c)
+        except ertext.ErtError as ex:
+            for c in tctx:
+                c.close()
+            return {"unavailable": str(ex)}
+        counts = [0] * threads
+
+        def worker(k):
+            c = tctx[k]
+            t_end = time.perf_counter() + seconds
+            while time.perf_counter() < t_end:
+                c.enqueue_jpeg(jpegs, W, H, upto=a.upto)
+                r = c.fetch()
+                if r.status:
+                    raise RuntimeError("device status %d" % r.status)
+                counts[k] += 1
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(threads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        out = {"unit": UNIT, "threads_per_rank": threads, "frames_per_batch": fpg, "jpeg_bytes_per_step": int(sum(map(len, jpegs))),
+               "pixel_h2d_bytes_per_step": 0, "backend": tctx[0].jpeg_backend_name(), "decode_ms_per_batch": tctx[0].jpeg_decode_ms(),
+               "limiter": "nvJPEG's host-side Huffman stage (backend above; no hardware JPEG engine is exposed on this device: nvjpegCreateEx(HARDWARE) answers ARCH_MISMATCH)"}
+        for c in tctx:
+            c.close()
+        sec = reduce_max(sec * 1e3) * 1e-3
+        nt = torch.tensor([sum(counts)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(nt, op=dist.ReduceOp.SUM)
+        out["value"] = fpg * int(nt.item()) / sec
+        out["seconds"] = sec
+        return out
+
     def h2d_ceiling():
         """copies only: the same pinned host batches to the device, the same bytes per step per rank, nothing else"""
         bufs = [torch.empty_like(dev_batches[0]) for _ in range(NC)]
@@ -395,6 +454,7 @@ def run_ours(a, rank, local_rank, world):
     sus = sustained(a.sustained_seconds) if a.sustained_seconds > 0 else None
     clocks = sampler.stop() if rank == 0 else None
     ceiling = h2d_ceiling()
+    e2e_jpeg = jpeg_leg(a.jpeg_seconds, a.jpeg_threads) if a.jpeg_seconds > 0 and a.upto >= 3 else None
 
     # the dominant kernel timed ALONE (one context, nothing else in flight): CUDA events recorded by the library
     # around the k_tile_build2 launch on its launching stream; this is the roofline numerator's time base
@@ -433,7 +493,7 @@ def run_ours(a, rank, local_rank, world):
                    "numa": numa},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fpg * W * H * 3, "d2h_bytes_per_step": int(stats["d2h"] / max(stats["steps"], 1)),
                 "ms_per_step": ms_e2e / a.steps, "h2d_ceiling": ceiling, "fraction_of_h2d_ceiling": e2e / ceiling["frames_per_s"],
-                "rank0_brackets": brackets},
+                "rank0_brackets": brackets, "from_jpeg": e2e_jpeg},
         "gpu_launches": int(res_stats["launches"]),
         "roofline": {"bound": "hbm", "kernel": "k_tile_build2 (64x32 tile + halo per TMA box, 256 threads, 4 px per lane)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,

@@ -329,6 +329,19 @@ ERT_API int ert_gather_regions_enqueue(ert_dist *d, ert_ctx *ctx, const int32_t 
 ERT_API int ert_gather_regions_collect(ert_dist *d, const ert_gather_result **out);
 ERT_API int ert_gather_regions_outstanding(ert_dist *d);
 
+/* ---- compressed input ------------------------------------------------------ */
+/* replaces `cap >> frame` + compute_channels of video_mode (src/utils.cpp:107-113) for JPEG frames: n_frames baseline-JPEG
+ * bitstreams (host memory), each W x H, are decoded by nvJPEG straight into the context's device BGR buffer on the batch's
+ * stream; then as ert_detect_classify_device.  Collect with ert_fetch_result.  nvJPEG is opened with dlopen at first use. */
+ERT_API int ert_enqueue_jpeg(ert_ctx *ctx, const uint8_t *const *data, const size_t *sizes, int n_frames, int W, int H, int upto);
+/* the decoded pixels of the last ert_enqueue_jpeg ([n_frames][H][W][3] BGR): what parity is stated on (nvJPEG's IDCT and
+ * chroma upsampling differ from libjpeg's in the last bit) */
+ERT_API int ert_jpeg_fetch_frames(ert_ctx *ctx, uint8_t *bgr_out);
+/* backend -1 = best available (hardware engine, else GPU Huffman, else default) or an nvjpegBackend_t value; cpu_threads >= 1 */
+ERT_API int ert_set_jpeg_backend(ert_ctx *ctx, int backend, int cpu_threads);
+ERT_API const char *ert_jpeg_backend_name(ert_ctx *ctx);
+ERT_API double ert_jpeg_decode_ms(ert_ctx *ctx);
+
 /* ---- plumbing -------------------------------------------------------------------------------- */
 /* use an external CUDA stream (cudaStream_t as integer, e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */
 ERT_API int ert_set_stream(ert_ctx *ctx, uint64_t cuda_stream);

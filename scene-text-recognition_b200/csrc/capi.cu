@@ -400,6 +400,7 @@ ert_ctx *ert_create(const ert_params *params, int device)
 		cudaEventCreateWithFlags(&c->ev_post_done, cudaEventDisableTiming);
 		cudaEventCreateWithFlags(&c->ev_planes, cudaEventDisableTiming);
 		cudaEventCreateWithFlags(&c->ev_resized, cudaEventDisableTiming);
+		cudaEventCreate(&c->ev_decode[0]); cudaEventCreate(&c->ev_decode[1]);
 	}
 	build_aran_table(c);
 	if (cudaMalloc((void **)&c->d_aran_tbl, 64) != cudaSuccess || cudaMemcpy(c->d_aran_tbl, c->aran_tbl_h, 64, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -431,6 +432,8 @@ void ert_destroy(ert_ctx *c)
 	if (c->ev_post_done) cudaEventDestroy(c->ev_post_done);
 	if (c->ev_planes) cudaEventDestroy(c->ev_planes);
 	if (c->ev_resized) cudaEventDestroy(c->ev_resized);
+	for (cudaEvent_t e : c->ev_decode) if (e) cudaEventDestroy(e);
+	if (c->jpeg) { jpeg_decoder_destroy(c->jpeg); c->jpeg = nullptr; }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }

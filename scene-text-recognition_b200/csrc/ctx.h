@@ -60,6 +60,8 @@ static inline int svm_gemm_flag_check(uint8_t *tcws, int n)
 	return 0;
 }
 
+void jpeg_decoder_destroy(void *decoder);   // ingest.cu
+
 template <typename T>
 static int dev_upload(T **dptr, const std::vector<T> &v)
 {
@@ -97,6 +99,9 @@ struct ert_ctx {
 	int split_streams = 1;
 	int planes_per_frame = 6;             // BGR entry points: 6 = Y, Cr, Cb and their inverses (compute_channels); 3 = Y, Cr, Cb only
 	cudaEvent_t ev_planes = nullptr;      // the batch's source planes are complete in d_ycc (pyramid levels of other contexts wait on it)
+	cudaEvent_t ev_decode[2] = {nullptr, nullptr};   // around nvjpegDecodeBatched (ingest.cu)
+	void *jpeg = nullptr;                 // JpegDecoder (ingest.cu), created by the first ert_enqueue_jpeg
+	int jpeg_backend = -1, jpeg_cpu_threads = 4, jpeg_frames = 0, jpeg_W = 0, jpeg_H = 0;
 	cudaEvent_t ev_resized = nullptr;     // this context finished READING another context's planes (ert_enqueue_pyramid_level)
 	std::vector<cudaEvent_t> readers;     // events of contexts that still read this context's planes: the next batch waits for them
 	cudaStream_t work_stream() const { return (split_streams && post_stream) ? post_stream : stream; }

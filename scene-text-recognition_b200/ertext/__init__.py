@@ -83,6 +83,7 @@ class OcrResult:
 
 
 EXPORTS = [
+    "ert_enqueue_jpeg", "ert_jpeg_fetch_frames", "ert_set_jpeg_backend", "ert_jpeg_backend_name", "ert_jpeg_decode_ms",
     "ert_set_tile_fifo", "ert_set_nms_sequential", "ert_host_alloc", "ert_host_free", "ert_batch_done", "ert_er_track", "ert_er_track_regions", "ert_ocr_chain_run_batch", "ert_ocr_chain_run_plane", "ert_ocr_features_plane",
     "ert_abi_version", "ert_last_error", "ert_status_string", "ert_create", "ert_destroy", "ert_set_thresh_step",
     "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_config", "ert_set_node_capacity", "ert_debug_phase_cycles", "ert_set_capacity", "ert_load_cascade",
@@ -129,6 +130,11 @@ def load_library():
     L.ert_detect_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, RP]
     L.ert_detect_classify_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ert_enqueue_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ert_enqueue_jpeg.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ert_jpeg_fetch_frames.argtypes = [C.c_void_p, C.c_void_p]
+    L.ert_set_jpeg_backend.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ert_jpeg_backend_name.argtypes = [C.c_void_p]; L.ert_jpeg_backend_name.restype = C.c_char_p
+    L.ert_jpeg_decode_ms.argtypes = [C.c_void_p]; L.ert_jpeg_decode_ms.restype = C.c_double
     L.ert_fetch_result.argtypes = [C.c_void_p, RP]
     L.ert_compute_channels.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
     L.ert_planes_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, RP]
@@ -335,6 +341,31 @@ class ErText:
         self._keep = a
         f, h, w, _ = a.shape
         self._check(self.L.ert_enqueue_host(self.ctx, a.ctypes.data, f, w, h, w * 3, upto))
+
+    def enqueue_jpeg(self, jpegs, w, h, upto=STAGE_CLASSIFY):
+        """enqueue a batch of JPEG bitstreams (bytes-like, each w x h): decoded on the device by nvJPEG, no pixel H2D copy"""
+        bufs = [np.frombuffer(j, dtype=np.uint8) for j in jpegs]
+        self._keep = bufs
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+        self._jpeg_shape = (n, h, w, 3)
+        self._check(self.L.ert_enqueue_jpeg(self.ctx, ptrs, sizes, n, w, h, upto))
+
+    def jpeg_fetch_frames(self):
+        out = np.empty(self._jpeg_shape, dtype=np.uint8)
+        self._check(self.L.ert_jpeg_fetch_frames(self.ctx, out.ctypes.data))
+        return out
+
+    def set_jpeg_backend(self, backend=-1, cpu_threads=4):
+        self._check(self.L.ert_set_jpeg_backend(self.ctx, backend, cpu_threads))
+
+    def jpeg_backend_name(self):
+        r = self.L.ert_jpeg_backend_name(self.ctx)
+        return r.decode() if r else None
+
+    def jpeg_decode_ms(self):
+        return self.L.ert_jpeg_decode_ms(self.ctx)
 
     def enqueue_device(self, dev_ptr, f, w, h, stride, upto=STAGE_CLASSIFY):
         self._check(self.L.ert_detect_classify_device(self.ctx, dev_ptr, f, w, h, stride, upto))

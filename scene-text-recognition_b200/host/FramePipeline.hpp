@@ -30,6 +30,45 @@ struct FrameRegions {
 	int n_strong = 0;
 	std::vector<int32_t> tracked;          // `tracked` (all_er) as indices into cand, the reference's order
 	double batch_ms = 0;                   // device time of the batch this frame travelled in
+	// the batch's device time per module, divided by its frames: the shares video_mode adds into avg_time[0..3]
+	// (src/utils.cpp:152-157: extract, nms, classify, track) -- plus decode for compressed input
+	double extract_ms = 0, nms_ms = 0, classify_ms = 0, track_ms = 0, decode_ms = 0;
+};
+
+// video_mode's avg_time[7] (src/utils.cpp:98, 152-157, 205-211): [0] extract [1] nms [2] classify [3] track [4] grouping
+// [5] ocr [6] total wall seconds.  [0..3] are device milliseconds here (the reference's are the slowest channel's host
+// seconds), accumulated per frame; [4] and [5] are whatever the caller measures around its er_grouping / OCR step.
+struct VideoTimes {
+	double t[7] = {0, 0, 0, 0, 0, 0, 0};
+	long long frames = 0;
+	void add(const FrameRegions &f) { t[0] += f.extract_ms * 1e-3; t[1] += f.nms_ms * 1e-3; t[2] += f.classify_ms * 1e-3; t[3] += f.track_ms * 1e-3; frames++; }
+};
+
+// video_mode's outer loop (src/utils.cpp:102-211): the tracked regions of `frame_count` (2) consecutive frames are
+// accumulated (tracked_vec), the channels of frame frame_count / 2 are kept for er_ocr (channel_vec), then er_grouping /
+// er_ocr run once per group.  push() returns true when a group is complete; the caller hands `tracked` (and the middle
+// frame's index) to the reference's own er_grouping, which stays host code outside the path (out of scope).
+class FrameAccumulator {
+public:
+	explicit FrameAccumulator(int frame_count = 2) : frame_count_(frame_count < 1 ? 1 : frame_count) {}
+	bool push(FrameRegions &&f)
+	{
+		if ((int)frames_.size() == frame_count_) clear();
+		for (int32_t i : f.tracked) tracked_.push_back(f.cand[(size_t)i]);
+		if ((int)frames_.size() == frame_count_ / 2) middle_index_ = f.frame_index;
+		frames_.push_back(std::move(f));
+		return (int)frames_.size() == frame_count_;
+	}
+	const std::vector<ert_tracked> &tracked() const { return tracked_; }      // tracked_vec
+	long long middle_frame_index() const { return middle_index_; }             // the frame whose channels er_ocr reads
+	const std::vector<FrameRegions> &frames() const { return frames_; }
+	void clear() { frames_.clear(); tracked_.clear(); middle_index_ = -1; }
+
+private:
+	int frame_count_;
+	std::vector<FrameRegions> frames_;
+	std::vector<ert_tracked> tracked_;
+	long long middle_index_ = -1;
 };
 
 class FramePipeline {
@@ -67,6 +106,7 @@ public:
 	{
 		Slot &s = slots_[fill_];
 		if (s.in_flight) collect(fill_);                       // all slots busy: take the oldest batch home first
+		if (s.n > 0 && s.compressed) throw std::runtime_error("FramePipeline: raw and JPEG frames in one batch");
 		return s.staging + frame_bytes() * (size_t)s.n;
 	}
 	// ... and commits it
@@ -76,6 +116,18 @@ public:
 		if (s.n == 0) s.first_index = next_index_;
 		s.n++; next_index_++;
 		if (s.n == fpb_) submit();
+	}
+	// compressed input: one baseline-JPEG bitstream of a W x H frame.  The bitstream is kept (it is ~20x
+	// smaller than the pixels) and the whole batch is decoded on the device by nvJPEG when it is submitted: no pixel H2D copy.
+	// A batch is either all compressed or all raw.
+	void push_jpeg(const unsigned char *data, size_t size)
+	{
+		Slot &s = slots_[fill_];
+		if (s.in_flight) collect(fill_);
+		if (s.n > 0 && !s.compressed) throw std::runtime_error("FramePipeline: raw and JPEG frames in one batch");
+		s.compressed = true;
+		s.jpeg.emplace_back(data, data + size);
+		commit();
 	}
 	// submit a partially filled batch (end of stream, or latency matters more than throughput)
 	void flush() { if (slots_[fill_].n > 0 && !slots_[fill_].in_flight) submit(); }
@@ -107,6 +159,8 @@ private:
 		int n = 0;
 		bool in_flight = false;
 		long long first_index = 0;
+		bool compressed = false;
+		std::vector<std::vector<unsigned char>> jpeg;   // the batch's bitstreams (push_jpeg)
 	};
 	int W_, H_, fpb_, upto_;
 	std::vector<Slot> slots_;
@@ -121,7 +175,11 @@ private:
 	void submit()
 	{
 		Slot &s = slots_[fill_];
-		if (ert_enqueue_host(s.ctx, s.staging, s.n, W_, H_, W_ * 3, upto_)) fail("ert_enqueue_host");
+		if (s.compressed) {
+			std::vector<const uint8_t *> ptr; std::vector<size_t> len;
+			for (const auto &j : s.jpeg) { ptr.push_back(j.data()); len.push_back(j.size()); }
+			if (ert_enqueue_jpeg(s.ctx, ptr.data(), len.data(), s.n, W_, H_, upto_)) fail("ert_enqueue_jpeg");
+		} else if (ert_enqueue_host(s.ctx, s.staging, s.n, W_, H_, W_ * 3, upto_)) fail("ert_enqueue_host");
 		s.in_flight = true;
 		order_.push_back(fill_);
 		fill_ = (fill_ + 1) % slots_.size();
@@ -149,6 +207,9 @@ private:
 			FrameRegions fr;
 			fr.frame_index = s.first_index + f;
 			fr.batch_ms = r->stage_ms[5];
+			fr.extract_ms = r->stage_ms[0] / s.n; fr.nms_ms = r->stage_ms[1] / s.n; fr.classify_ms = r->stage_ms[2] / s.n;
+			fr.track_ms = t ? t->track_ms / s.n : 0.0;
+			fr.decode_ms = s.compressed ? ert_jpeg_decode_ms(s.ctx) / s.n : 0.0;
 			for (int ch = 0; ch < 6; ch++) {
 				const int p = f * 6 + ch;
 				const ert_node *nodes = r->nodes + r->node_offset[p];
@@ -166,6 +227,8 @@ private:
 		}
 		s.n = 0;
 		s.in_flight = false;
+		s.compressed = false;
+		s.jpeg.clear();
 	}
 };
 
