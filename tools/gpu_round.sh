@@ -31,7 +31,7 @@ except Exception as ex: print("bench c$c failed", ex)
 PY
 done
 fi
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${T}_launches.csv python bench.py --steps 2 --warmup 3 --contexts 1 --no-cpu-baseline --no-next-rows --sustained-seconds 0 > $O/${T}_ncu_b.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${T}_launches.csv python bench.py --steps 2 --warmup 3 --contexts 1 --no-cpu-baseline --no-next-rows --sustained-seconds 0 --jpeg-seconds 0 --parity-frames 0 > $O/${T}_ncu_b.log 2>&1
 python - <<PY
 import csv, collections, re, statistics
 try:

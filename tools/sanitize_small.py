@@ -35,5 +35,15 @@ print("track regions", ft.tracked)
 o = e.ocr_chain_run_plane(pl, [(0, 0, 120, 90), (5, 5, 60, 60), (7, 9, 3, 40), (20, 20, 40, 30)], [0.0, 0.0, 0.0, -0.5])
 print("ocr plane", o.label, o.img.sum())
 print(e.ocr_features_plane(pl, [(1, 1, 2, 2)]).feat.sum())
+# pyramid level, SVM batch with a partial tile, JPEG ingest (when an encoder is importable)
+x = np.load(os.path.join(ROOT, "tests", "golden", "ref_svm.npz"))["x_u8"]
+print("svm 24", e.svm_predict_probability(np.tile(x, (8, 1))[:150])[0][:3])
+try:
+    import cv2
+    jp = [cv2.imencode(".jpg", g[0, :160, :240])[1].tobytes()]
+    e.enqueue_jpeg(jp, 240, 160); rj = e.fetch()
+    print("jpeg", e.jpeg_backend_name(), sum(len(p.nodes) for p in rj.planes))
+except ImportError:
+    print("jpeg skipped (no cv2)")
 e.close()
 print("done")
