@@ -6,7 +6,7 @@
  * reproduces the reference's arithmetic AND traversal order, so node sets, child order, pool
  * order, histograms and scores are comparable bit for bit.
  *
- * Parity pin: tests/test_oracle_port_vs_ref.py checks every function here against
+ * Parity pin: tests/test_oracle.py and tests/test_port_next.py check every function here against
  * oracle/_ref/libref_oracle.so (the reference's own code, built by oracle/build_ref.sh) on the
  * ICDAR fixtures and on synthetic planes, and tests/golden/ holds the outputs of that
  * reference build for the GPU box (where /root/reference does not exist).

@@ -62,7 +62,7 @@ int index_of(const RefTree *t, const ER *e)
 
 // BGR -> the six planes of ERFilter::compute_channels (src/ER.cpp:114-128).  cvtColor is not
 // available in the shim; this is the integer restatement of OpenCV's 8-bit BGR2YCrCb
-// (pinned against cv2 in tests/test_cvshim_vs_cv2.py).
+// (pinned against cv2 in tests/test_oracle.py).
 void channels_from_bgr(const uchar *bgr, int w, int h, int stride, std::vector<cv::Mat> &ch)
 {
 	ch.clear();

@@ -1,7 +1,8 @@
 // er_tile.cu -- k_tile_build2: the tile-local component-tree build of er_tree_extract (src/ER.cpp:240-413),
-// second generation.  Same contract as k_tile_build in er_extract.cu (same global outputs: par / attr / node_list /
-// seam records), rebuilt around four ideas measured against the round-1 kernel (issue-slot bound, ~25 warp
-// instructions per pixel, 130 SASS instructions per iteration of its union loop):
+// second generation.  Global outputs: nodes that leave the tile get a dense SLOT in the plane's par / attr / node_key arrays,
+// seam records name the (level, slot) that stands for every side pixel.  Rebuilt around four ideas measured against the
+// round-1 kernel (k_tile_build: issue-slot bound, ~25 warp instructions per pixel, 130 SASS instructions per iteration
+// of its union loop):
 //   * the 64x32 tile arrives WITH its one-pixel halo as ONE tensor-map TMA box (cp.async.bulk.tensor.3d, SASS UTMALDG;
 //     96x34 bytes, out-of-plane bytes zero-filled by the TMA unit) instead of 32 row copies + ~190 scalar halo loads;
 //   * the per-pixel sweeps (quantise, horizontal runs, edge list) are vectorised: one lane owns 4 consecutive pixels

@@ -3,13 +3,16 @@
 //  :2501-2575, Kernel::k_function RBF :325-365, sigmoid_predict :1818-1826, multiclass_probability
 //  :1829-1890) for a BATCH of dense feature vectors (the reference scores one ER at a time).
 //
-//   k_svm_kvalue : K[n][s] = exp(-gamma * sum_d (x[n][d] - sv[s][d])^2) as a register-tiled FP64
-//                  "distance GEMM" (64x64 output tile per CTA, 4x4 per thread, operands staged in
-//                  shared memory).  FP64 keeps the parsed support-vector values exact: the audit path and the path for
-//                  arbitrary double inputs; u8 features take k_svm_kvalue_tc below (tcgen05, two integer GEMMs).
-//   k_svm_prob   : one warp per vector: 2080 pairwise decision values (per-pair order of the reference),
-//                  Platt sigmoid, clamp, and the Wu-Lin-Weng coupling iteration with p / Qp in registers,
-//                  shuffle broadcasts and one reciprocal per Gauss-Seidel step (last-bit differences only).
+//   k_svm_prep_x     : u8 features padded to 1920 bytes per row + their squared norms
+//   k_svm_kvalue_tma : (svm_gemm.cu) K[n][s] = exp(-gamma |x_n - sv_s|^2) for u8 features as two integer GEMMs on the tensor
+//                      cores (tcgen05 kind::i8, TMA ring, TMEM double buffer) with an FP64 epilogue; k_svm_kvalue_tc below is the
+//                      round-1 single-stage form of the same GEMMs (A-B, bit-identical results)
+//   k_svm_kvalue     : the same matrix as a register-tiled FP64 "distance GEMM" on CUDA cores: arbitrary double inputs, and
+//                      the audit path (parsed support-vector values enter as they are: ~1e-13 against the reference)
+//   k_svm_decide     : per class block [vectors x nsv_c] x [nsv_c x 64] -> S[vector][class][other] (cp.async ring)
+//   k_svm_couple     : one warp per vector: decision values from S, Platt sigmoid, clamp, Wu-Lin-Weng coupling on the full
+//                      symmetric matrix in shared memory (last-bit differences from libsvm only)
+//   k_svm_prob       : round-1 form of the last two (one warp per vector for everything), kept for A-B (ert_set_svm_legacy_prob)
 #include "common.cuh"
 #include "kernels.h"
 #include "svm_math.cuh"
