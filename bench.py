@@ -76,6 +76,7 @@ def parse():
     ap.add_argument("--parity-frames", type=int, default=2, help="frames of one step checked against the oracles outside the timed region (0 = skip)")
     ap.add_argument("--jpeg-seconds", type=float, default=2.0, help="decode-inclusive leg: JPEG bitstreams in, nvJPEG on the device (0 = skip)")
     ap.add_argument("--jpeg-threads", type=int, default=6, help="host threads (one context each) feeding the decode-inclusive leg")
+    ap.add_argument("--post-footprint", type=int, default=-1, help="A/B: CTAs per SM for the post-tile kernels (ert_set_post_footprint; -1 = library default)")
     ap.add_argument("--no-gather", action="store_true", help="A/B at N > 1: leave the labelled regions on their rank (no ert_gather_regions_*)")
     ap.add_argument("--contexts", type=int, default=5, help="contexts / streams used round-robin (copy/compute overlap)")
     return ap.parse_args()
@@ -269,6 +270,8 @@ def run_ours(a, rank, local_rank, world):
             c.set_seam_list(False)
         if a.tile_config:
             c.set_tile_config(a.tile_config)
+        if a.post_footprint >= 0:
+            c.set_post_footprint(a.post_footprint)
 
     gather = edist.LibraryGather(local_rank, rank, world) if world > 1 and not a.no_gather else None
     stats = {"tile_ms": [], "extract_ms": [], "nms_ms": [], "classify_ms": [], "launches": 0, "d2h": 0, "regions": 0, "kept": 0, "steps": 0,

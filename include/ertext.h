@@ -159,6 +159,9 @@ ERT_API int ert_set_stream_split(ert_ctx *ctx, int on);
 ERT_API int ert_set_tile_config(ert_ctx *ctx, int id);
 /* A-B: 1 (default) = seams through k_seam_link_list (edges compacted per CTA, warp-converged drain); 0 = k_seam_link_rec */
 ERT_API int ert_set_seam_list(ert_ctx *ctx, int on);
+/* scheduling: CTAs per SM the post-tile kernels (seam / fold / refit / emit) may occupy (default 2; 0 = no cap).  They run at
+ * high priority under the NEXT batch's tile kernel; uncapped they fill the SMs first and the two run one after the other. */
+ERT_API int ert_set_post_footprint(ert_ctx *ctx, int ctas_per_sm);
 /* debug: per-phase cycle sums (clock64, thread 0 of every CTA) of the tile-build kernel since the last call */
 ERT_API int ert_debug_phase_cycles(ert_ctx *ctx, int enable, unsigned long long *out16);
 /* capacity hints (defaults: 16384 kept nodes and 2048 pooled regions per plane) */

@@ -177,6 +177,7 @@ int ensure_workspace(ert_ctx *c, int n_planes, int W, int H)
 	c->wk.node_blocks = 32;
 	c->wk.tile_cfg = c->tile_cfg;
 	c->wk.seam_list = c->seam_list;
+	c->wk.post_ctas = c->post_ctas_per_sm * c->sm_count;
 	c->wk.node_cap = (int)node_cap;
 	c->wk.prof = c->d_prof;
 	c->nms_stride = nms_scratch_stride(c->kept_cap);
@@ -391,6 +392,7 @@ ert_ctx *ert_create(const ert_params *params, int device)
 	else { c->prm.thresh_step = 8; c->prm.min_area = 120; c->prm.max_area = 900000; c->prm.stability_t = 2; c->prm.overlap_coef = 0.7; c->prm.min_ocr_prob = 0.15; }
 	if (c->prm.thresh_step < 5 || c->prm.thresh_step > 255) { set_error("thresh_step %d unsupported (5..255)", c->prm.thresh_step); delete c; return nullptr; }
 	c->device = device;
+	if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count < 1) c->sm_count = 148;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); delete c; return nullptr; }
 	for (int i = 0; i < 12; i++) cudaEventCreate(&c->ev[i]);
 	{
@@ -468,6 +470,13 @@ int ert_debug_phase_cycles(ert_ctx *c, int enable, unsigned long long *out16)
 	c->wk.prof = c->d_prof;
 	return 0;
 }
+int ert_set_post_footprint(ert_ctx *c, int ctas_per_sm)
+{
+	if (!c || ctas_per_sm < 0 || ctas_per_sm > 32) { set_error("bad arguments"); return -1; }
+	c->post_ctas_per_sm = ctas_per_sm; c->wk.post_ctas = ctas_per_sm * c->sm_count;
+	return 0;
+}
+
 int ert_set_seam_list(ert_ctx *c, int on) { c->seam_list = on ? 1 : 0; c->wk.seam_list = c->seam_list; return 0; }
 int ert_set_tile_config(ert_ctx *c, int id)
 {

@@ -171,9 +171,13 @@ __global__ void __launch_bounds__(SEAM_NT) k_seam_link_list(ExtractParams P, con
 	const int RINGW = 2 * (TW + TH);
 	const int nvs = (P.W - 1) / TW, nhs = (P.H - 1) / TH;
 	const long long nv = (long long)nvs * P.H, nh = (long long)nhs * P.W;
-	const long long e0 = (long long)blockIdx.x * SEAM_CHUNK;
 	const uint32_t *recP = ring_rec + (size_t)plane * tiles_per_plane * RINGW;
 	uint32_t *parP = par_g + (size_t)plane * P.node_cap;
+	bool guard_hit = false;
+	// a CTA walks several chunks when the launcher caps the grid (the kernel runs under another batch's tile kernel and must
+	// not take the SMs away from it: launch_extract)
+	for (long long e0 = (long long)blockIdx.x * SEAM_CHUNK; e0 < nv + nh; e0 += (long long)gridDim.x * SEAM_CHUNK) {
+	__syncthreads();
 	if (tid == 0) { s_n = 0; s_cursor = 0; }
 	__syncthreads();
 	for (int k = tid; k < SEAM_CHUNK; k += SEAM_NT) {
@@ -236,7 +240,9 @@ __global__ void __launch_bounds__(SEAM_NT) k_seam_link_list(ExtractParams P, con
 			} else if (ra && rb) a = b = 0;
 		}
 	}
-	if (a != b) atomicOr(status, ERR_LOOP_GUARD);
+	guard_hit |= (a != b);
+	}
+	if (guard_hit) atomicOr(status, ERR_LOOP_GUARD);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -466,7 +472,9 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 		if (edges > 0) {
 			const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
 			if (wk.seam_list) {
-				dim3 g2((unsigned)((edges + SEAM_CHUNK - 1) / SEAM_CHUNK), P.n_planes);
+				unsigned gx = (unsigned)((edges + SEAM_CHUNK - 1) / SEAM_CHUNK);
+				if (wk.post_ctas > 0) gx = std::min(gx, (unsigned)std::max(1, wk.post_ctas / P.n_planes));
+				dim3 g2(gx, P.n_planes);
 				k_seam_link_list<<<g2, SEAM_NT, 0, st>>>(P, wk.ring_rec, wk.par, wk.status, TILE_W, TILE_H, tiles_x, tiles_x * tiles_y);
 			} else {
 				dim3 grid((unsigned)((edges + 255) / 256), P.n_planes);
@@ -476,7 +484,9 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 		}
 	}
 	{
-		dim3 grid(wk.node_blocks, P.n_planes);
+		int nb = wk.node_blocks;
+		if (wk.post_ctas > 0) nb = std::min(nb, std::max(1, wk.post_ctas / P.n_planes));
+		dim3 grid(nb, P.n_planes);
 		k_fold<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_key, wk.node_count);
 		ERT_CUDA_CHECK(cudaGetLastError());
 		k_refit<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_count);

@@ -20,6 +20,7 @@ struct ExtractWork {
 	uint32_t *kept_count;   // [n_planes]
 	uint32_t *status;       // [1]
 	int node_blocks;        // grid.x of the node-list kernels
+	int post_ctas;          // CTAs the post-tile kernels (seam / fold / refit / emit) may put on the device at once; 0 = no cap
 	int tile_cfg;           // index into the tile configuration table
 	unsigned long long *prof;   // optional [16] per-phase cycle sums of k_tile_build (debug)
 	uint32_t *ring_rec;     // [n_planes][tiles][2*(TW+TH)] root keys on the tile sides (seam records)

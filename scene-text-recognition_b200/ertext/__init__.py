@@ -93,7 +93,7 @@ EXPORTS = [
     "ert_svm_predict_probability_batch_u8", "ert_set_stream", "ert_get_stream", "ert_last_launch_count",
     "ert_bench_cascade_u8", "ert_bench_svm_u8",
     "ert_set_params", "ert_set_cascade", "ert_cascade_stage_info", "ert_svm_total_sv", "ert_svm_labels", "ert_svm_gamma", "ert_calc_lbp",
-    "ert_er_track_regions_ycc", "ert_set_stream_split", "ert_set_seam_list", "ert_enqueue_pyramid_level", "ert_set_planes_per_frame", "ert_set_svm_legacy_prob",
+    "ert_er_track_regions_ycc", "ert_set_stream_split", "ert_set_seam_list", "ert_set_post_footprint", "ert_enqueue_pyramid_level", "ert_set_planes_per_frame", "ert_set_svm_legacy_prob",
     "ert_dist_unique_id", "ert_dist_create", "ert_dist_destroy", "ert_gather_regions_enqueue", "ert_gather_regions_collect", "ert_gather_regions_outstanding",
 ]
 
@@ -114,7 +114,7 @@ def load_library():
     L.ert_create.restype = C.c_void_p
     L.ert_create.argtypes = [C.POINTER(ErtParams), C.c_int]
     L.ert_destroy.argtypes = [C.c_void_p]
-    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_config", "ert_set_node_capacity", "ert_set_tile_fifo", "ert_set_nms_sequential", "ert_set_stream_split", "ert_set_seam_list"):
+    for f in ("ert_set_thresh_step", "ert_set_min_area", "ert_set_return_hist", "ert_set_tile_config", "ert_set_node_capacity", "ert_set_tile_fifo", "ert_set_nms_sequential", "ert_set_stream_split", "ert_set_seam_list", "ert_set_post_footprint"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_int]
     L.ert_set_capacity.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ert_enqueue_pyramid_level.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -265,6 +265,9 @@ class ErText:
     def enqueue_pyramid_level(self, src, div, upto=STAGE_CLASSIFY):
         """this context <- the planes of `src`'s batch in flight, resized by 1/div on the device; collect with fetch()"""
         self._check(self.L.ert_enqueue_pyramid_level(self.ctx, src.ctx, int(div), upto))
+
+    def set_post_footprint(self, ctas_per_sm):
+        self._check(self.L.ert_set_post_footprint(self.ctx, int(ctas_per_sm)))
 
     def set_seam_list(self, on):
         self._check(self.L.ert_set_seam_list(self.ctx, int(on)))
