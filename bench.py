@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the er_track / chain_run leg (SURVEY 8f rows, outside the timed region)")
-    ap.add_argument("--no-tile-fifo", action="store_true", help="A/B: do not chain the tile kernels of the contexts in submission order")
+    ap.add_argument("--tile-fifo", action="store_true", help="A/B: chain the tile kernels of the contexts in submission order (round-1 default)")
     ap.add_argument("--no-stream-split", action="store_true", help="A/B: run every stage of a batch on ONE stream (no high-priority post stream)")
     ap.add_argument("--no-seam-list", action="store_true", help="A/B: the round-1 seam kernel (one thread per seam position)")
     ap.add_argument("--tile-config", type=int, default=0, help="A/B: variant of the tile kernel (ert_set_tile_config)")
@@ -262,8 +262,8 @@ def run_ours(a, rank, local_rank, world):
     streams = [torch.cuda.Stream(device=dev) for _ in range(NC)]
     for c, s in zip(ctxs, streams):
         c.set_stream(s.cuda_stream)
-        if a.no_tile_fifo:
-            c.set_tile_fifo(False)
+        if a.tile_fifo:
+            c.set_tile_fifo(True)
         if a.no_stream_split:
             c.set_stream_split(False)
         if a.no_seam_list:

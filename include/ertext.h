@@ -146,8 +146,9 @@ ERT_API int ert_set_return_hist(ert_ctx *ctx, int on);
 /* audit / A-B: 1 = non_maximum_supression's walk on ONE thread per plane, literally as the reference orders it;
  * 0 (default) = the level-parallel statement of the same result (er_nms.cu).  Pools are identical either way. */
 ERT_API int ert_set_nms_sequential(ert_ctx *ctx, int on);
-/* scheduling: 1 (default) = the tile-build kernels of all contexts on a device run in submission order (an event
- * chain); keeps the oldest batch in flight from being starved when several contexts are used round-robin */
+/* scheduling: 1 = the tile-build kernels of all contexts on a device run in submission order (an event chain: the oldest
+ * batch in flight is never starved; round-1 default); 0 (default) = unchained: with the post-tile kernels capped
+ * (ert_set_post_footprint) the tile kernels of neighbouring batches fill each other's tails, +3 % throughput */
 ERT_API int ert_set_tile_fifo(ert_ctx *ctx, int on);
 /* scheduling: 1 (default) = the stages after the tile-build kernel (seams, fold, refit, NMS, classify, result compaction,
  * er_track) run on a second, highest-priority stream of the context and are joined back into the context's stream:
@@ -159,7 +160,7 @@ ERT_API int ert_set_stream_split(ert_ctx *ctx, int on);
 ERT_API int ert_set_tile_config(ert_ctx *ctx, int id);
 /* A-B: 1 (default) = seams through k_seam_link_list (edges compacted per CTA, warp-converged drain); 0 = k_seam_link_rec */
 ERT_API int ert_set_seam_list(ert_ctx *ctx, int on);
-/* scheduling: CTAs per SM the post-tile kernels (seam / fold / refit / emit) may occupy (default 2; 0 = no cap).  They run at
+/* scheduling: CTAs per SM the post-tile kernels (seam / fold / refit / emit) may occupy (default 1, applied to batches of more than 12 planes; 0 = no cap).  They run at
  * high priority under the NEXT batch's tile kernel; uncapped they fill the SMs first and the two run one after the other. */
 ERT_API int ert_set_post_footprint(ert_ctx *ctx, int ctas_per_sm);
 /* debug: per-phase cycle sums (clock64, thread 0 of every CTA) of the tile-build kernel since the last call */

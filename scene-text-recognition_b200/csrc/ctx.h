@@ -107,10 +107,11 @@ struct ert_ctx {
 	cudaStream_t work_stream() const { return (split_streams && post_stream) ? post_stream : stream; }
 	cudaEvent_t ev[12];
 	int nms_sequential = 0;  // 1: run the reference's walk on one thread per plane (audit / A-B) instead of the level-parallel form
-	int tile_fifo = 1;       // chain the tile kernels of all contexts on the device in submission order
+	int tile_fifo = 0;       // 1: chain the tile kernels of all contexts on the device in submission order (round-1 default; with the
+	                         // post-tile kernels capped, unchained tile kernels fill each other's tails: 4 619 -> 4 760 frames/s)
 	int tile_cfg = 0;
 	int sm_count = 148;
-	int post_ctas_per_sm = 2; // footprint of the post-tile kernels: they run at high priority under the next tile kernel and must leave its CTAs room
+	int post_ctas_per_sm = 1; // footprint of the post-tile kernels: they run at high priority under the next tile kernel and must leave its CTAs room
 	int seam_list = 1;       // seam kernel: compacted edge lists (1) or one thread per seam position (0, round 1)
 	int return_hist = 0;
 	int kept_cap = 16384, pool_cap = 2048;

@@ -473,7 +473,7 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 			const int tiles_x = (P.W + TILE_W - 1) / TILE_W, tiles_y = (P.H + TILE_H - 1) / TILE_H;
 			if (wk.seam_list) {
 				unsigned gx = (unsigned)((edges + SEAM_CHUNK - 1) / SEAM_CHUNK);
-				if (wk.post_ctas > 0) gx = std::min(gx, (unsigned)std::max(1, wk.post_ctas / P.n_planes));
+				if (wk.post_ctas > 0 && P.n_planes > 12) gx = std::min(gx, (unsigned)std::max(1, wk.post_ctas / P.n_planes));   // small batches are latency-oriented: no cap
 				dim3 g2(gx, P.n_planes);
 				k_seam_link_list<<<g2, SEAM_NT, 0, st>>>(P, wk.ring_rec, wk.par, wk.status, TILE_W, TILE_H, tiles_x, tiles_x * tiles_y);
 			} else {
@@ -485,7 +485,7 @@ int launch_extract(const ExtractParams &P, const PlaneSrc *d_planes, ExtractWork
 	}
 	{
 		int nb = wk.node_blocks;
-		if (wk.post_ctas > 0) nb = std::min(nb, std::max(1, wk.post_ctas / P.n_planes));
+		if (wk.post_ctas > 0 && P.n_planes > 12) nb = std::min(nb, std::max(1, wk.post_ctas / P.n_planes));
 		dim3 grid(nb, P.n_planes);
 		k_fold<<<grid, 256, 0, st>>>(P, wk.par, wk.attr, wk.node_key, wk.node_count);
 		ERT_CUDA_CHECK(cudaGetLastError());

@@ -187,7 +187,7 @@ private:
 
 	void collect(size_t k)
 	{
-		// batches complete in submission order (every context has its own stream, the tile kernels are chained FIFO)
+		// batches are taken home in submission order (a later batch may finish first; its result waits in its context)
 		while (!order_.empty()) {
 			const size_t j = order_.front();
 			order_.pop_front();
