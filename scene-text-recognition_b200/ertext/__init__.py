@@ -206,6 +206,7 @@ class ErText:
     def __init__(self, device=0, thresh_step=8, min_area=120, max_area=900000, stability_t=2, overlap_coef=0.7,
                  min_ocr_prob=0.15, load_cascades=True, load_svm=False):
         self.L = load_library()
+        self._pinned = []
         prm = ErtParams(thresh_step, min_area, max_area, stability_t, overlap_coef, min_ocr_prob)
         self.ctx = self.L.ert_create(C.byref(prm), device)
         if not self.ctx:
@@ -225,6 +226,9 @@ class ErText:
         if getattr(self, "ctx", None):
             self.L.ert_destroy(self.ctx)
             self.ctx = None
+        for p in getattr(self, "_pinned", []):
+            self.L.ert_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -438,21 +442,33 @@ class ErText:
         self._check(self.L.ert_cascade_predict_batch(self.ctx, which, _ptr(fv, _f64p), n, d, _ptr(out, _f64p)))
         return out
 
-    def cascade_classify_u8(self, hist):
+    def pinned_array(self, shape, dtype):
+        """numpy array over page-locked host memory (ert_host_alloc); freed with the object"""
+        shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.L.ert_host_alloc(max(nbytes, 1))
+        if not p:
+            raise ErtError("ert_host_alloc(%d) failed: %s" % (nbytes, self.L.ert_last_error().decode()))
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned.append(p)
+        return arr
+
+    def cascade_classify_u8(self, hist, out=None):
         hist = np.ascontiguousarray(hist, dtype=np.uint8)
         n = hist.shape[0]
-        label = np.zeros(n, np.int32); ss = np.zeros(n); ws = np.zeros(n)
+        label, ss, ws = out if out is not None else (np.zeros(n, np.int32), np.zeros(n), np.zeros(n))
         self._check(self.L.ert_cascade_classify_u8(self.ctx, _ptr(hist, _u8p), n, _ptr(label, _i32p), _ptr(ss, _f64p), _ptr(ws, _f64p)))
         return label, ss, ws
 
-    def svm_predict_probability(self, x):
+    def svm_predict_probability(self, x, out=None):
         k = self.L.ert_svm_nr_class(self.ctx)
         if k < 0:
             raise ErtError("svm model is not loaded")
         if x.dtype == np.uint8:
             x = np.ascontiguousarray(x)
             n = x.shape[0]
-            label = np.zeros(n); prob = np.zeros((n, k))
+            label, prob = out if out is not None else (np.zeros(n), np.zeros((n, k)))
             self._check(self.L.ert_svm_predict_probability_batch_u8(self.ctx, _ptr(x, _u8p), n, _ptr(label, _f64p), _ptr(prob, _f64p)))
         else:
             x = np.ascontiguousarray(x, dtype=np.float64)
