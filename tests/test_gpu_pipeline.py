@@ -444,6 +444,26 @@ def test_batch_equals_frame_by_frame_and_all_tile_shapes_agree(ert):
         ert.set_tile_config(0)
 
 
+def test_scheduling_knobs_do_not_change_results(ert):
+    """ert_set_post_footprint (grid caps of the post-tile kernels: a seam CTA then walks several chunks, the node kernels stride
+    further), ert_set_tile_fifo, ert_set_stream_split and ert_set_seam_list are scheduling / work-distribution choices: a
+    3-frame 1080p batch (18 planes, above the 12-plane threshold of the cap) gives byte-identical results under all of them."""
+    from ertext import synth
+    pytest.importorskip("cv2")
+    frames = synth.s_text_batch(910, 3)
+    base = ert.detect_classify(frames)
+    assert base.status == 0
+    sig = [(p.nodes.tobytes(), p.pool.tobytes(), p.label.tobytes()) for p in base.planes]
+    try:
+        for fp, fifo, split, seam in ((0, 0, 1, 1), (1, 1, 1, 1), (3, 0, 0, 1), (32, 1, 0, 0), (1, 0, 1, 0)):
+            ert.set_post_footprint(fp); ert.set_tile_fifo(fifo); ert.set_stream_split(split); ert.set_seam_list(seam)
+            r = ert.detect_classify(frames)
+            assert r.status == 0
+            assert [(p.nodes.tobytes(), p.pool.tobytes(), p.label.tobytes()) for p in r.planes] == sig, (fp, fifo, split, seam)
+    finally:
+        ert.set_post_footprint(1); ert.set_tile_fifo(0); ert.set_stream_split(1); ert.set_seam_list(1)
+
+
 def test_cpp_frame_pipeline_streams_frames_in_order(ert, golden_frames, tmp_path):
     """host/FramePipeline.hpp (the C++ streaming runtime: pinned staging, batches, several contexts round-robin) returns
     per-frame regions in push order, identical to one-shot calls through the binding -- incl. a partial last batch."""
