@@ -64,6 +64,7 @@ struct NcclApi {
 	void *h = nullptr;
 	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
 	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr;   // optional (NCCL >= 2.14)
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -86,6 +87,7 @@ static NcclApi *nccl_api()
 #define ERT_NCCL_SYM(field, name) *(void **)(&api.field) = dlsym(h, name); if (!api.field) { set_error("libnccl.so.2 lacks %s", name); return nullptr; }
 	ERT_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
 	ERT_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+	*(void **)(&api.CommInitRankConfig) = dlsym(h, "ncclCommInitRankConfig");
 	ERT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
 	ERT_NCCL_SYM(AllGather, "ncclAllGather")
 	ERT_NCCL_SYM(Send, "ncclSend")
@@ -208,7 +210,16 @@ ert_dist *ert_dist_create(int device, int rank, int world, const void *id128, in
 		if (!api) { ert_dist_destroy(d); return nullptr; }
 		ncclUniqueId id;
 		memcpy(&id, id128, sizeof id);
-		const ncclResult_t r = api->CommInitRank(&d->comm, world, id, rank);
+		// the payload is a few KB per step: one CTA per NCCL kernel is plenty, and every CTA more is one that spins on an SM the
+		// tile kernel wants while the peer is a step behind
+		ncclResult_t r = ncclInternalError;
+		if (api->CommInitRankConfig) {
+			ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+			cfg.minCTAs = 1; cfg.maxCTAs = 1;
+			r = api->CommInitRankConfig(&d->comm, world, id, rank, &cfg);
+			if (r != ncclSuccess) d->comm = nullptr;
+		}
+		if (r != ncclSuccess) r = api->CommInitRank(&d->comm, world, id, rank);
 		if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", api->GetErrorString(r)); d->comm = nullptr; ert_dist_destroy(d); return nullptr; }
 	}
 	return d;
