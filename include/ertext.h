@@ -129,7 +129,7 @@ typedef struct {
 	double ocr_ms;          /* device time, features + SVM (CUDA events) */
 } ert_ocr_result;
 
-ERT_API int ert_abi_version(void);
+ERT_API int ert_abi_version(void);   /* 2 since ert_result carries plane_order_sensitive (round 2) */
 ERT_API const char *ert_last_error(void);
 ERT_API const char *ert_status_string(uint32_t status);
 

@@ -367,7 +367,7 @@ void build_aran_table(ert_ctx *c)
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
-int ert_abi_version(void) { return 1; }
+int ert_abi_version(void) { return 2; }   // 2: ert_result grew (plane_order_sensitive), round-2 entry points
 const char *ert_last_error(void) { return g_err; }
 
 const char *ert_status_string(uint32_t s)

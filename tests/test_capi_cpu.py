@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert sorted(names) == sorted(ertext.EXPORTS)
-    assert L.ert_abi_version() == 1
+    assert L.ert_abi_version() == 2
 
 
 def test_no_cpu_fallback():
