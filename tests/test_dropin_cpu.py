@@ -72,3 +72,24 @@ def test_dropin_defines_the_reference_signatures():
                 "vector<double> ERFilter::make_LBP_hist(Mat input, const int N, const int normalize_size)", "Mat ERFilter::calc_LBP(Mat input, const int size)",
                 "double CascadeBoost::predict(vector<double> fv)"):
         assert sig in txt, sig
+
+
+def test_frame_accumulator_and_video_times_host_logic(tmp_path):
+    """host/FramePipeline.hpp: FrameAccumulator = video_mode's tracked_vec over frame_count = 2 frames and the middle frame
+    for er_ocr (src/utils.cpp:96-144); VideoTimes = avg_time[0..3].  Host logic only, no device call."""
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    PKG = os.path.join(ROOT, "scene-text-recognition_b200")
+    exe = str(tmp_path / "acc")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", os.path.join(ROOT, "tests", "cpp", "accumulator_cpu.cpp"), "-o", exe,
+                           "-L", PKG, "-l:libertext.so", "-Wl,-rpath," + PKG])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == "push 0 ready 0 frames 1 tracked 1002 1000 middle -1"
+    assert lines[1] == "push 1 ready 1 frames 2 tracked 1002 1000 1101 middle 11"       # group (10, 11): middle = the second frame
+    assert lines[2] == "push 2 ready 0 frames 1 tracked middle -1"                        # a new group starts; frame 12 tracked nothing
+    assert lines[3] == "push 3 ready 1 frames 2 tracked 1303 1301 1300 middle 13"
+    assert lines[4] == "push 4 ready 0 frames 1 tracked 1400 middle -1"
+    assert lines[5] == "times 0.005000 0.001250 0.002500 0.000625 frames 5"
+    assert lines[6] == "single 1 middle 7"
